@@ -1,0 +1,126 @@
+/*
+ * latticenet_b200.h -- C ABI of libltn_b200.so, the sm_100a implementation of the permutohedral
+ * lattice hot path under Temporal LatticeNet.
+ *
+ * What it replaces.  The reference has no FFI of its own for this path: it imports a pybind11
+ * module, `latticenet` (C++/CUDA, github.com/peerschuett/lattice_net, un-vendored -- reference
+ * README.md:47-48), and the Python package `latticenet_py` built on it.  Each entry point below
+ * cites the reference call site whose work it performs; the Python binding that presents these
+ * entry points under the reference's names lives in temporal_latticenet_b200/ (see INTEGRATION.md).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch tensors); the library allocates
+ *    nothing persistent and frees nothing;  `stream` is a cudaStream_t passed as void*;
+ *  - return value: 0 on success, a cudaError_t (>0) from the launch, or <0 for an argument the
+ *    kernels do not support (-2 shape, -3 shared memory);
+ *  - no exceptions, no host synchronisation inside any call;
+ *  - pos_dim is 3 (4 simplex vertices per point, filter extent 9: lattice_modules.py:299,310-311);
+ *  - rows are point-major: row = point*4 + r (models.py:452); indices are int32, -1 = absent.
+ *
+ * Hash-table storage (all allocated by the caller, `nslots` a power of two >= 2*capacity):
+ *    slot_keys  uint64[nslots]  packed key (3 x 21 bit), all-ones = empty
+ *    slot_ids   int32 [nslots]  vertex id of the slot, -1 until numbered
+ *    slot_first int32 [nslots]  scratch: smallest row that touched a new slot in this batch
+ *    keys       int32 [capacity,4]  key of vertex id (x,y,z,-(x+y+z))
+ *    counters   int32 [8]       [0] vertices, [1] vertices before the last batch,
+ *                               [2] dropped on overflow, [3] keys out of the packable range
+ */
+#ifndef LATTICENET_B200_H
+#define LATTICENET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- lattice structure (latticenet.Lattice / HashTable: train_ln.py:106,239;
+ *      lattice_modules.py:7-8) ------------------------------------------------------------- */
+
+/* HashTable::clear -- begin a new sequence (models.py:287-289, reset_hashmap=True) */
+int ltn_hash_clear(uint64_t* slot_keys, int* slot_ids, int* slot_first, int nslots, int* counters, void* stream);
+
+/* Insert the 4 enclosing-simplex vertices of N points (scale s = inv_std_dev/(sigma*sqrt((i+1)(i+2))))
+ * and number NEW vertices in order of first appearance (append-only ids).  Used for the coarse
+ * lattices of GnReluCoarsen (models.py:182,353).  row_slot [4N] and block_sums [ceil(4N/1024)+1]
+ * are scratch; row_w [4N] (nullable) receives the barycentric weights. */
+int ltn_insert_points(const float* pos, int N, float sx, float sy, float sz, uint64_t* slot_keys, int* slot_ids,
+                      int* slot_first, int nslots, int* counters, int* keys, int capacity, int* row_slot,
+                      float* row_w, int* block_sums, void* stream);
+
+/* DistributeLatticeModule.forward (models.py:62,297-298): rows [4N, 3+val_dim+1] = [xyz, val, bary],
+ * idx [4N], w [4N]; subtract_mean != 0 also subtracts the per-vertex mean position from rows[:,0:3].
+ * vert_acc [capacity,4] double scratch; afterwards vert_acc[v,3] = number of rows on vertex v. */
+int ltn_distribute(const float* pos, const float* val, int N, int val_dim, float sx, float sy, float sz,
+                   uint64_t* slot_keys, int* slot_ids, int* slot_first, int nslots, int* counters, int* keys,
+                   int capacity, int* row_slot, int* block_sums, double* vert_acc, float* rows, int* idx, float* w,
+                   int subtract_mean, void* stream);
+
+/* rows-per-vertex as float [V] (lattice_modules.py:519-521, scatter_add of ones) */
+int ltn_vertex_counts(const double* vert_acc, int V, float* counts, void* stream);
+
+/* Neighbour table [Vq,9] (slot 2a = +o_a, 2a+1 = -o_a, 8 = centre; -1 absent).  mode 0: same level
+ * (ConvLatticeModule / Im2RowLattice / Im2RowIndicesLattice, lattice_modules.py:301,304,440,573);
+ * mode 1: query coarse, table fine (CoarsenLattice, models.py:353); mode 2: query fine, table
+ * coarse (FinefyLattice, models.py:398).  vq_dev (nullable): device-side vertex count. */
+int ltn_neighbours(const int* keys_q, int Vq, const int* vq_dev, const uint64_t* slot_keys, const int* slot_ids,
+                   int nslots, int mode, int dilation, int same_table, int* out, void* stream);
+
+/* ---- gathers / scatters ---------------------------------------------------------------------- */
+
+/* Im2RowLattice.apply (lattice_modules.py:301): out [Vq, 9*C], zeros where absent. C % 4 == 0 */
+int ltn_im2row(const float* vals, int Vvals, const int* vvals_dev, const int* nbr, int Vq, const int* vq_dev, int C,
+               float* out, void* stream);
+/* backward of im2row as a gather through the opposite-direction table nbrT [Vu,9] */
+int ltn_row2im(const float* grad_rows, int Vrows, const int* nbrT, int Vu, int C, float* grad_vals, void* stream);
+
+/* SplatLatticeModule (models.py:234): out [V, C+1] += w*[val,1]; caller zeroes out */
+int ltn_splat(const float* val, int N, int C, const int* idx, const float* w, float* out, int V, void* stream);
+/* SliceLatticeModule (models.py:233): out [N,C] = sum_r w*vals[idx]. C % 4 == 0 */
+int ltn_slice(const float* vals, int V, int C, const int* idx, const float* w, int N, float* out, void* stream);
+int ltn_slice_bwd(const float* grad_out, int N, int C, const int* idx, const float* w, float* grad_vals, int V,
+                  void* stream);
+/* GatherLattice inside SliceFastCUDALatticeModule (models.py:232,465): out [N, 4*(C+1)] */
+int ltn_gather(const float* vals, int V, int C, const int* idx, const float* w, int N, float* out, void* stream);
+int ltn_gather_bwd(const float* grad_out, int N, int C, const int* idx, const float* w, float* grad_vals, int V,
+                   void* stream);
+/* SliceClassifyLattice (models.py:465): out [N,K]; sliced [N,C] (nullable) saved for the weight grad */
+int ltn_slice_classify(const float* vals, int V, int C, const int* idx, const float* w, const float* dw, int N,
+                       const float* Wc, const float* bias, int K, float* out, float* sliced, void* stream);
+int ltn_slice_classify_bwd(const float* grad_logit, const float* vals, int V, int C, const int* idx, const float* w,
+                           const float* dw, int N, const float* Wc, int K, float* grad_vals, float* grad_dw,
+                           void* stream);
+
+/* ---- segmented reductions, normalisation ------------------------------------------------------ */
+
+/* torch_scatter.scatter_max(src[R,C], idx[R], dim=0) (lattice_modules.py:512): packed [V,C] u64 scratch */
+int ltn_scatter_max(const float* src, const int* idx, int R, int C, int V, unsigned long long* packed, float* out,
+                    long long* arg, void* stream);
+/* torch_scatter.scatter_add (lattice_modules.py:497,502,520); out pre-zeroed */
+int ltn_scatter_add(const float* src, const int* idx, int R, int C, float* out, int V, void* stream);
+/* GroupNorm over [1,C,V] (Gn / GnRelu1x1 / GnReluConv, lattice_modules.py:75,100,436-437): sums [G,2] double */
+int ltn_gn_stats(const float* x, int V, const int* v_dev, int C, int G, double* sums, void* stream);
+int ltn_gn_apply(const float* x, int V, const int* v_dev, int C, int G, const double* sums, const float* gamma,
+                 const float* beta, float eps, int relu, float* y, void* stream);
+
+/* ---- temporal fusion (seq_lattice/lattice_modules.py:17-339) ------------------------------------ */
+
+/* GRUModule.forward pointwise stage (lattice_modules.py:58-63); rows >= Vh are the zero padding */
+int ltn_gru_pointwise(const float* gi, const float* gh, const float* h, const float* b_hh, int V, int Vh, int C,
+                      float* out, void* stream);
+/* LSTMModule.forward pointwise stage with c_prev = 0 (lattice_modules.py:32-37) */
+int ltn_lstm_pointwise(const float* gi, const float* gh, const float* b_hh, int V, int Vh, int C, float* out,
+                       void* stream);
+/* CustomKernelConvLatticeIm2RowModule.forward (lattice_modules.py:282-339) fused:
+ * out [V,C], weights_out [V,9] (nullable) */
+int ltn_aflow(const float* lv, const float* h, int V, int Vh, int C, const int* nbr, const float* alpha,
+              const float* beta, const float* bias, float pad_value, int use_center, float* out, float* weights_out,
+              void* stream);
+
+/* library version / build info */
+int ltn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

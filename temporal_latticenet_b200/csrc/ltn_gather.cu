@@ -1,0 +1,346 @@
+// Bandwidth-bound gather / scatter kernels over the lattice: im2row (+ its transpose), splat, slice,
+// gather, slice_classify and their backward passes.  sm_100a; 128-bit vectorised row accesses.
+//
+// Neighbour tables ([V,9] int32, -1 = absent) are built once per lattice state by ltn_neighbours and
+// shared by every convolution on that level, so none of these kernels touches the hash table.
+#include "ltn_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// out[v, s*C + c] = vals[nbr[v,s], c] ; one thread per float4.  C % 4 == 0.
+__global__ void __launch_bounds__(kThreads)
+k_im2row(const float* __restrict__ vals, int Vvals, const int* __restrict__ vvals_dev, const int* __restrict__ nbr,
+         int Vq, const int* __restrict__ vq_dev, int C4, float4* __restrict__ out) {
+    if (vq_dev) Vq = min(Vq, *vq_dev);
+    if (vvals_dev) Vvals = min(Vvals, *vvals_dev);
+    long long total = (long long)Vq * LTN_FEXT * C4;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        long long vs = t / C4;
+        int c4 = (int)(t - vs * C4);
+        int id = __ldg(nbr + vs);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (id >= 0 && id < Vvals) x = ld4(vals + ((size_t)id * C4 + c4) * 4);
+        out[t] = x;
+    }
+}
+
+// transpose of im2row as a GATHER (no atomics): grad_vals[u, c] = sum_s grad_rows[nbrT[u, s^1], s*C + c]
+// (+ centre slot 8 -> nbrT[u, 8]).  nbrT is the table of the opposite direction: the same table for a
+// same-level convolution (neighbour relation is symmetric with the slot pair swapped), the finefy
+// table for coarsen and the coarsen table for finefy.  Vrows = number of rows of grad_rows.
+__global__ void __launch_bounds__(kThreads)
+k_row2im(const float* __restrict__ grad_rows, int Vrows, const int* __restrict__ nbrT, int Vu, int C4,
+         float4* __restrict__ grad_vals) {
+    long long total = (long long)Vu * C4;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int u = (int)(t / C4);
+        int c4 = (int)(t - (long long)u * C4);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < LTN_FEXT; ++s) {
+            int st = (s < 2 * LTN_D1) ? (s ^ 1) : s;
+            int v = __ldg(nbrT + (size_t)u * LTN_FEXT + st);
+            if (v >= 0 && v < Vrows) {
+                float4 g = ld4(grad_rows + (((size_t)v * LTN_FEXT + s) * C4 + c4) * 4);
+                acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+            }
+        }
+        grad_vals[t] = acc;
+    }
+}
+
+// splat: out[idx, 0:C] += w * val[p] ; out[idx, C] += w.   One warp per point, lanes over channels.
+__global__ void __launch_bounds__(kThreads)
+k_splat(const float* __restrict__ val, int N, int C, const int* __restrict__ idx, const float* __restrict__ w,
+        float* out, int V) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= N) return;
+    int4 i4 = __ldg(reinterpret_cast<const int4*>(idx) + warp);
+    float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + warp);
+    int ids[4] = {i4.x, i4.y, i4.z, i4.w};
+    float ws[4] = {w4.x, w4.y, w4.z, w4.w};
+    for (int c = lane; c <= C; c += 32) {
+        float x = (c < C) ? __ldg(val + (size_t)warp * C + c) : 1.0f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (ids[r] >= 0 && ids[r] < V) atomicAdd(out + (size_t)ids[r] * (C + 1) + c, ws[r] * x);
+    }
+}
+
+// slice: out[p, :] = sum_r w[p,r] * vals[idx[p,r], :]   (r in order 0..3).  C % 4 == 0.
+__global__ void __launch_bounds__(kThreads)
+k_slice(const float* __restrict__ vals, int V, int C4, const int* __restrict__ idx, const float* __restrict__ w, int N,
+        float4* __restrict__ out) {
+    long long total = (long long)N * C4;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int p = (int)(t / C4);
+        int c4 = (int)(t - (long long)p * C4);
+        int4 i4 = __ldg(reinterpret_cast<const int4*>(idx) + p);
+        float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + p);
+        int ids[4] = {i4.x, i4.y, i4.z, i4.w};
+        float ws[4] = {w4.x, w4.y, w4.z, w4.w};
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (ids[r] >= 0 && ids[r] < V) {
+                float4 x = ld4(vals + ((size_t)ids[r] * C4 + c4) * 4);
+                acc.x = fmaf(ws[r], x.x, acc.x); acc.y = fmaf(ws[r], x.y, acc.y);
+                acc.z = fmaf(ws[r], x.z, acc.z); acc.w = fmaf(ws[r], x.w, acc.w);
+            }
+        out[t] = acc;
+    }
+}
+
+// slice backward wrt vals: grad_vals[idx[p,r], :] += w[p,r] * grad_out[p, :]  (atomics)
+__global__ void __launch_bounds__(kThreads)
+k_slice_bwd(const float* __restrict__ grad_out, int N, int C, const int* __restrict__ idx,
+            const float* __restrict__ w, float* grad_vals, int V) {
+    long long total = (long long)N * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int p = (int)(t / C);
+        int c = (int)(t - (long long)p * C);
+        float g = __ldg(grad_out + t);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int id = __ldg(idx + (size_t)p * 4 + r);
+            if (id >= 0 && id < V) atomicAdd(grad_vals + (size_t)id * C + c, __ldg(w + (size_t)p * 4 + r) * g);
+        }
+    }
+}
+
+// gather: out[p, r*(C+1) + c] = w*vals[id, c] ; out[p, r*(C+1) + C] = w ; absent -> zeros (conv. U6)
+__global__ void __launch_bounds__(kThreads)
+k_gather(const float* __restrict__ vals, int V, int C, const int* __restrict__ idx, const float* __restrict__ w, int N,
+         float* __restrict__ out) {
+    const int W1 = C + 1;
+    long long total = (long long)N * 4 * W1;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        long long row = t / W1;
+        int c = (int)(t - row * W1);
+        int id = __ldg(idx + row);
+        float r = 0.f;
+        if (id >= 0 && id < V) {
+            float ww = __ldg(w + row);
+            r = (c < C) ? __fmul_rn(ww, __ldg(vals + (size_t)id * C + c)) : ww;
+        }
+        out[t] = r;
+    }
+}
+
+// gather backward wrt vals: grad_vals[id, c] += w * grad_out[p, r*(C+1)+c]
+__global__ void __launch_bounds__(kThreads)
+k_gather_bwd(const float* __restrict__ grad_out, int N, int C, const int* __restrict__ idx,
+             const float* __restrict__ w, float* grad_vals, int V) {
+    const int W1 = C + 1;
+    long long total = (long long)N * 4 * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        long long row = t / C;
+        int c = (int)(t - row * C);
+        int id = __ldg(idx + row);
+        if (id >= 0 && id < V) atomicAdd(grad_vals + (size_t)id * C + c, __ldg(w + row) * __ldg(grad_out + row * W1 + c));
+    }
+}
+
+// slice_classify forward: one warp per point.
+//   s[c]      = sum_r (w+dw)[p,r] * vals[id_r, c]
+//   logit[k]  = b[k] + sum_c Wc[k,c] * s[c]
+// Wc (K x C) is staged in shared memory once per block.
+__global__ void __launch_bounds__(kThreads)
+k_slice_classify(const float* __restrict__ vals, int V, int C, const int* __restrict__ idx,
+                 const float* __restrict__ w, const float* __restrict__ dw, int N, const float* __restrict__ Wc,
+                 const float* __restrict__ bias, int K, float* __restrict__ out, float* __restrict__ sliced) {
+    extern __shared__ float sW[];  // K*C
+    for (int i = threadIdx.x; i < K * C; i += blockDim.x) sW[i] = __ldg(Wc + i);
+    __syncthreads();
+    int lane = threadIdx.x & 31;
+    int warps_per_block = blockDim.x >> 5;
+    for (int p = blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < N; p += gridDim.x * warps_per_block) {
+        int4 i4 = __ldg(reinterpret_cast<const int4*>(idx) + p);
+        float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + p);
+        float4 d4 = __ldg(reinterpret_cast<const float4*>(dw) + p);
+        int ids[4] = {i4.x, i4.y, i4.z, i4.w};
+        float ws[4] = {w4.x + d4.x, w4.y + d4.y, w4.z + d4.z, w4.w + d4.w};
+        // channel sums for this lane's channels (C <= 256 -> at most 8 per lane), gathered once
+        float sc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int c = lane + 32 * j;
+            float s = 0.f;
+            if (c < C) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (ids[r] >= 0 && ids[r] < V) s = fmaf(ws[r], __ldg(vals + (size_t)ids[r] * C + c), s);
+                if (sliced) sliced[(size_t)p * C + c] = s;
+            }
+            sc[j] = s;
+        }
+        for (int k = 0; k < K; ++k) {
+            float v = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int c = lane + 32 * j;
+                if (c < C) v = fmaf(sW[k * C + c], sc[j], v);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) out[(size_t)p * K + k] = v + __ldg(bias + k);
+        }
+    }
+}
+
+// slice_classify backward.  Given grad_logit [N,K]:
+//   gs[c]          = sum_k grad_logit[p,k] * Wc[k,c]
+//   grad_dw[p,r]   = sum_c gs[c] * vals[id_r, c]
+//   grad_vals[id_r, c] += (w+dw)[p,r] * gs[c]                       (atomics)
+// grad_Wc = grad_logit^T @ sliced and grad_b = column sums are done with a GEMM / reduction on the
+// host side from the `sliced` tensor saved by the forward.
+__global__ void __launch_bounds__(kThreads)
+k_slice_classify_bwd(const float* __restrict__ grad_logit, const float* __restrict__ vals, int V, int C,
+                     const int* __restrict__ idx, const float* __restrict__ w, const float* __restrict__ dw, int N,
+                     const float* __restrict__ Wc, int K, float* grad_vals, float* __restrict__ grad_dw) {
+    extern __shared__ float sW[];
+    for (int i = threadIdx.x; i < K * C; i += blockDim.x) sW[i] = __ldg(Wc + i);
+    __syncthreads();
+    int lane = threadIdx.x & 31;
+    int warps_per_block = blockDim.x >> 5;
+    for (int p = blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < N; p += gridDim.x * warps_per_block) {
+        int4 i4 = __ldg(reinterpret_cast<const int4*>(idx) + p);
+        float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + p);
+        float4 d4 = __ldg(reinterpret_cast<const float4*>(dw) + p);
+        int ids[4] = {i4.x, i4.y, i4.z, i4.w};
+        float ws[4] = {w4.x + d4.x, w4.y + d4.y, w4.z + d4.z, w4.w + d4.w};
+        float gd[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = lane; c < C; c += 32) {
+            float gs = 0.f;
+            for (int k = 0; k < K; ++k) gs = fmaf(__ldg(grad_logit + (size_t)p * K + k), sW[k * C + c], gs);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (ids[r] >= 0 && ids[r] < V) {
+                    gd[r] = fmaf(gs, __ldg(vals + (size_t)ids[r] * C + c), gd[r]);
+                    atomicAdd(grad_vals + (size_t)ids[r] * C + c, ws[r] * gs);
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float v = gd[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) grad_dw[(size_t)p * 4 + r] = v;
+        }
+    }
+}
+
+inline int grid_for(long long work_items, int threads) {
+    long long b = (work_items + threads - 1) / threads;
+    const long long cap = 148LL * 32;  // persistent-ish: a few waves of 148 SMs, grid-stride inside
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+extern "C" {
+
+int ltn_im2row(const float* vals, int Vvals, const int* vvals_dev, const int* nbr, int Vq, const int* vq_dev, int C,
+               float* out, void* stream) {
+    if (Vq <= 0 || C <= 0) return 0;
+    if (C % 4) return -2;
+    long long total = (long long)Vq * LTN_FEXT * (C / 4);
+    k_im2row<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(vals, Vvals, vvals_dev, nbr, Vq, vq_dev,
+                                                                              C / 4, reinterpret_cast<float4*>(out));
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+int ltn_row2im(const float* grad_rows, int Vrows, const int* nbrT, int Vu, int C, float* grad_vals, void* stream) {
+    if (Vu <= 0 || C <= 0) return 0;
+    if (C % 4) return -2;
+    long long total = (long long)Vu * (C / 4);
+    k_row2im<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(grad_rows, Vrows, nbrT, Vu, C / 4,
+                                                                              reinterpret_cast<float4*>(grad_vals));
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+// out [V, C+1] must be zeroed by the caller
+int ltn_splat(const float* val, int N, int C, const int* idx, const float* w, float* out, int V, void* stream) {
+    if (N <= 0) return 0;
+    k_splat<<<ltn_blocks((long long)N * 32, kThreads), kThreads, 0, (cudaStream_t)stream>>>(val, N, C, idx, w, out, V);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+int ltn_slice(const float* vals, int V, int C, const int* idx, const float* w, int N, float* out, void* stream) {
+    if (N <= 0 || C <= 0) return 0;
+    if (C % 4) return -2;
+    long long total = (long long)N * (C / 4);
+    k_slice<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(vals, V, C / 4, idx, w, N,
+                                                                             reinterpret_cast<float4*>(out));
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+// grad_vals [V,C] must be zeroed by the caller
+int ltn_slice_bwd(const float* grad_out, int N, int C, const int* idx, const float* w, float* grad_vals, int V,
+                  void* stream) {
+    if (N <= 0 || C <= 0) return 0;
+    k_slice_bwd<<<grid_for((long long)N * C, kThreads), kThreads, 0, (cudaStream_t)stream>>>(grad_out, N, C, idx, w,
+                                                                                            grad_vals, V);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+int ltn_gather(const float* vals, int V, int C, const int* idx, const float* w, int N, float* out, void* stream) {
+    if (N <= 0) return 0;
+    long long total = (long long)N * 4 * (C + 1);
+    k_gather<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(vals, V, C, idx, w, N, out);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+// grad_vals [V,C] must be zeroed by the caller
+int ltn_gather_bwd(const float* grad_out, int N, int C, const int* idx, const float* w, float* grad_vals, int V,
+                   void* stream) {
+    if (N <= 0) return 0;
+    k_gather_bwd<<<grid_for((long long)N * 4 * C, kThreads), kThreads, 0, (cudaStream_t)stream>>>(grad_out, N, C, idx,
+                                                                                                 w, grad_vals, V);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+// sliced (nullable): [N,C] = sum_r (w+dw) vals[id_r] saved for the weight gradient
+int ltn_slice_classify(const float* vals, int V, int C, const int* idx, const float* w, const float* dw, int N,
+                       const float* Wc, const float* bias, int K, float* out, float* sliced, void* stream) {
+    if (N <= 0) return 0;
+    size_t smem = sizeof(float) * (size_t)K * C;
+    if (smem > 200 * 1024 || C > 256) return -3;
+    cudaError_t e = cudaFuncSetAttribute(k_slice_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int blocks = (int)((N + 7) / 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_slice_classify<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(vals, V, C, idx, w, dw, N, Wc, bias, K, out, sliced);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+// grad_vals [V,C] must be zeroed by the caller; grad_dw [N,4] is fully written
+int ltn_slice_classify_bwd(const float* grad_logit, const float* vals, int V, int C, const int* idx, const float* w,
+                           const float* dw, int N, const float* Wc, int K, float* grad_vals, float* grad_dw,
+                           void* stream) {
+    if (N <= 0) return 0;
+    size_t smem = sizeof(float) * (size_t)K * C;
+    if (smem > 200 * 1024) return -3;
+    cudaError_t e = cudaFuncSetAttribute(k_slice_classify_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int blocks = (int)((N + 7) / 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_slice_classify_bwd<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(grad_logit, vals, V, C, idx, w, dw, N, Wc, K,
+                                                                           grad_vals, grad_dw);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

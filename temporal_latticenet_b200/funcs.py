@@ -1,0 +1,242 @@
+"""Autograd Functions over the C ABI -- the `latticenet_py.lattice.lattice_funcs` surface
+(/root/reference/seq_lattice/lattice_modules.py:14,301,304; models.py:6).
+
+Forward and backward both run hand-written sm_100a kernels; dense contractions go through
+`ops.matmul` (fp32).  No CPU fallback.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from . import ops
+
+FEXT = 9
+
+
+def _f32c(t):
+    return t.contiguous().float()
+
+
+# ---------------------------------------------------------------------------------------------
+# raw kernels
+# ---------------------------------------------------------------------------------------------
+def im2row_raw(values, nbr, nr_rows=None):
+    values = _f32c(values)
+    vq = nbr.shape[0] if nr_rows is None else nr_rows
+    C = values.shape[1]
+    out = torch.empty(vq, FEXT * C, dtype=torch.float32, device=values.device)
+    p = _lib.ptr
+    _lib.check(_lib.load().ltn_im2row(p(values), values.shape[0], None, p(nbr), vq, None, C, p(out), _lib.stream()),
+               "ltn_im2row")
+    return out
+
+
+def row2im_raw(grad_rows, nbr_t, nr_vals, C):
+    grad_rows = _f32c(grad_rows)
+    out = torch.zeros(nr_vals, C, dtype=torch.float32, device=grad_rows.device)
+    vu = min(nr_vals, nbr_t.shape[0])
+    p = _lib.ptr
+    _lib.check(_lib.load().ltn_row2im(p(grad_rows), grad_rows.shape[0], p(nbr_t), vu, C, p(out), _lib.stream()),
+               "ltn_row2im")
+    return out
+
+
+class _GatherConv(Function):
+    """out = im2row(values, nbr) @ weight.  nbr_t is the opposite-direction table used to run the
+    transpose as a gather (see csrc/ltn_gather.cu::k_row2im).  The [V,9C] buffer is not kept for
+    backward; it is rebuilt (bandwidth is cheaper than holding 200 MB per conv alive)."""
+
+    @staticmethod
+    def forward(ctx, values, weight, nbr, nbr_t):
+        rows = im2row_raw(values, nbr)
+        out = ops.matmul(rows, weight)
+        ctx.save_for_backward(values, weight, nbr, nbr_t)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        values, weight, nbr, nbr_t = ctx.saved_tensors
+        grad_out = _f32c(grad_out)
+        gv = gw = None
+        if ctx.needs_input_grad[0]:
+            grad_rows = ops.matmul(grad_out, weight.t())
+            gv = row2im_raw(grad_rows, nbr_t, values.shape[0], values.shape[1])
+        if ctx.needs_input_grad[1]:
+            rows = im2row_raw(values, nbr)
+            gw = ops.matmul(rows.t(), grad_out)
+        return gv, gw, None, None
+
+
+def gather_conv(values, weight, nbr, nbr_t_fn):
+    """nbr_t_fn() builds the opposite-direction table; it is only evaluated when a gradient with
+    respect to `values` can be asked for."""
+    needs = torch.is_grad_enabled() and values.requires_grad
+    nbr_t = nbr_t_fn() if needs else nbr
+    return _GatherConv.apply(values, weight, nbr, nbr_t)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference-named Functions
+# ---------------------------------------------------------------------------------------------
+class Im2RowLattice(Function):
+    """[V, 9*C] neighbour rows, slot 8 = centre, zeros where absent (lattice_modules.py:301,316)."""
+
+    @staticmethod
+    def forward(ctx, values, ls, filter_extent, dilation, nr_filters):
+        if filter_extent != FEXT:
+            raise RuntimeError("filter_extent must be 9")
+        nbr = ls.neighbours(dilation=dilation)
+        ctx.save_for_backward(nbr)
+        ctx.shape = tuple(values.shape)
+        return im2row_raw(values, nbr)
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        (nbr,) = ctx.saved_tensors
+        return row2im_raw(grad_rows, nbr, ctx.shape[0], ctx.shape[1]), None, None, None, None
+
+
+class Im2RowIndicesLattice(Function):
+    """[V, 9*nr_filters] int32: neighbour id replicated nr_filters times (the reference strides it
+    with [:, ::nr_filters], lattice_modules.py:318,325,339); -1 absent; centre = own id (U5)."""
+
+    @staticmethod
+    def forward(ctx, values, ls, filter_extent, dilation, nr_filters):
+        nbr = ls.neighbours(dilation=dilation)
+        return nbr.repeat_interleave(int(nr_filters), dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, None, None, None, None
+
+
+class ConvIm2RowLattice:
+    @staticmethod
+    def apply(values, ls, weight, dilation):
+        nbr = ls.neighbours(dilation=dilation)
+        return gather_conv(values, weight, nbr, lambda: nbr)
+
+
+class CoarsenLattice:
+    @staticmethod
+    def apply(values_fine, ls_fine, weight):
+        coarse = ls_fine.create_coarse_verts()
+        nbr = coarse.neighbours(ls_fine, mode=1)
+        return gather_conv(values_fine, weight, nbr, lambda: ls_fine.neighbours(coarse, mode=2)), coarse
+
+
+class FinefyLattice:
+    @staticmethod
+    def apply(values_coarse, ls_coarse, ls_fine, weight):
+        nbr = ls_fine.neighbours(ls_coarse, mode=2)
+        return gather_conv(values_coarse, weight, nbr, lambda: ls_coarse.neighbours(ls_fine, mode=1))
+
+
+class DistributeLattice:
+    @staticmethod
+    def apply(ls, positions, values, reset_hashmap=True, subtract_mean=True):
+        with torch.no_grad():
+            return ls.distribute(positions, values, reset_hashmap, subtract_mean)
+
+
+class GatherLattice(Function):
+    """[N, 4*(C+1)]: per simplex vertex [w*v, w] (convention U6)."""
+
+    @staticmethod
+    def forward(ctx, values, ls, positions, indices, weights):
+        values = _f32c(values)
+        n, C = positions.shape[0], values.shape[1]
+        out = torch.empty(n, 4 * (C + 1), dtype=torch.float32, device=values.device)
+        p = _lib.ptr
+        _lib.check(_lib.load().ltn_gather(p(values), values.shape[0], C, p(indices), p(weights), n, p(out), _lib.stream()),
+                   "ltn_gather")
+        ctx.save_for_backward(indices, weights)
+        ctx.shape = tuple(values.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        indices, weights = ctx.saved_tensors
+        V, C = ctx.shape
+        g = _f32c(g)
+        gv = torch.zeros(V, C, dtype=torch.float32, device=g.device)
+        p = _lib.ptr
+        _lib.check(_lib.load().ltn_gather_bwd(p(g), g.shape[0], C, p(indices), p(weights), p(gv), V, _lib.stream()),
+                   "ltn_gather_bwd")
+        return gv, None, None, None, None
+
+
+class SliceLattice(Function):
+    @staticmethod
+    def forward(ctx, values, ls, positions, indices, weights):
+        values = _f32c(values)
+        n, C = positions.shape[0], values.shape[1]
+        out = torch.empty(n, C, dtype=torch.float32, device=values.device)
+        p = _lib.ptr
+        _lib.check(_lib.load().ltn_slice(p(values), values.shape[0], C, p(indices), p(weights), n, p(out), _lib.stream()),
+                   "ltn_slice")
+        ctx.save_for_backward(indices, weights)
+        ctx.shape = tuple(values.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        indices, weights = ctx.saved_tensors
+        V, C = ctx.shape
+        g = _f32c(g)
+        gv = torch.zeros(V, C, dtype=torch.float32, device=g.device)
+        p = _lib.ptr
+        _lib.check(_lib.load().ltn_slice_bwd(p(g), g.shape[0], C, p(indices), p(weights), p(gv), V, _lib.stream()),
+                   "ltn_slice_bwd")
+        return gv, None, None, None, None
+
+
+class SliceClassifyLattice(Function):
+    """logit[p,k] = b[k] + sum_c W[k,c] * sum_r (w+dw)[p,r] * lv[idx[p,r], c]  (models.py:465)."""
+
+    @staticmethod
+    def forward(ctx, values, ls, positions, delta_weights, linear_weight, linear_bias, nr_classes, indices, weights):
+        values, dw = _f32c(values), _f32c(delta_weights)
+        W, b = _f32c(linear_weight), _f32c(linear_bias)
+        n, C, K = positions.shape[0], values.shape[1], W.shape[0]
+        out = torch.empty(n, K, dtype=torch.float32, device=values.device)
+        need_grad = any(ctx.needs_input_grad)
+        sliced = torch.empty(n, C, dtype=torch.float32, device=values.device) if need_grad else None
+        p = _lib.ptr
+        _lib.check(_lib.load().ltn_slice_classify(p(values), values.shape[0], C, p(indices), p(weights), p(dw), n, p(W),
+                                                  p(b), K, p(out), p(sliced), _lib.stream()), "ltn_slice_classify")
+        if need_grad:
+            ctx.save_for_backward(values, dw, W, indices, weights, sliced)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        values, dw, W, indices, weights, sliced = ctx.saved_tensors
+        g = _f32c(g)
+        V, C = values.shape
+        n, K = g.shape
+        gv = torch.zeros(V, C, dtype=torch.float32, device=g.device)
+        gdw = torch.empty(n, 4, dtype=torch.float32, device=g.device)
+        p = _lib.ptr
+        _lib.check(_lib.load().ltn_slice_classify_bwd(p(g), p(values), V, C, p(indices), p(weights), p(dw), n, p(W), K,
+                                                      p(gv), p(gdw), _lib.stream()), "ltn_slice_classify_bwd")
+        gW = ops.matmul(g.t(), sliced)
+        gb = g.sum(0)
+        return gv, None, None, gdw, gW, gb, None, None, None
+
+
+class SplatLattice:
+    """values[idx] += w*[val, 1] (homogeneous coordinate last); returns (lv [V,C+1], idx, w)."""
+
+    @staticmethod
+    def apply(ls, positions, values):
+        with torch.no_grad():
+            values = _f32c(values)
+            zeros = torch.zeros(positions.shape[0], 1, dtype=torch.float32, device=positions.device)
+            _, idx, w = ls.distribute(positions, zeros, True, False)
+            V = ls.nr_lattice_vertices()
+            out = torch.zeros(V, values.shape[1] + 1, dtype=torch.float32, device=values.device)
+            p = _lib.ptr
+            _lib.check(_lib.load().ltn_splat(p(values), values.shape[0], values.shape[1], p(idx), p(w), p(out), V,
+                                             _lib.stream()), "ltn_splat")
+            return out, idx, w

@@ -1,0 +1,229 @@
+"""Window executor: the LatticeNet U-Net over lattice levels sigma, 2 sigma, 4 sigma with temporal
+fusion at four depths -- the computation /root/reference/seq_lattice/models.py::LNN_SEQ performs,
+laid out as a flat list of stages built once from the cfg.
+
+It takes the same constructor arguments and `forward(ls, positions, values, early_return,
+with_gradient)` contract as LNN_SEQ (models.py:16,284), returns the same triples at the same
+early-return points (models.py:307-309,346-349,427-430,474-476), creates its parameters lazily in
+the same places and under the same names, so a state-dict produced by either loads into the other
+(tests/test_golden_gpu.py loads the reference-generated shapes).  Reference quirks Q1, Q3, Q7, Q8
+ are reproduced and marked below.
+
+The reference file itself cannot travel to the GPU box, which is why this executor exists; where
+/root/reference is mounted the unmodified models.py runs over the same modules through
+temporal_latticenet_b200/shims.
+"""
+import torch
+
+from . import ops
+from .fusion import FUSION_TYPES, make_fusion
+from .modules import (BottleneckBlock, ConvLatticeModule, DistributeLatticeModule, GnReluCoarsen, GnReluFinefy,
+                      ResnetBlock, SliceFastCUDALatticeModule, SliceLatticeModule, SplatLatticeModule)
+
+_EXPERIMENTS = ("none", "slice_no_deform", "pointnet_no_elevate", "pointnet_no_local_mean",
+                "pointnet_no_elevate_no_local_mean", "splat", "attention_pool")
+_MIN_POINTS_PER_VERTEX = 4  # lattice_modules.py:528
+
+
+class PointNetSeq(torch.nn.Module):
+    """Per-(point, vertex) MLP, max over the rows of each vertex, barycentric weights of the winning
+    rows, early fusion, last_conv (lattice_modules.py:343-576).  State-dict keys: layers.N.*,
+    fusion_module.*, last_conv.weight."""
+
+    def __init__(self, layer_widths, nr_outputs_last_layer, experiment, rnn_modules, sequence_learning):
+        super().__init__()
+        if experiment in ("attention_pool", "splat", "pointnet_no_elevate", "pointnet_no_elevate_no_local_mean"):
+            raise RuntimeError("experiment %r is not part of the hot path built here" % experiment)
+        self.layer_widths = list(layer_widths)
+        self.layers = torch.nn.ModuleList([])
+        self.sequence_learning = sequence_learning
+        self.fusion_kind = rnn_modules[0] if sequence_learning else "none"
+        self.fusion_module = make_fusion(self.fusion_kind, self.layer_widths[-1] * 2)
+        self.last_conv = None
+        self.nr_outputs_last_layer = nr_outputs_last_layer
+
+    def reset_sequence(self):
+        if self.fusion_module is not None:
+            self.fusion_module.reset_sequence()
+
+    def _create(self, nr_in, device):
+        for width in self.layer_widths:
+            lin = torch.nn.Linear(nr_in, width, bias=True).to(device)
+            with torch.no_grad():
+                torch.nn.init.kaiming_normal_(lin.weight, mode="fan_in", nonlinearity="relu")
+            self.layers.append(lin)
+            nr_in = width
+        self.last_conv = ConvLatticeModule(nr_filters=self.nr_outputs_last_layer, neighbourhood_size=1, dilation=1, bias=False)
+
+    def forward(self, ls, distributed, indices):
+        if self.last_conv is None:
+            self._create(distributed.shape[1] - 1, distributed.device)
+        bary = distributed[:, -1]
+        x = distributed[:, :-1]
+        for i, lin in enumerate(self.layers):
+            x = ops.linear(x, lin.weight, lin.bias)
+            if i < len(self.layers) - 1:
+                x = torch.relu(x)
+        V = ls.nr_lattice_vertices()
+        R = x.shape[0]
+        # ids < 0 (overflow) fold onto row 0 inside the kernel (lattice_modules.py:479-480)
+        red, argmax = ops.scatter_max(x, indices, dim_size=V)
+        # Q3, literally: row indices are compared with the NUMBER OF VERTICES (lattice_modules.py:513-514)
+        arg = torch.where(argmax > V, torch.zeros_like(argmax), argmax).clamp(max=R - 1)
+        bary_red = bary.index_select(0, arg.flatten()).view(V, -1)
+        red = torch.cat((red, bary_red), 1)
+        if self.fusion_kind != "maxpool":
+            few = ls.rows_per_vertex(V) < _MIN_POINTS_PER_VERTEX
+            red = red.masked_fill(few.unsqueeze(1), 0.0)
+        ls.set_values(red)
+        if self.fusion_kind == "maxpool":
+            half = red.shape[1] // 2
+            untouched = red[:, :half].abs().sum(1, keepdim=True) == 0
+            red = red.masked_fill(untouched, -9900.0)  # lattice_modules.py:555-563 (Q6)
+            red, ls = self.fusion_module(red, ls)
+        elif self.fusion_module is not None:
+            red, ls = self.fusion_module(red, ls)
+        # Q7: vertex 0 is the sink of invalid indices and carries no features (lattice_modules.py:569-570)
+        red = torch.cat([torch.zeros_like(red[:1]), red[1:]], 0)
+        ls.set_values(red)
+        red, ls = self.last_conv(red, ls)
+        return red, ls
+
+
+class LatticeNetSeq(torch.nn.Module):
+    """Same constructor / forward contract and state-dict keys as LNN_SEQ (models.py:15-476)."""
+
+    def __init__(self, nr_classes, model_params, config_parser):
+        super().__init__()
+        model_cfg = config_parser.get_model_vars()
+        self.nr_classes = nr_classes
+        self.model_params = model_params
+        mp = model_params
+        experiment = mp.experiment()
+        if experiment not in _EXPERIMENTS:
+            raise RuntimeError("Experiment " + experiment + " is not valid")
+        self.sequence_learning = bool(model_cfg["sequence_learning"])
+        kinds = [str(k).lower() for k in model_cfg["rnn_modules"]]
+        self.rnn_modules = [k if k in FUSION_TYPES else "none" for k in kinds]
+        if all(k == "none" for k in self.rnn_modules):
+            raise RuntimeError("rnn_modules can not all be none (models.py:56)")
+        self.first_sequence = True
+        nd = self.nr_downsamples = mp.nr_downsamples()
+        self.nr_blocks_down_stage = mp.nr_blocks_down_stage()
+        self.nr_blocks_bottleneck = mp.nr_blocks_bottleneck()
+        self.nr_blocks_up_stage = mp.nr_blocks_up_stage()
+        start = mp.pointnet_start_nr_channels()
+
+        self.distribute = DistributeLatticeModule(experiment)
+        self.point_net_seq = PointNetSeq(mp.pointnet_layers(), start, experiment, self.rnn_modules, self.sequence_learning)
+
+        # middle (C = start), bottleneck (4*start), late (3*start): models.py:73-155
+        if self.sequence_learning:
+            widths = (start, start * 4, start * 3)
+            self.recurrent_fusion_modules = torch.nn.ModuleList(
+                [make_fusion(self.rnn_modules[1 + i], widths[i]) for i in range(3)])
+        else:
+            self.recurrent_fusion_modules = None
+
+        # down path (models.py:161-184)
+        self.resnet_blocks_per_down_lvl_list = torch.nn.ModuleList([])
+        self.coarsens_list = torch.nn.ModuleList([])
+        skip_channels, cur = [], start
+        for i in range(nd):
+            blocks = torch.nn.ModuleList([])
+            for _ in range(self.nr_blocks_down_stage[i]):
+                if i < mp.nr_levels_down_with_normal_resnet():
+                    blocks.append(ResnetBlock(cur, [1, 1], [False, False], False))
+                else:
+                    blocks.append(BottleneckBlock(cur, [False, False, False]))
+            self.resnet_blocks_per_down_lvl_list.append(blocks)
+            skip_channels.append(cur)
+            cur = int(cur * 2 * mp.compression_factor())
+            self.coarsens_list.append(GnReluCoarsen(cur))
+
+        # bottleneck (models.py:190-193)
+        self.resnet_blocks_bottleneck = torch.nn.ModuleList(
+            [BottleneckBlock(cur, [False, False, False]) for _ in range(self.nr_blocks_bottleneck)])
+
+        # up path (models.py:201-230)
+        self.finefy_list = torch.nn.ModuleList([])
+        self.resnet_blocks_per_up_lvl_list = torch.nn.ModuleList([])
+        for i in range(nd):
+            skip = skip_channels.pop()
+            nr_finefy = int(cur / 2)
+            self.finefy_list.append(GnReluFinefy(nr_finefy))
+            cur = skip + nr_finefy
+            blocks = torch.nn.ModuleList([])
+            for j in range(self.nr_blocks_up_stage[i]):
+                last = (j == self.nr_blocks_up_stage[i] - 1) and (i == nd - 1)
+                if i >= nd - mp.nr_levels_up_with_normal_resnet():
+                    blocks.append(ResnetBlock(cur, [1, 1], [False, last], False))
+                else:
+                    blocks.append(BottleneckBlock(cur, [False, False, last]))
+            self.resnet_blocks_per_up_lvl_list.append(blocks)
+
+        self.slice_fast_cuda = SliceFastCUDALatticeModule(nr_classes=nr_classes, dropout_prob=mp.dropout_last_layer(),
+                                                          experiment=experiment)
+        self.slice = SliceLatticeModule()
+        self.splat = SplatLatticeModule()
+        self.logsoftmax = torch.nn.LogSoftmax(dim=1)
+
+    def reset_sequence(self):
+        self.first_sequence = True
+        if self.sequence_learning:
+            self.point_net_seq.reset_sequence()
+            for m in self.recurrent_fusion_modules:
+                if m is not None:
+                    m.reset_sequence()
+
+    def _fuse(self, slot, lv, ls):
+        if self.sequence_learning and self.recurrent_fusion_modules[slot] is not None:
+            lv, ls = self.recurrent_fusion_modules[slot](lv, ls)
+        return lv, ls
+
+    def forward(self, ls, positions, values, early_return=False, with_gradient=True, vis_aflow=False):
+        seq, rnn = self.sequence_learning, self.rnn_modules
+        reset_hashmap = not (seq and not self.first_sequence)  # models.py:287-289
+        with torch.no_grad():  # Q9
+            ls, distributed, indices, weights = self.distribute(ls, positions, values, reset_hashmap)
+        lv, ls = self.point_net_seq(ls, distributed, indices)
+        if early_return and seq and rnn[1] == "none" and rnn[2] == "none" and rnn[3] == "none":
+            self.first_sequence = False
+            return lv, lv, ls
+
+        skips = []
+        for i in range(self.nr_downsamples):
+            for block in self.resnet_blocks_per_down_lvl_list[i]:
+                lv, ls = block(lv, ls)
+            skips.append((ls, lv))
+            if i == 0:
+                lv, ls = self._fuse(0, lv, ls)
+                if early_return and seq and rnn[2] == "none" and rnn[3] == "none":
+                    self.first_sequence = False
+                    return lv, lv, ls
+            lv, ls = self.coarsens_list[i](lv, ls)
+
+        for block in self.resnet_blocks_bottleneck:
+            lv, ls = block(lv, ls)
+        lv, ls = self._fuse(1, lv, ls)
+
+        grad_on = (not (early_return and seq and rnn[3] == "none")) and with_gradient and torch.is_grad_enabled()
+        with torch.set_grad_enabled(grad_on):  # models.py:386
+            last = self.nr_downsamples - 1
+            for i in range(self.nr_downsamples):
+                fine_ls, fine_lv = skips.pop()
+                lv, ls = self.finefy_list[i](lv, ls, fine_ls)
+                lv = torch.cat((lv, fine_lv), 1)
+                if i == last:
+                    lv, ls = self._fuse(2, lv, ls)
+                    if early_return and seq:
+                        self.first_sequence = False
+                        return lv, lv, ls
+            # Q1: the up-path residual blocks run for the LAST level only (models.py:435 sits outside
+            # the `for i` loop); resnet_blocks_per_up_lvl_list[0] never creates parameters.
+            for block in self.resnet_blocks_per_up_lvl_list[last]:
+                lv, ls = block(lv, ls)
+
+        sv = self.slice_fast_cuda(lv, ls, positions, indices, weights)
+        self.first_sequence = False
+        return self.logsoftmax(sv), sv, ls

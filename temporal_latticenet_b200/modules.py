@@ -1,0 +1,306 @@
+"""nn.Modules over the sm_100a kernels -- the `latticenet_py.lattice.lattice_modules` surface the
+reference imports with `*` (/root/reference/seq_lattice/lattice_modules.py:15, models.py:7).
+
+Same names, same `(lv, ls)` protocol, same lazy parameter creation and parameter names as the
+recipes in SURVEY.md section 2.2 (E4-E13), so a state-dict moves between the reference-driven
+oracle run and this implementation unchanged.  GroupNorm+ReLU is one fused op; every convolution
+on a level reuses that level's neighbour table.
+"""
+import math
+
+import torch
+
+from . import funcs as F_
+from . import ops
+from .funcs import *  # noqa: F401,F403  (the reference expects the Functions in this namespace too)
+
+_NO_LOCAL_MEAN = ("pointnet_no_local_mean", "pointnet_no_elevate_no_local_mean", "splat")
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _conv_weight(rows, nr_filters):
+    """uniform(+-sqrt(3)*gain/sqrt(fan_out)); fan_out of a [rows, filters] tensor is `rows`
+    (the rule the reference keeps a copy of at lattice_modules.py:264-272)."""
+    bound = math.sqrt(3.0) * math.sqrt(2.0) / math.sqrt(rows)
+    return torch.nn.Parameter(torch.empty(rows, nr_filters, device=_dev()).uniform_(-bound, bound))
+
+
+def _linear(nr_in, nr_out, bias):
+    lin = torch.nn.Linear(nr_in, nr_out, bias=bias).to(_dev())
+    with torch.no_grad():
+        torch.nn.init.kaiming_normal_(lin.weight, mode="fan_in", nonlinearity="relu")
+    return lin
+
+
+class DistributeLatticeModule(torch.nn.Module):
+    """models.py:62,297-298: (ls, positions[N,3], values[N,vd], reset) ->
+    (ls, distributed[4N, 3+vd+1], indices[4N] i32, weights[4N])."""
+
+    def __init__(self, experiment):
+        super().__init__()
+        self.experiment = experiment
+
+    def forward(self, ls, positions, values, reset_hashmap=True):
+        rows, idx, w = F_.DistributeLattice.apply(ls, positions, values, reset_hashmap,
+                                                  self.experiment not in _NO_LOCAL_MEAN)
+        return ls, rows, idx, w
+
+
+class GroupNormLatticeModule(torch.nn.Module):
+    """GroupNorm over [1,C,V]; parameters live in `gn` (a torch GroupNorm used as the container so
+    the state-dict keys are gn.weight / gn.bias)."""
+
+    def __init__(self, nr_params, affine=True):
+        super().__init__()
+        self.groups = ops.gn_groups(nr_params)
+        self.gn = torch.nn.GroupNorm(self.groups, nr_params, affine=affine).to(_dev())
+
+    def forward(self, lv, ls, relu=False):
+        lv = ops.group_norm(lv, self.gn.weight, self.gn.bias, self.groups, self.gn.eps, relu)
+        ls.set_values(lv)
+        return lv, ls
+
+
+class Gn(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.norm = None
+
+    def forward(self, lv, ls):
+        if self.norm is None:
+            self.norm = GroupNormLatticeModule(lv.shape[1])
+        return self.norm(lv, ls)
+
+
+class Conv1x1(torch.nn.Module):
+    """single tensor in / out (lattice_modules.py:95,102)"""
+
+    def __init__(self, out_channels, bias):
+        super().__init__()
+        self.out_channels, self.use_bias, self.linear = out_channels, bias, None
+
+    def forward(self, lv):
+        if self.linear is None:
+            self.linear = _linear(lv.shape[1], self.out_channels, self.use_bias)
+        return ops.linear(lv, self.linear.weight, self.linear.bias)
+
+
+class GnRelu1x1(torch.nn.Module):
+    def __init__(self, out_channels, bias):
+        super().__init__()
+        self.out_channels, self.use_bias = out_channels, bias
+        self.norm, self.linear = None, None
+
+    def forward(self, lv, ls):
+        if self.norm is None:
+            self.norm = GroupNormLatticeModule(lv.shape[1])
+            self.linear = _linear(lv.shape[1], self.out_channels, self.use_bias)
+        lv, ls = self.norm(lv, ls, relu=True)
+        lv = ops.linear(lv, self.linear.weight, self.linear.bias)
+        ls.set_values(lv)
+        return lv, ls
+
+
+class ConvLatticeModule(torch.nn.Module):
+    """(lv[V,C], ls) -> (lv[V,F], ls); weight [9C, F], slot-major."""
+
+    def __init__(self, nr_filters, neighbourhood_size=1, dilation=1, bias=True):
+        super().__init__()
+        self.nr_filters, self.neighbourhood_size, self.dilation, self.use_bias = nr_filters, neighbourhood_size, dilation, bias
+        self.weight, self.bias = None, None
+
+    def forward(self, lv, ls):
+        ls.set_values(lv)
+        if self.weight is None:
+            rows = ls.get_filter_extent(self.neighbourhood_size) * lv.shape[1]
+            self.weight = _conv_weight(rows, self.nr_filters)
+            if self.use_bias:
+                b = 1.0 / math.sqrt(rows)
+                self.bias = torch.nn.Parameter(torch.empty(self.nr_filters, device=_dev()).uniform_(-b, b))
+        out = F_.ConvIm2RowLattice.apply(lv, ls, self.weight, self.dilation)
+        if self.bias is not None:
+            out = out + self.bias
+        ls.set_values(out)
+        return out, ls
+
+
+class CoarsenLatticeModule(torch.nn.Module):
+    def __init__(self, nr_filters):
+        super().__init__()
+        self.nr_filters, self.weight = nr_filters, None
+
+    def forward(self, lv, ls):
+        ls.set_values(lv)
+        if self.weight is None:
+            self.weight = _conv_weight(ls.get_filter_extent(1) * lv.shape[1], self.nr_filters)
+        out, coarse = F_.CoarsenLattice.apply(lv, ls, self.weight)
+        coarse.set_values(out)
+        return out, coarse
+
+
+class FinefyLatticeModule(torch.nn.Module):
+    def __init__(self, nr_filters):
+        super().__init__()
+        self.nr_filters, self.weight = nr_filters, None
+
+    def forward(self, lv_coarse, ls_coarse, ls_fine):
+        ls_coarse.set_values(lv_coarse)
+        if self.weight is None:
+            self.weight = _conv_weight(ls_coarse.get_filter_extent(1) * lv_coarse.shape[1], self.nr_filters)
+        out = F_.FinefyLattice.apply(lv_coarse, ls_coarse, ls_fine, self.weight)
+        ls_fine.set_values(out)
+        return out, ls_fine
+
+
+class GnReluConv(torch.nn.Module):
+    def __init__(self, nr_filters, dilation, bias, with_dropout):
+        super().__init__()
+        self.norm = None
+        self.conv = ConvLatticeModule(nr_filters, 1, dilation, bias)
+        self.drop = torch.nn.Dropout(0.2) if with_dropout else None
+
+    def forward(self, lv, ls):
+        if self.norm is None:
+            self.norm = GroupNormLatticeModule(lv.shape[1])
+        lv, ls = self.norm(lv, ls, relu=True)
+        if self.drop is not None:
+            lv = self.drop(lv)
+        return self.conv(lv, ls)
+
+
+class GnReluCoarsen(torch.nn.Module):
+    """models.py:182,353: (lv_fine, ls_fine) -> (lv_coarse[Vc,F], ls_coarse)"""
+
+    def __init__(self, nr_filters):
+        super().__init__()
+        self.norm = None
+        self.coarse = CoarsenLatticeModule(nr_filters)
+
+    def forward(self, lv, ls):
+        if self.norm is None:
+            self.norm = GroupNormLatticeModule(lv.shape[1])
+        lv, ls = self.norm(lv, ls, relu=True)
+        return self.coarse(lv, ls)
+
+
+class GnReluFinefy(torch.nn.Module):
+    """models.py:214,398: (lv_coarse, ls_coarse, ls_fine) -> (lv_fine[Vf,F], ls_fine)"""
+
+    def __init__(self, nr_filters):
+        super().__init__()
+        self.norm = None
+        self.fine = FinefyLatticeModule(nr_filters)
+
+    def forward(self, lv_coarse, ls_coarse, ls_fine):
+        if self.norm is None:
+            self.norm = GroupNormLatticeModule(lv_coarse.shape[1])
+        lv_coarse, ls_coarse = self.norm(lv_coarse, ls_coarse, relu=True)
+        return self.fine(lv_coarse, ls_coarse, ls_fine)
+
+
+class ResnetBlock(torch.nn.Module):
+    """models.py:175,227: 2 x (GN -> ReLU -> conv) + identity"""
+
+    def __init__(self, nr_filters, dilations, biases, with_dropout):
+        super().__init__()
+        self.conv1 = GnReluConv(nr_filters, dilations[0], biases[0], False)
+        self.conv2 = GnReluConv(nr_filters, dilations[1], biases[1], with_dropout)
+
+    def forward(self, lv, ls):
+        skip = lv
+        lv, ls = self.conv1(lv, ls)
+        lv, ls = self.conv2(lv, ls)
+        lv = lv + skip
+        ls.set_values(lv)
+        return lv, ls
+
+
+class BottleneckBlock(torch.nn.Module):
+    """models.py:178,193,230: 1x1 (C/4) -> conv (C/4) -> 1x1 (C) + identity"""
+
+    def __init__(self, out_channels, biases):
+        super().__init__()
+        self.contract = GnRelu1x1(int(out_channels / 4), biases[0])
+        self.conv = GnReluConv(int(out_channels / 4), 1, biases[1], False)
+        self.expand = GnRelu1x1(out_channels, biases[2])
+
+    def forward(self, lv, ls):
+        skip = lv
+        lv, ls = self.contract(lv, ls)
+        lv, ls = self.conv(lv, ls)
+        lv, ls = self.expand(lv, ls)
+        lv = lv + skip
+        ls.set_values(lv)
+        return lv, ls
+
+
+class SliceLatticeModule(torch.nn.Module):
+    def forward(self, lv, ls, positions, indices=None, weights=None):
+        ls.set_values(lv)
+        return F_.SliceLattice.apply(lv, ls, positions, indices, weights)
+
+
+class SplatLatticeModule(torch.nn.Module):
+    def forward(self, ls, positions, values):
+        lv, idx, w = F_.SplatLattice.apply(ls, positions, values)
+        ls.set_values(lv)
+        return lv, ls, idx, w
+
+
+class SliceFastCUDALatticeModule(torch.nn.Module):
+    """models.py:232,465 (recipe SURVEY E12): 1x1 chain C -> C -> C/2 -> 8, gather [N, 4*9], subtract
+    gamma*max-over-simplex + beta, Linear 36->36, GN, ReLU, Linear 36->4 = delta weights,
+    slice_classify(lv, delta, W[classes, C], b)."""
+
+    def __init__(self, nr_classes, dropout_prob, experiment):
+        super().__init__()
+        self.nr_classes, self.experiment = nr_classes, experiment
+        self.bottleneck_size = 8
+        self.stepdown = torch.nn.ModuleList([])
+        self.bottleneck = None
+        self.linear_pre_deltaW = None
+        self.dropout = torch.nn.Dropout(dropout_prob) if dropout_prob > 0.0 else None
+
+    def _create(self, C):
+        dev = _dev()
+        for i in range(2):
+            self.stepdown.append(GnRelu1x1(int(C / (2 ** i)), False))
+        self.bottleneck = GnRelu1x1(self.bottleneck_size, False)
+        g = 4 * (self.bottleneck_size + 1)
+        self.linear_pre_deltaW = torch.nn.Linear(g, g, bias=False).to(dev)
+        self.gn_middle = GroupNormLatticeModule(g)
+        self.linear_deltaW = torch.nn.Linear(g, 4, bias=True).to(dev)
+        self.linear_clasify = torch.nn.Linear(C, self.nr_classes, bias=True).to(dev)
+        self.gamma = torch.nn.Parameter(torch.ones(self.bottleneck_size + 1, device=dev))
+        self.beta = torch.nn.Parameter(torch.zeros(self.bottleneck_size + 1, device=dev))
+        with torch.no_grad():
+            torch.nn.init.kaiming_uniform_(self.linear_pre_deltaW.weight, mode="fan_in", nonlinearity="relu")
+            self.linear_deltaW.weight.mul_(0.1)
+            self.linear_deltaW.bias.zero_()
+
+    def forward(self, lv, ls, positions, indices, weights):
+        if self.bottleneck is None:
+            self._create(lv.shape[1])
+        if self.dropout is not None:
+            lv = self.dropout(lv)
+        ls.set_values(lv)
+        b, lsb = lv, ls
+        for i in range(2):
+            b, lsb = self.stepdown[i](b, lsb)
+        b, lsb = self.bottleneck(b, lsb)
+        g = F_.GatherLattice.apply(b, lsb, positions, indices, weights)
+        N = positions.shape[0]
+        g3 = g.view(N, 4, self.bottleneck_size + 1)
+        mx = g3.max(1, keepdim=True)[0]
+        g = (g3 - (self.gamma * mx + self.beta)).reshape(N, -1)
+        g = ops.linear(g, self.linear_pre_deltaW.weight)
+        g, _ = self.gn_middle(g, lsb, relu=True)
+        dw = ops.linear(g, self.linear_deltaW.weight, self.linear_deltaW.bias)
+        if self.experiment == "slice_no_deform":
+            dw = dw * 0
+        ls.set_values(lv)
+        return F_.SliceClassifyLattice.apply(lv, ls, positions, dw, self.linear_clasify.weight,
+                                             self.linear_clasify.bias, self.nr_classes, indices, weights)

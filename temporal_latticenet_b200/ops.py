@@ -1,0 +1,115 @@
+"""Dense / reduction primitives shared by the lattice modules: fp32 matmul, GroupNorm(+ReLU) over
+lattice vertices, segmented max / add / mean.  GPU only."""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+
+def matmul(a, b):
+    """fp32 GEMM.  TF32 stays off so the fp32 parity tolerance (rel 1e-4 on accumulations) holds; the
+    reference stack (torch 1.7.1 on Ampere) defaulted to TF32 here, so this is >= its precision."""
+    return torch.mm(a, b)
+
+
+def linear(x, weight, bias=None):
+    return torch.nn.functional.linear(x, weight, bias)
+
+
+def gn_groups(nr_channels):
+    """32 groups, or C/2 when C is not divisible by 32."""
+    return 32 if nr_channels % 32 == 0 else int(nr_channels / 2)
+
+
+class _GroupNormRelu(Function):
+    """GroupNorm over [1,C,V] (statistics over C/G channels x ALL vertices), optionally fused with
+    the ReLU that always follows it in GnRelu* modules.  Two kernels: double-precision group sums,
+    then a single read-modify-write pass."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, relu):
+        x = x.contiguous().float()
+        V, C = x.shape
+        lib = _lib.load()
+        p = _lib.ptr
+        sums = torch.empty(groups, 2, dtype=torch.float64, device=x.device)
+        y = torch.empty_like(x)
+        _lib.check(lib.ltn_gn_stats(p(x), V, None, C, groups, p(sums), _lib.stream()), "ltn_gn_stats")
+        _lib.check(lib.ltn_gn_apply(p(x), V, None, C, groups, p(sums), p(gamma), p(beta), float(eps), 1 if relu else 0,
+                                    p(y), _lib.stream()), "ltn_gn_apply")
+        ctx.save_for_backward(x, gamma, sums, y)
+        ctx.cfg = (groups, eps, relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, sums, y = ctx.saved_tensors
+        groups, eps, relu = ctx.cfg
+        V, C = x.shape
+        cpg = C // groups
+        n = float(V * cpg)
+        gy = gy.contiguous().float()
+        if relu:
+            gy = gy * (y > 0).to(gy.dtype)
+        mean = (sums[:, 0] / n)
+        var = (sums[:, 1] / n - mean * mean).clamp(min=0.0)
+        rstd = (1.0 / torch.sqrt(var + eps)).float()
+        mean = mean.float()
+        xh = ((x.view(V, groups, cpg) - mean.view(1, groups, 1)) * rstd.view(1, groups, 1))
+        g3 = (gy * gamma.view(1, C)).view(V, groups, cpg)
+        m1 = g3.sum(dim=(0, 2), keepdim=True) / n
+        m2 = (g3 * xh).sum(dim=(0, 2), keepdim=True) / n
+        gx = ((g3 - m1 - xh * m2) * rstd.view(1, groups, 1)).reshape(V, C)
+        ggamma = (gy * xh.reshape(V, C)).sum(0)
+        gbeta = gy.sum(0)
+        return gx, ggamma, gbeta, None, None, None
+
+
+def group_norm(x, gamma, beta, groups, eps=1e-5, relu=False):
+    return _GroupNormRelu.apply(x, gamma, beta, groups, eps, relu)
+
+
+def scatter_max(src, index, dim_size=None):
+    """torch_scatter.scatter_max(src[R,C], index[R], dim=0) semantics: out 0 and argmax = R for empty
+    segments, ids < 0 folded to 0 by the caller, smallest row wins ties.  Differentiable: the
+    value is re-gathered from src at argmax so autograd routes the gradient to the arg-max rows."""
+    R, C = src.shape
+    idx32 = index.to(torch.int32).contiguous()
+    if dim_size is None:
+        dim_size = int(index.max().item()) + 1 if index.numel() > 0 else 0
+    V = int(dim_size)
+    srcd = src.detach().contiguous().float()
+    packed = torch.empty(V, C, dtype=torch.int64, device=src.device)
+    out = torch.empty(V, C, dtype=torch.float32, device=src.device)
+    arg = torch.empty(V, C, dtype=torch.int64, device=src.device)
+    p = _lib.ptr
+    _lib.check(_lib.load().ltn_scatter_max(p(srcd), p(idx32), R, C, V, p(packed), p(out), p(arg), _lib.stream()),
+               "ltn_scatter_max")
+    if torch.is_grad_enabled() and src.requires_grad:
+        empty = arg >= R
+        val = src.gather(0, arg.clamp(max=max(R - 1, 0)))
+        out = torch.where(empty, torch.zeros_like(val), val)
+    return out, arg
+
+
+def scatter_add(src, index, dim_size=None, out=None):
+    squeeze = src.dim() == 1
+    s2 = src.reshape(src.shape[0], -1).contiguous().float()
+    idx32 = index.to(torch.int32).contiguous()
+    if out is None:
+        if dim_size is None:
+            dim_size = int(index.max().item()) + 1 if index.numel() > 0 else 0
+        out = torch.zeros(int(dim_size), s2.shape[1], dtype=torch.float32, device=src.device)
+    else:
+        out = out.reshape(out.shape[0], -1)
+    p = _lib.ptr
+    _lib.check(_lib.load().ltn_scatter_add(p(s2), p(idx32), s2.shape[0], s2.shape[1], p(out), out.shape[0],
+                                           _lib.stream()), "ltn_scatter_add")
+    return out.reshape(-1) if squeeze else out
+
+
+def scatter_mean(src, index, dim_size=None, out=None):
+    total = scatter_add(src, index, dim_size, out)
+    ones = torch.ones(index.shape[0], dtype=torch.float32, device=src.device)
+    count = scatter_add(ones, index, total.shape[0]).clamp(min=1)
+    return total / (count if total.dim() == 1 else count.unsqueeze(1))
