@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""bench.py -- 4-frame scans/sec of the Temporal LatticeNet hot path on B200 (BASELINE.json metric).
+
+A "step" is one 4-frame window (BASELINE config 3: rnn_modules [gru,gru,aflow,gru], frames 4, scope 3,
+sigma 0.6, 26 classes, inference, seeded weights because the pretrained checkpoint is missing) of
+synthetic SemanticKITTI-shaped scans (~125k points each) pushed through the window runner.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one process per GPU)
+  python bench.py --impl reference ...                            CPU arm: the scalar oracle + torch CPU
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+CFG = os.path.join(REPO, "configs", "lnn_eval_semantic_kitti.cfg")
+METRIC = "4-frame scans/sec"
+UNIT = "scans/s"
+FRAMES = 4
+NR_CLASSES = 26
+WORKLOAD = "config3: LNN_SEQ [gru,gru,aflow,gru], 4 frames, scope 3, sigma 0.6, 26 classes, inference, fp32"
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# inputs
+# ------------------------------------------------------------------------------------------------
+def make_windows(nr_windows, seed0):
+    from temporal_latticenet_b200 import synthetic
+    return [synthetic.window(seed0 + i, frames=FRAMES, scope=3) for i in range(nr_windows)]
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_window_seconds(window, repeats=1):
+    """Times the oracle's window executor (oracle/window_oracle.py: the reference's model recipe in
+    plain torch-CPU over the scalar C lattice oracle) on one 4-frame window with all host threads."""
+    import torch
+    from oracle import window_oracle as WO
+    torch.set_num_threads(os.cpu_count() or 1)
+    runner = WO.OracleWindowRunner(CFG, NR_CLASSES)
+    runner.materialise_parameters(window[:1])
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        runner.infer_window(window)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    window = make_windows(1, 1000)[0]
+    import torch
+    from oracle import window_oracle as WO
+    torch.set_num_threads(os.cpu_count() or 1)
+    runner = WO.OracleWindowRunner(CFG, NR_CLASSES)
+    runner.materialise_parameters(window[:1])
+    for _ in range(args.warmup):
+        runner.infer_window(window)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        runner.infer_window(window)
+    dt = time.perf_counter() - t0
+    value = FRAMES * args.steps / dt
+    pts = [int(p.shape[0]) for p, _ in window]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "points_per_scan": pts, "frames": FRAMES},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d whole 4-frame window(s) of the same synthetic workload" % args.steps},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class Probe:
+    """CUDA-event brackets around chosen C-ABI entry points / ops on torch's current stream (the
+    stream every kernel of the library is launched on)."""
+
+    def __init__(self):
+        self.records = {}
+
+    def wrap(self, name, fn, work_fn):
+        import torch
+
+        def wrapped(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a)
+            e1.record()
+            self.records.setdefault(name, []).append((e0, e1, work_fn(*a) if work_fn else 0.0))
+            return r
+        return wrapped
+
+    def summary(self):
+        out = {}
+        for name, recs in self.records.items():
+            ms = [a.elapsed_time(b) for a, b, _ in recs]
+            work = sum(w for _, _, w in recs)
+            out[name] = {"launches": len(recs), "ms_total": sum(ms), "work": work}
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--windows", type=int, default=2, help="distinct synthetic windows cycled through")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="add a per-entry-point time breakdown (extra untimed pass)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as G
+    G.build()
+    from temporal_latticenet_b200 import _lib
+    from temporal_latticenet_b200.runner import WindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    lib = _lib.load()
+
+    # inputs: every rank owns its windows (sharded by window); pinned host + device copies
+    windows_np = make_windows(args.windows, 1000 + 100 * rank)
+    host = [[(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in w] for w in windows_np]
+    devw = [[(p.to(dev), v.to(dev)) for p, v in w] for w in host]
+    pts = [int(p.shape[0]) for p, _ in windows_np[0]]
+
+    runner = WindowRunner(CFG, NR_CLASSES, dev)
+    runner.materialise_parameters(devw[0], seeded_state)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        runner.infer_window_device(devw[i % len(devw)])
+    torch.cuda.synchronize()
+    v_counts = [runner.lattice.nr_lattice_vertices()]
+    lvl = runner.lattice
+    while lvl._coarse is not None:
+        lvl = lvl._coarse
+        v_counts.append(lvl.nr_lattice_vertices())
+
+    # ---- timed region 1: device-resident inputs ------------------------------------------------------
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    launches0 = lib.ltn_launch_count()
+    evs = []
+    for i in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        runner.infer_window_device(devw[i % len(devw)])
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = lib.ltn_launch_count() - launches0
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- timed region 2: end to end through the runner with pinned HOST buffers ----------------------
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        labels = runner.infer_window(host[i % len(host)])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+    h2d = sum(p.numel() * 4 + v.numel() * 4 for p, v in host[0])
+    d2h = int(labels.numel() * 8)
+
+    # ---- roofline of the dominant kernel: CUDA events around its launches in a repeat of the timed steps
+    probe = Probe()
+    names = {}
+    if args.breakdown:
+        for name, _ in _lib.declared_functions():
+            if name not in ("ltn_version", "ltn_launch_count"):
+                names[name] = None
+    names["ltn_im2row"] = lambda vals, Vvals, vd, nbr, Vq, vqd, C, out, st: float(Vq) * (12 + 40 * C)
+    originals = {}
+    for name, wf in names.items():
+        originals[name] = getattr(lib, name)
+        setattr(lib, name, probe.wrap(name, originals[name], wf))
+    import temporal_latticenet_b200.ops as ops
+    mm_orig, lin_orig = ops.matmul, ops.linear
+    ops.matmul = probe.wrap("torch.mm(cuBLAS sgemm)", mm_orig, lambda a, b: 2.0 * a.shape[0] * a.shape[1] * b.shape[1])
+    ops.linear = probe.wrap("torch.linear(cuBLAS sgemm)", lin_orig,
+                            lambda x, w, b=None: 2.0 * x.shape[0] * x.shape[1] * w.shape[0])
+    for i in range(min(args.steps, 4)):
+        flush.zero_()
+        runner.infer_window_device(devw[i % len(devw)])
+    torch.cuda.synchronize()
+    for name, fn in originals.items():
+        setattr(lib, name, fn)
+    ops.matmul, ops.linear = mm_orig, lin_orig
+    summ = probe.summary()
+    pk = peaks()
+    im = summ.get("ltn_im2row")
+    roofline = None
+    if im and im["ms_total"] > 0:
+        achieved = im["work"] / (im["ms_total"] * 1e-3) / 1e9
+        roofline = {"kernel": "k_im2row", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                    "launches_per_step": im["launches"] / min(args.steps, 4),
+                    "avg_launch_us": 1e3 * im["ms_total"] / im["launches"]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            sec, cores = cpu_window_seconds(windows_np[0])
+            cpu = {"value": FRAMES / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "one whole 4-frame window of the same workload (oracle/window_oracle.py), %.1f s" % sec}
+        except Exception as e:  # the baseline leg must never take the GPU number down with it
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+
+    total_scans = FRAMES * args.steps * world
+    line = {"metric": METRIC, "value": total_scans / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "points_per_scan": pts, "frames": FRAMES, "vertices_per_level_after_4_frames": v_counts,
+                       "l2": "256 MB flush between steps; per-step working set (im2row buffers) also exceeds L2",
+                       "parallelism": "windows sharded over %d rank(s), no data-path collective" % world},
+            "e2e": {"value": total_scans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+    if args.breakdown:
+        line["breakdown_ms_per_step"] = {k: v["ms_total"] / min(args.steps, 4) for k, v in
+                                         sorted(summ.items(), key=lambda kv: -kv[1]["ms_total"])}
+        line["gemm_tflops"] = {k: v["work"] / (v["ms_total"] * 1e-3) / 1e12 for k, v in summ.items()
+                               if k.startswith("torch.") and v["ms_total"] > 0}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

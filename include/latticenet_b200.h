@@ -119,6 +119,8 @@ int ltn_aflow(const float* lv, const float* h, int V, int Vh, int C, const int* 
 
 /* library version / build info */
 int ltn_version(void);
+/* kernels launched by this library since it was loaded, modulo 2^31 (bench.py: gpu_launches) */
+int ltn_launch_count(void);
 
 #ifdef __cplusplus
 }

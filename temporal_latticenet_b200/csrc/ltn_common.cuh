@@ -16,10 +16,14 @@
 #define LTN_CNT_OVERFLOW 2    // vertices dropped because the table was full (convention U4)
 #define LTN_CNT_RANGE 3       // keys outside the packable +-2^20 range
 
+// host-side count of kernel launches issued by this library (ltn_launch_count in the C ABI)
+extern unsigned long long g_ltn_launches;
+
 #define LTN_CHECK_LAUNCH()                       \
     do {                                         \
         cudaError_t e__ = cudaGetLastError();    \
         if (e__ != cudaSuccess) return (int)e__; \
+        ++g_ltn_launches;                        \
     } while (0)
 
 static inline int ltn_blocks(long long n, int threads) { return (int)((n + threads - 1) / threads); }

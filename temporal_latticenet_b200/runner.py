@@ -1,0 +1,64 @@
+"""Window runner: the loop the reference's drivers run around the model (test_ln.py:149-231,
+train_ln.py:160-239) reduced to what the hot path needs -- a fresh lattice per window, frames fed in
+order with early_return on all but the last, arg-max labels of the last frame back on the host.
+
+This is the public entry point `bench.py` times end to end (host buffers in, host labels out).
+"""
+import torch
+
+from .config import ConfigParser
+from .lattice import Lattice, ModelParams
+from .model import LatticeNetSeq
+
+
+class WindowRunner:
+    def __init__(self, cfg_path, nr_classes=26, device=None):
+        self.cfg_path = cfg_path
+        self.device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
+        self.model = LatticeNetSeq(nr_classes, ModelParams.create(cfg_path), ConfigParser(cfg_path)).to(self.device)
+        self.model.train(False)
+        self.lattice = None
+        self._labels_host = None
+
+    def new_lattice(self):
+        """a fresh lattice per window (train_ln.py:236-239, test_ln.py:264)"""
+        self.model.reset_sequence()
+        self.lattice = Lattice.create(self.cfg_path, "lattice")
+        return self.lattice
+
+    def materialise_parameters(self, frames_dev, state_dict_fn=None):
+        """Parameters are created lazily by the first full window (test_ln.py:165-185); then an
+        optional name->tensor function provides the weights (the pretrained checkpoint is missing
+        from the reference mount, so tests and the bench seed them by name)."""
+        with torch.no_grad():
+            self.infer_window_device(frames_dev)
+        if state_dict_fn is not None:
+            shapes = {k: tuple(v.shape) for k, v in self.model.state_dict().items()}
+            self.model.load_state_dict(state_dict_fn(shapes))
+        return self
+
+    def infer_window_device(self, frames_dev):
+        """frames_dev: list of (positions [N,3], values [N,1]) CUDA tensors.  Returns the final
+        frame's log-softmax [N, classes] (device)."""
+        ls = self.new_lattice()
+        out = None
+        last = len(frames_dev) - 1
+        with torch.no_grad():
+            for i, (p, v) in enumerate(frames_dev):
+                out, _, ls = self.model(ls, p, v, i != last, False)
+        self.lattice = ls
+        return out
+
+    def infer_window(self, frames_host):
+        """frames_host: list of (positions, values) PINNED host tensors.  Returns predicted labels of
+        the last frame as a pinned host int64 tensor (test_ln.py:219-222), synchronised."""
+        dev = self.device
+        frames = [(p.to(dev, non_blocking=True), v.to(dev, non_blocking=True)) for p, v in frames_host]
+        out = self.infer_window_device(frames)
+        labels = out.argmax(1)
+        if self._labels_host is None or self._labels_host.shape[0] < labels.shape[0]:
+            self._labels_host = torch.empty(labels.shape[0], dtype=torch.int64).pin_memory()
+        host = self._labels_host[: labels.shape[0]]
+        host.copy_(labels, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host

@@ -2,7 +2,6 @@
 vertex order."""
 import os
 import sys
-import zlib
 
 import numpy as np
 import torch
@@ -15,24 +14,7 @@ GOLDEN = os.path.join(REPO, "tests", "golden")
 CFG = os.path.join(REPO, "configs", "lnn_eval_semantic_kitti.cfg")
 
 
-def seeded_tensor(name, shape):
-    """Deterministic value for a parameter, a function of its NAME and SHAPE only (the pretrained
-    checkpoint is missing from the reference mount -- .MISSING_LARGE_BLOBS:1 -- so oracle and CUDA
-    paths both load this instead)."""
-    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)
-    shape = tuple(shape)
-    if len(shape) == 0:
-        return torch.tensor(0.1)  # AFlow alpha / beta (lattice_modules.py:252-253)
-    x = torch.randn(shape, generator=g)
-    if name.endswith("gn.weight") or name.endswith(".gamma"):
-        return 1.0 + 0.1 * x
-    if len(shape) == 1:
-        return 0.1 * x
-    return x * float(np.sqrt(2.0 / max(shape)))
-
-
-def seeded_state(shapes):
-    return {k: seeded_tensor(k, v) for k, v in sorted(shapes.items())}
+from temporal_latticenet_b200.seeding import seeded_state, seeded_tensor  # noqa: E402,F401
 
 
 def small_window(seed=1, frames=4, radius=9.0, max_points=6000):

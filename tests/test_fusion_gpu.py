@@ -1,0 +1,158 @@
+"""GPU parity of the per-vertex temporal fusion kernels (seq_lattice/lattice_modules.py:17-339) and
+the segmented reductions / GroupNorm against plain torch fp32 on the CPU (floating-point kernels:
+torch is the checker here, the goldens in test_golden_gpu.py pin the reference's own module code).
+
+Tolerances: pointwise gate kernels rel 1e-5 (expf/tanhf vs the CPU's libm differ in the last ulp);
+AFlow rel 1e-4 (9 x C-term distances, sqrt, division); GroupNorm 1e-5 abs on unit-variance data.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import small_window
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _lattice_two_frames(dev):
+    from temporal_latticenet_b200.lattice import Lattice
+    frames = small_window(seed=8, frames=2, radius=9.0, max_points=5000)
+    ls = Lattice(60000, 1.2, device=dev)
+    counts = []
+    for f, (p, v) in enumerate(frames):
+        ls.distribute(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev), f == 0)
+        counts.append(ls.nr_lattice_vertices())
+    return ls, counts
+
+
+@pytest.mark.parametrize("C", [64, 128, 192])
+def test_gru_and_lstm_fused_equal_torch_cells(dev, C):
+    from temporal_latticenet_b200.fusion import GRUModule, LSTMModule
+    ls, (vh, v) = _lattice_two_frames(dev)
+    g = torch.Generator().manual_seed(C)
+    h0, x1 = torch.randn(vh, C, generator=g), torch.randn(v, C, generator=g)
+    for cls, cell_name in ((GRUModule, "GRU"), (LSTMModule, "lstm")):
+        torch.manual_seed(1)
+        m = cls(C)
+        m_cpu_state = {k: t.clone() for k, t in m.state_dict().items()}
+        m = m.to(dev)
+        with torch.no_grad():
+            m(h0.to(dev), ls)
+            out, _ = m(x1.to(dev), ls)
+        # the reference's recipe, literally, on the CPU (lattice_modules.py:27-37,53-63)
+        ref = cls(C)
+        ref.load_state_dict(m_cpu_state)
+        with torch.no_grad():
+            h = ref.hidden_linear(h0)
+            h = torch.nn.utils.rnn.pad_sequence([h, x1], padding_value=0.0)[:, 0, :]
+            if cell_name == "GRU":
+                want = ref.GRU(x1, h)
+            else:
+                want, _ = ref.lstm(x1, (h, torch.zeros_like(h)))
+        np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-4, atol=2e-5)
+        # and the differentiable path (used under autograd) gives the same numbers
+        m.reset_sequence()
+        xg = x1.to(dev).requires_grad_(True)
+        m(h0.to(dev), ls)
+        out2, _ = m(xg, ls)
+        np.testing.assert_allclose(out2.detach().cpu().numpy(), out.cpu().numpy(), rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("C,use_center", [(64, True), (256, True), (128, False)])
+def test_aflow_fused_equals_reference_recipe(dev, C, use_center):
+    """lattice_modules.py:298-339 restated with torch on the CPU over the oracle's neighbour table"""
+    from temporal_latticenet_b200.fusion import CustomKernelConvLatticeIm2RowModule
+    ls, (vh, v) = _lattice_two_frames(dev)
+    g = torch.Generator().manual_seed(C)
+    h, lv = torch.randn(vh, C, generator=g), torch.randn(v, C, generator=g)
+    m = CustomKernelConvLatticeIm2RowModule(C, use_center=use_center).to(dev)
+    with torch.no_grad():
+        out, w, nbr = m(lv.to(dev), h.to(dev), ls)
+    bias = m.bias.detach().cpu()
+    nbr_c = nbr.cpu().long()
+    hp = torch.nn.functional.pad(h, (0, 0, 0, v - vh), value=-999999.0)
+    pad = torch.cat([hp, torch.zeros(1, C)], 0)
+    nb = pad[torch.where(nbr_c < 0, torch.full_like(nbr_c, v), nbr_c)]  # [V,9,C]
+    present = (nbr_c != -1).float()
+    d = torch.cdist(nb, lv.unsqueeze(1), p=2.0).squeeze(2) * present
+    if not use_center:
+        d[:, 8] = 0
+    d = d / d.sum(1, keepdim=True)
+    a = torch.ones_like(d) * 0.1
+    ww = (a - torch.min(d, a)) * 0.1 * present
+    if not use_center:
+        ww[:, 8] = 0
+    want = (nb * ww.unsqueeze(2)).sum(1) + bias
+    got, gw = out.cpu(), w.cpu()
+    assert torch.equal(torch.isnan(gw), torch.isnan(ww))  # quirk Q5: NaNs where the reference makes them
+    ok = ~torch.isnan(ww).any(1)
+    np.testing.assert_allclose(gw[ok].numpy(), ww[ok].numpy(), rtol=1e-4, atol=1e-6)
+    scale = float(want[ok].abs().max())
+    assert float((got[ok] - want[ok]).abs().max()) < 1e-4 * scale
+    # differentiable path == fused path
+    lvg = lv.to(dev).requires_grad_(True)
+    out2, w2, _ = m(lvg, h.to(dev), ls)
+    assert float((out2.detach().cpu()[ok] - got[ok]).abs().max()) < 1e-4 * scale
+
+
+@pytest.mark.parametrize("V,C", [(1000, 64), (4097, 192), (300, 36), (5, 8)])
+def test_group_norm_relu(dev, V, C):
+    from temporal_latticenet_b200 import ops
+    g = torch.Generator().manual_seed(V)
+    x = torch.randn(V, C, generator=g) * 3 + 1
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    G = ops.gn_groups(C)
+    xg = x.to(dev).requires_grad_(True)
+    gg, bg = gamma.to(dev).requires_grad_(True), beta.to(dev).requires_grad_(True)
+    y = ops.group_norm(xg, gg, bg, G, 1e-5, True)
+    xc, gc, bc = x.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    yc = torch.relu(torch.nn.functional.group_norm(xc.t().unsqueeze(0), G, gc, bc, 1e-5).squeeze(0).t())
+    np.testing.assert_allclose(y.detach().cpu().numpy(), yc.detach().float().numpy(), rtol=1e-5, atol=1e-5)
+    go = torch.randn(V, C, generator=g)
+    y.backward(go.to(dev))
+    yc.backward(go.double())
+    for a, b in ((xg, xc), (gg, gc), (bg, bc)):
+        s = float(b.grad.abs().max()) + 1e-9
+        assert float((a.grad.cpu().double() - b.grad).abs().max()) / s < 1e-4
+
+
+def test_scatter_max_add_mean_semantics(dev):
+    """torch_scatter 2.0.4 semantics at the reference's call sites (lattice_modules.py:485-520):
+    empty segment -> 0 / argmax = R; ids < 0 folded by the caller; smallest row wins ties."""
+    from temporal_latticenet_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    R, C, V = 5000, 64, 700
+    src = torch.randn(R, C, generator=g)
+    src[10] = src[3]  # a tie between rows 3 and 10 when they share a segment
+    idx = torch.randint(0, V - 50, (R,), generator=g)  # last 50 segments empty
+    idx[10] = idx[3]
+    out, arg = ops.scatter_max(src.to(dev), idx.to(dev), dim_size=V)
+    want = torch.full((V, C), float("-inf")).scatter_reduce(0, idx.view(-1, 1).expand(R, C), src, "amax")
+    empty = torch.isinf(want)
+    want = torch.where(empty, torch.zeros_like(want), want)
+    assert torch.equal(out.cpu(), want)
+    a = arg.cpu()
+    assert bool((a[empty] == R).all())
+    assert torch.equal(src.gather(0, a.clamp(max=R - 1))[~empty], want[~empty])
+    seg = int(idx[3])
+    tie_cols = (a[seg] == 10)
+    assert not bool(tie_cols.any())  # row 3 beats row 10 on equal values
+    add = ops.scatter_add(src.to(dev), idx.to(dev), dim_size=V).cpu()
+    want_add = torch.zeros(V, C).index_add(0, idx, src)
+    np.testing.assert_allclose(add.numpy(), want_add.numpy(), rtol=1e-4, atol=1e-4)
+    mean = ops.scatter_mean(src.to(dev), idx.to(dev), dim_size=V).cpu()
+    cnt = torch.bincount(idx, minlength=V).clamp(min=1).float().unsqueeze(1)
+    np.testing.assert_allclose(mean.numpy(), (want_add / cnt).numpy(), rtol=1e-4, atol=1e-4)
+    # differentiable: gradient lands on the arg-max rows only
+    s = src.to(dev).requires_grad_(True)
+    o, ar = ops.scatter_max(s, idx.to(dev), dim_size=V)
+    o.sum().backward()
+    hits = torch.zeros(R, C)
+    hits.scatter_add_(0, a.clamp(max=R - 1), (~empty).float())
+    assert torch.equal(s.grad.cpu(), hits)
