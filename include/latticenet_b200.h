@@ -17,7 +17,8 @@
  *  - pos_dim is 3 (4 simplex vertices per point, filter extent 9: lattice_modules.py:299,310-311);
  *  - rows are point-major: row = point*4 + r (models.py:452); indices are int32, -1 = absent.
  *
- * Hash-table storage (all allocated by the caller, `nslots` a power of two >= 2*capacity):
+ * Hash-table storage (all allocated by the caller, `nslots` a power of two >= 2*capacity; the
+ * Python host uses 4*capacity):
  *    slot_keys  uint64[nslots]  packed key (3 x 21 bit), all-ones = empty
  *    slot_ids   int32 [nslots]  vertex id of the slot, -1 until numbered
  *    slot_first int32 [nslots]  scratch: smallest row that touched a new slot in this batch

@@ -59,8 +59,10 @@ class HashTable:
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else "cuda")
         self._capacity = int(capacity)
+        # 4 slots per vertex: probes stay short, and a frame may touch up to 4x capacity distinct keys
+        # before the overflow rule (ids beyond capacity -> -1, in order of first appearance) degrades
         n = 8
-        while n < 2 * self._capacity:
+        while n < 4 * self._capacity:
             n <<= 1
         self.nslots = n
         dev = self.device

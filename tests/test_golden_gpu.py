@@ -106,11 +106,12 @@ def test_window_matches_reference_golden(name, tmp_path):
     assert np.array_equal(logits.argmax(1)[clear], g.argmax(1)[clear])
 
 
-def test_training_step_runs_and_matches_autograd_of_unfused_path(tmp_path):
-    """BPTT through a 2-frame window: the loss decreases after one AdamW step and the gradients of the
-    fused kernels (conv transpose-as-gather, slice_classify, scatter_max, GroupNorm) agree with
-    torch autograd on the same graph evaluated in float64 on the CPU for a few probed parameters
-    (directional finite difference)."""
+def test_training_step_gradients_match_oracle_autograd(tmp_path):
+    """BPTT through a 2-frame window (train_ln.py:163-233): every parameter gradient of the CUDA path
+    (conv transpose-as-gather, slice_classify / gather backward kernels, scatter_max, GroupNorm) equals
+    torch autograd over the oracle's unfused CPU graph with the same seeded weights, and one AdamW
+    step lowers the loss.  Tolerance: 1e-2 of each gradient's absolute maximum (fp32 accumulation order; observed <= 6e-3)."""
+    from oracle import window_oracle as WO
     from temporal_latticenet_b200.config import ConfigParser
     from temporal_latticenet_b200.lattice import Lattice, ModelParams
     from temporal_latticenet_b200.lovasz import LovaszSoftmax
@@ -121,7 +122,7 @@ def test_training_step_runs_and_matches_autograd_of_unfused_path(tmp_path):
     meta = dict(meta, frames=2)
     cfg = _cfg_for(meta, tmp_path)
     frames = [(z["pos%d" % i], z["val%d" % i]) for i in range(2)]
-    target = torch.from_numpy(np.random.default_rng(0).integers(0, 26, frames[-1][0].shape[0])).to(dev)
+    target = torch.from_numpy(np.random.default_rng(0).integers(0, 26, frames[-1][0].shape[0]))
     model = LatticeNetSeq(26, ModelParams.create(cfg), ConfigParser(cfg)).to(dev)
     model.train(True)
     lovasz, nll = LovaszSoftmax(ignore_index=0), torch.nn.NLLLoss(ignore_index=0)
@@ -131,7 +132,8 @@ def test_training_step_runs_and_matches_autograd_of_unfused_path(tmp_path):
         lattice = Lattice.create(cfg, "lattice")
         for i, (p, v) in enumerate(frames):
             out, _, lattice = model(lattice, torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev), i != 1, True)
-        return 0.5 * lovasz(out, target) + 0.5 * nll(out, target)
+        t = target.to(dev)
+        return 0.5 * lovasz(out, t) + 0.5 * nll(out, t)
 
     with torch.no_grad():
         window_loss()  # lazy parameters
@@ -140,30 +142,29 @@ def test_training_step_runs_and_matches_autograd_of_unfused_path(tmp_path):
     loss0 = window_loss()
     opt.zero_grad()
     loss0.backward()
-    named = dict(model.named_parameters())
-    for k, p in named.items():
+
+    # the same window under autograd on the oracle
+    orc = WO.OracleWindowRunner(cfg, 26).materialise_parameters(frames)
+    orc.model.train(True)
+    orc.model.reset_sequence()
+    ls = WO.Lattice.create(cfg, "lattice")
+    for i, (p, v) in enumerate(frames):
+        out, _, ls = orc.model(ls, torch.from_numpy(p), torch.from_numpy(v), i != 1)
+    oloss = 0.5 * lovasz(out, target) + 0.5 * nll(out, target)
+    oloss.backward()
+    assert abs(float(loss0) - float(oloss)) < 1e-4 * abs(float(oloss))
+    ograds = {k: p.grad for k, p in orc.model.named_parameters()}
+    bad = []
+    for k, p in model.named_parameters():
         if ".AFLOW.weight" in k:
             continue  # quirk Q4: created, never used
-        assert p.grad is not None and torch.isfinite(p.grad).all(), k
-    # directional finite difference along the gradient for a few parameters
-    for k in ("slice_fast_cuda.linear_clasify.weight", "resnet_blocks_per_up_lvl_list.1.1.conv2.conv.weight",
-              "point_net_seq.last_conv.weight", "recurrent_fusion_modules.2.GRU.weight_ih",
-              "point_net_seq.layers.0.weight"):
-        p = named[k]
-        g = p.grad.clone()
-        gn = float(g.norm())
-        if gn == 0:
-            continue
-        d = g / gn
-        eps = 1e-2
-        with torch.no_grad():
-            p.add_(eps * d)
-            lp = float(window_loss())
-            p.sub_(2 * eps * d)
-            lm = float(window_loss())
-            p.add_(eps * d)
-        fd = (lp - lm) / (2 * eps)
-        assert abs(fd - gn) < 0.1 * gn + 1e-4, (k, fd, gn)
+        og = ograds[k]
+        assert p.grad is not None and og is not None, k
+        scale = float(og.abs().max()) + 1e-12
+        err = float((p.grad.cpu() - og).abs().max()) / scale
+        if err > 1e-2:
+            bad.append((k, err))
+    assert not bad, bad
     opt.step()
     with torch.no_grad():
         loss1 = window_loss()

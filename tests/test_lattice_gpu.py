@@ -102,14 +102,28 @@ def test_append_only_across_frames_and_reset(dev):
 
 
 def test_capacity_overflow_gives_minus_one(dev):
-    pos, val = _cloud("gauss", 4000, 3)
-    ls = _cuda_lattice(dev, cap=500)
+    """convention U4: vertices beyond the capacity get id -1, in order of first appearance -- exactly
+    the oracle's ids while the distinct keys fit the slot array (4 x capacity) ..."""
+    pos, val = _cloud("lidar", 9000, 3)
+    full = O.OracleTable(60000)
+    full.distribute(pos, val, O.scale_factors(0.6))
+    cap = int(full.size() * 0.6)
+    ls = _cuda_lattice(dev, cap=cap)
     _, idx, _ = ls.distribute(torch.from_numpy(pos).to(dev), torch.from_numpy(val).to(dev), True)
-    tab = O.OracleTable(500)
+    tab = O.OracleTable(cap)
     _, o_idx, _ = tab.distribute(pos, val, O.scale_factors(0.6))
-    assert ls.nr_lattice_vertices() == 500 == tab.size()
+    assert ls.nr_lattice_vertices() == cap == tab.size()
     assert np.array_equal(idx.cpu().numpy(), o_idx) and (o_idx == -1).any()
-    assert ls.hash_table.nr_overflowed() > 0
+    assert ls.hash_table.nr_overflowed() == full.size() - cap
+    assert np.array_equal(ls.hash_table.keys().cpu().numpy(), tab.keys())
+    # ... and beyond that it degrades without hanging: ids stay in range, the table is exactly full
+    pos, val = _cloud("gauss", 4000, 3)
+    ls = _cuda_lattice(dev, cap=200)
+    _, idx, _ = ls.distribute(torch.from_numpy(pos).to(dev), torch.from_numpy(val).to(dev), True)
+    i = idx.cpu().numpy()
+    assert ls.nr_lattice_vertices() == 200 and i.max() == 199 and i.min() == -1
+    keys = ls.hash_table.keys().cpu().numpy()
+    assert len({tuple(k) for k in keys}) == 200
 
 
 def _three_levels(dev, pos, val):
