@@ -104,6 +104,24 @@ int ltn_gn_stats(const float* x, int V, const int* v_dev, int C, int G, double* 
 int ltn_gn_apply(const float* x, int V, const int* v_dev, int C, int G, const double* sums, const float* gamma,
                  const float* beta, float eps, int relu, float* y, void* stream);
 
+/* ---- fused convolution on the tensor cores (csrc/ltn_conv.cu) ------------------------------------- */
+
+/* ConvLatticeModule / CoarsenLattice / FinefyLattice (lattice_modules.py:440,573; models.py:353,398) and
+ * the dense layers around them (GnRelu1x1, Conv1x1, nn.Linear, GRU/LSTM gate GEMMs) WITHOUT the [V,9C]
+ * im2row buffer:  out[v,f] = sum_{s<S} sum_c act(x[nbr[v,s],c]) * W[s*C+c, f] (+bias[f]) (+res[v,f]),
+ * act(t) = relu?(t*a_scale[c] + a_shift[c]) on present rows, 0 for absent ones (nbr < 0 or >= Vx).
+ * wt = W transposed, [F, S*C] (K-major);  nbr == NULL means S = 1, identity rows.  vx_dev / vq_dev
+ * (nullable): device-side row counts.  C % 32 == 0, C <= 256, F % 16 == 0, ldo % 4 == 0.
+ * passes = 3: fp32-parity (hi/lo split, three tf32 tensor-core passes); passes = 1: plain TF32. */
+int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int Vq, const int* vq_dev, int C, int S,
+                const float* wt, int F, const float* a_scale, const float* a_shift, int relu, const float* bias,
+                const float* res, float* out, int ldo, int passes, void* stream);
+/* [K,F] -> [F,K] (builds wt from a reference-layout conv weight) */
+int ltn_transpose(const float* in, int K, int F, float* out, void* stream);
+/* GroupNorm sums [G,2] (ltn_gn_stats) -> per-channel scale/shift for ltn_conv_tc's folded GN */
+int ltn_gn_affine(const double* sums, int V, const int* v_dev, int C, int G, const float* gamma, const float* beta,
+                  float eps, float* scale, float* shift, void* stream);
+
 /* ---- temporal fusion (seq_lattice/lattice_modules.py:17-339) ------------------------------------ */
 
 /* GRUModule.forward pointwise stage (lattice_modules.py:58-63); rows >= Vh are the zero padding */

@@ -113,3 +113,51 @@ def scatter_mean(src, index, dim_size=None, out=None):
     ones = torch.ones(index.shape[0], dtype=torch.float32, device=src.device)
     count = scatter_add(ones, index, total.shape[0]).clamp(min=1)
     return total / (count if total.dim() == 1 else count.unsqueeze(1))
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused gather + GEMM on the tensor cores (csrc/ltn_conv.cu)
+# ---------------------------------------------------------------------------------------------------
+_WT_CACHE = {}
+TC_PASSES = 3  # 3 = fp32-parity split (default); 1 = single-pass TF32 (stated separately wherever used)
+
+
+def conv_tc_supported(C, F):
+    return C % 32 == 0 and 0 < C <= 256 and F % 16 == 0 and F > 0
+
+
+def k_major(weight, transposed=False):
+    """K-major ([F,K]) fp32 copy of a weight for the tensor-core kernel, cached per parameter version.
+    `transposed=True`: the tensor already is [F,K] (nn.Linear layout) and is used as it is."""
+    if transposed:
+        return weight.detach().contiguous()
+    key = id(weight)
+    hit = _WT_CACHE.get(key)
+    ver = weight._version
+    if hit is not None and hit[0] == ver and hit[1] == weight.data_ptr():
+        return hit[2]
+    K, F = weight.shape
+    wt = torch.empty(F, K, dtype=torch.float32, device=weight.device)
+    _lib.check(_lib.load().ltn_transpose(_lib.ptr(weight.detach().contiguous()), K, F, _lib.ptr(wt), _lib.stream()), "ltn_transpose")
+    _WT_CACHE[key] = (ver, weight.data_ptr(), wt)
+    return wt
+
+
+def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, relu=False, bias=None, res=None, out=None, passes=None):
+    """out[v,:] = sum_s act(x[nbr[v,s],:]) @ W[s] (+bias) (+res); nbr None = plain row-wise GEMM.
+    wt is the K-major weight [F, S*C]."""
+    x = x.contiguous()
+    C = x.shape[1]
+    S = 1 if nbr is None else nbr.shape[1]
+    F = wt.shape[0]
+    if wt.shape[1] != S * C:
+        raise RuntimeError("weight is [%d,%d], expected [%d,%d]" % (wt.shape[0], wt.shape[1], F, S * C))
+    Vq = (x.shape[0] if nbr is None else nbr.shape[0]) if nr_rows is None else nr_rows
+    if out is None:
+        out = torch.empty(Vq, F, dtype=torch.float32, device=x.device)
+    p = _lib.ptr
+    rc = _lib.load().ltn_conv_tc(p(x), x.shape[0], None, p(nbr), Vq, None, C, S, p(wt), F, p(a_scale), p(a_shift),
+                                 1 if relu else 0, p(bias), p(res), p(out), out.stride(0), TC_PASSES if passes is None else passes,
+                                 _lib.stream())
+    _lib.check(rc, "ltn_conv_tc")
+    return out

@@ -1,0 +1,110 @@
+"""GPU parity of the fused tcgen05 gather-GEMM (csrc/ltn_conv.cu) against a float64 CPU evaluation of
+the same contraction over the oracle's neighbour table (oracle im2row).
+
+Tolerance (stated, fp32-parity mode = 3-pass tf32 split): |err| <= 2e-5 * sum_k |a_k||w_k| per output
+-- fp32-class (plain fp32 accumulation of K = 576..2304 terms sits at the same level); the single-pass
+TF32 variant is checked separately at 2e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import small_window
+
+pytestmark = pytest.mark.gpu
+
+from oracle import lattice_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def lattice(dev):
+    from temporal_latticenet_b200.lattice import Lattice
+    p, v = small_window(seed=3, frames=1, radius=14.0, max_points=25000)[0]
+    ls = Lattice(60000, 0.6, device=dev)
+    ls.distribute(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev), True)
+    tab = O.OracleTable(60000)
+    tab.distribute(p, v, O.scale_factors(0.6))
+    assert ls.nr_lattice_vertices() == tab.size()
+    return ls, tab
+
+
+def _check(out, a64, w64, extra64, tol):
+    want = a64 @ w64 + extra64
+    bound = np.abs(a64) @ np.abs(w64) + np.abs(extra64) + 1e-30
+    err = np.abs(out.astype(np.float64) - want) / bound
+    assert float(err.max()) < tol, float(err.max())
+
+
+@pytest.mark.parametrize("C,F", [(64, 64), (128, 128), (192, 192), (256, 128), (64, 256), (32, 16)])
+def test_gather_conv_matches_float64(dev, lattice, C, F):
+    from temporal_latticenet_b200 import ops
+    ls, tab = lattice
+    V = tab.size()
+    g = torch.Generator().manual_seed(C * 1000 + F)
+    x = torch.randn(V, C, generator=g)
+    W = torch.randn(9 * C, F, generator=g) / (9 * C) ** 0.5
+    nbr = ls.neighbours()
+    rows = O.im2row(tab.neighbours(), x.numpy()).astype(np.float64)
+    wt = ops.k_major(W.to(dev))
+    out = ops.conv_tc(x.to(dev), nbr, wt).cpu().numpy()
+    _check(out, rows, W.double().numpy(), np.zeros((V, F)), 2e-5)
+    # single-pass TF32 variant, stated separately
+    out1 = ops.conv_tc(x.to(dev), nbr, wt, passes=1).cpu().numpy()
+    _check(out1, rows, W.double().numpy(), np.zeros((V, F)), 2e-3)
+
+
+def test_folded_groupnorm_relu_bias_residual_and_short_values(dev, lattice):
+    from temporal_latticenet_b200 import ops
+    ls, tab = lattice
+    V, C, F = tab.size(), 128, 64
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(V - 37, C, generator=g)          # fewer value rows than vertices (quirk Q8): missing rows read 0
+    W = torch.randn(9 * C, F, generator=g) / (9 * C) ** 0.5
+    sc, sh = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    bias, res = torch.randn(F, generator=g), torch.randn(V, F, generator=g)
+    act = torch.relu(x * sc + sh)
+    rows = O.im2row(tab.neighbours(), act.numpy()).astype(np.float64)   # absent / missing rows stay exactly 0
+    out = ops.conv_tc(x.to(dev), ls.neighbours(), ops.k_major(W.to(dev)), a_scale=sc.to(dev), a_shift=sh.to(dev), relu=True,
+                      bias=bias.to(dev), res=res.to(dev)).cpu().numpy()
+    _check(out, rows, W.double().numpy(), (bias + res).double().numpy(), 3e-5)
+
+
+@pytest.mark.parametrize("V,C,F", [(1, 64, 64), (127, 64, 48), (129, 96, 16), (5000, 128, 384), (3001, 192, 576), (777, 256, 256)])
+def test_dense_rows_and_n_tiling(dev, V, C, F):
+    """S = 1 (nn.Linear / GRU gate GEMMs): ragged tile tails, F > 256 split into N tiles"""
+    from temporal_latticenet_b200 import ops
+    g = torch.Generator().manual_seed(V + C + F)
+    x = torch.randn(V, C, generator=g)
+    W = torch.randn(F, C, generator=g) / C ** 0.5       # nn.Linear layout = K-major already
+    b = torch.randn(F, generator=g)
+    out = ops.conv_tc(x.to(dev), None, ops.k_major(W.to(dev), transposed=True), bias=b.to(dev)).cpu().numpy()
+    _check(out, x.double().numpy(), W.double().numpy().T, np.broadcast_to(b.double().numpy(), (V, F)), 2e-5)
+
+
+def test_cross_level_tables(dev, lattice):
+    """coarsen (query coarse, values fine) and finefy (query fine, values coarse) through the same kernel"""
+    from temporal_latticenet_b200 import ops
+    ls, tab = lattice
+    coarse = ls.create_coarse_verts()
+    tc = O.OracleTable(60000)
+    p = ls.positions().cpu().numpy()
+    tc.insert_points(p, O.scale_factors(1.2))
+    assert coarse.nr_lattice_vertices() == tc.size()
+    g = torch.Generator().manual_seed(11)
+    C, F = 64, 128
+    xf = torch.randn(tab.size(), C, generator=g)
+    W = torch.randn(9 * C, F, generator=g) / (9 * C) ** 0.5
+    out = ops.conv_tc(xf.to(dev), coarse.neighbours(ls, mode=1), ops.k_major(W.to(dev))).cpu().numpy()
+    rows = O.im2row(tc.neighbours(tab, mode=1), xf.numpy()).astype(np.float64)
+    _check(out, rows, W.double().numpy(), np.zeros((tc.size(), F)), 2e-5)
+    xc = torch.randn(tc.size(), F, generator=g)
+    W2 = torch.randn(9 * F, C, generator=g) / (9 * F) ** 0.5
+    out = ops.conv_tc(xc.to(dev), ls.neighbours(coarse, mode=2), ops.k_major(W2.to(dev))).cpu().numpy()
+    rows = O.im2row(tab.neighbours(tc, mode=2), xc.numpy()).astype(np.float64)
+    _check(out, rows, W2.double().numpy(), np.zeros((tab.size(), C)), 2e-5)
