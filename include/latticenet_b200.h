@@ -109,18 +109,22 @@ int ltn_gn_apply(const float* x, int V, const int* v_dev, int C, int G, const do
 /* ConvLatticeModule / CoarsenLattice / FinefyLattice (lattice_modules.py:440,573; models.py:353,398) and
  * the dense layers around them (GnRelu1x1, Conv1x1, nn.Linear, GRU/LSTM gate GEMMs) WITHOUT the [V,9C]
  * im2row buffer:  out[v,f] = sum_{s<S} sum_c act(x[nbr[v,s],c]) * W[s*C+c, f] (+bias[f]) (+res[v,f]),
- * act(t) = relu?(t*a_scale[c] + a_shift[c]) on present rows, 0 for absent ones (nbr < 0 or >= Vx).
- * wt = W transposed, [F, S*C] (K-major);  nbr == NULL means S = 1, identity rows.  vx_dev / vq_dev
- * (nullable): device-side row counts.  C % 32 == 0, C <= 256, F % 16 == 0, ldo % 4 == 0.
+ * act(t) = relu?(t*scale[c] + shift[c]) on present rows, 0 for absent ones (nbr < 0 or >= Vx).
+ * The per-channel affine is either explicit (a_scale/a_shift) or the GroupNorm of x folded from its
+ * statistics gn_sums [G,2] (ltn_gn_stats or a previous call's out_sums), gn_gamma/gn_beta [C].
+ * out_sums (nullable, caller-zeroed) [out_groups,2]: GroupNorm statistics of the OUTPUT, accumulated in
+ * the epilogue for the next layer.  wt_hi / wt_lo: ltn_split_tf32 copies of the weight, [F, S*C]
+ * (wt_lo may be NULL when passes == 1).  nbr == NULL means S = 1, identity rows.  vx_dev / vq_dev
+ * (nullable): device-side row counts.  C % 32 == 0 (C <= 256 with an affine), F % 16 == 0, ldo % 4 == 0.
  * passes = 3: fp32-parity (hi/lo split, three tf32 tensor-core passes); passes = 1: plain TF32. */
 int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int Vq, const int* vq_dev, int C, int S,
-                const float* wt, int F, const float* a_scale, const float* a_shift, int relu, const float* bias,
-                const float* res, float* out, int ldo, int passes, void* stream);
-/* [K,F] -> [F,K] (builds wt from a reference-layout conv weight) */
-int ltn_transpose(const float* in, int K, int F, float* out, void* stream);
-/* GroupNorm sums [G,2] (ltn_gn_stats) -> per-channel scale/shift for ltn_conv_tc's folded GN */
-int ltn_gn_affine(const double* sums, int V, const int* v_dev, int C, int G, const float* gamma, const float* beta,
-                  float eps, float* scale, float* shift, void* stream);
+                const float* wt_hi, const float* wt_lo, int F, const float* a_scale, const float* a_shift,
+                const double* gn_sums, const float* gn_gamma, const float* gn_beta, float gn_eps, int gn_groups, int relu,
+                const float* bias, const float* res, float* out, int ldo, double* out_sums, int out_groups, int passes,
+                void* stream);
+/* weight -> K-major [F,K] tf32 split: hi = round-to-tf32(w), lo = w - hi.  transposed_in = 0: w is the
+ * reference's conv layout [K,F] (lattice_modules.py:291); 1: w is [F,K] (nn.Linear) */
+int ltn_split_tf32(const float* w, int K, int F, int transposed_in, float* wt_hi, float* wt_lo, void* stream);
 
 /* ---- temporal fusion (seq_lattice/lattice_modules.py:17-339) ------------------------------------ */
 

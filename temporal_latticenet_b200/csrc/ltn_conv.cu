@@ -16,24 +16,32 @@
 //    the product is issued as hi*hi + lo*hi + hi*lo -- three tensor-core passes, ~2^-21 relative error per
 //    product, i.e. fp32-class results (the reference ran these GEMMs in fp32 / TF32 cuBLAS).
 //    PASSES = 1 is the single-pass TF32 variant (reported separately, never the default).
-//  * operands are staged K-major in 128-byte-swizzled shared memory (the UMMA canonical layout) by
-//    4 producer warps: one thread per tile row gathers 128 contiguous bytes of one vertex row (a whole
-//    cache line, L2-resident), applies the folded GroupNorm+ReLU, splits hi/lo and writes 16-byte chunks
-//    at chunk ^ (row & 7).  A multi-stage mbarrier ring decouples them from the single MMA-issuing
-//    thread; tcgen05.commit releases stages and finally hands the accumulator to the epilogue.
-//  * epilogue: tcgen05.ld 32x32b (thread = row, 32 columns at a time) -> + bias, + residual -> 128-byte
-//    row-segment stores.
+//  * operands are staged K-major in 128-byte-swizzled shared memory (the UMMA canonical layout).
+//    A (gathered, data dependent): two producer warpgroups take alternate k-blocks; one thread per tile
+//    row loads 128 contiguous bytes of one vertex row (a whole cache line, L2-resident), applies the
+//    folded GroupNorm+ReLU, splits hi/lo and writes 16-byte chunks at chunk ^ (row & 7).
+//    B (weights, dense): pre-split hi/lo copies streamed by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B)
+//    from a dedicated warp, completing on the same mbarrier as the A producers.
+//    A multi-stage mbarrier ring decouples both from the single MMA-issuing thread; tcgen05.commit
+//    releases stages and finally hands the accumulator to the epilogue.
+//  * epilogue (8 warps): tcgen05.ld 32x32b (thread = row, 32 columns at a time) -> + bias, + residual ->
+//    128-byte row-segment stores; optionally the GroupNorm statistics of the OUTPUT (sum, sum of squares
+//    per group) are reduced here with a warp reduce-scatter, so the next layer's normalisation costs no
+//    extra pass over the data.
 //  * sizes that only the device knows (vertex counts after hash insertion) are read from device
 //    memory (vq_dev / vx_dev), so the launch needs no host synchronisation.
 #include "ltn_common.cuh"
+#include <cuda.h>
 
 namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 8;          // tf32: 32 bytes per MMA
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 160;      // 4 producer/epilogue warps + 1 MMA warp
+constexpr int kGroups = 2;         // producer warpgroups (alternate k-blocks)
+constexpr int kGroupThreads = 128;
+constexpr int kMmaWarp = 8, kTmaWarp = 9;
+constexpr int kThreads = 320;      // 8 producer/epilogue warps + MMA warp + TMA warp
 constexpr int kMaxStages = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -43,6 +51,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -58,6 +69,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// TMA: 2-D tile global -> swizzled shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
 
 // D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -99,40 +116,50 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// warp reduce-scatter: lane L ends with sum over the 32 lanes of v[L]  (31 shuffles instead of 160)
+__device__ __forceinline__ float warp_column_sums(float* v, int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            float send = upper ? v[j] : v[j + off];
+            float keep = upper ? v[j + off] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
 struct ConvParams {
     const float* x;        // [Vx, C]
     const int* nbr;        // [Vq, S] or null (identity, S = 1)
-    const float* wt;       // [F, S*C]  K-major weights
-    const float* a_scale;  // [C] or null
-    const float* a_shift;  // [C] or null
+    const float* a_scale;  // [C] or null   explicit per-channel affine on A
+    const float* a_shift;
+    const double* gn_sums; // [G,2] or null GroupNorm of x folded into A: sums over the Vx rows
+    const float* gn_gamma;
+    const float* gn_beta;
     const float* bias;     // [F] or null
     const float* res;      // [Vq, F] or null
     float* out;            // [Vq, ldo]
+    double* out_sums;      // [Gout,2] or null: accumulate GroupNorm statistics of the output
     const int* vq_dev;     // device-side row counts (nullable)
     const int* vx_dev;
+    float gn_eps;
+    int gn_cpg, out_cpg;
     int Vq, Vx, C, S, F, ldo, relu;
     int n_tile;            // output channels per CTA (<= 256, multiple of 16)
     int stages;
 };
 
-// store 8 fp32 of one operand row as hi (and lo) parts at swizzled 16-byte chunks 2j, 2j+1
 template <int PASSES>
-__device__ __forceinline__ void stage_chunk(uint8_t* hi_row, uint8_t* lo_row, int row, int chunk, float4 v) {
-    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-    int off = ((chunk ^ (row & 7)) << 4);
-    *reinterpret_cast<float4*>(hi_row + off) = h;
-    if (PASSES == 3) {
-        float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        *reinterpret_cast<float4*>(lo_row + off) = l;
-    }
-}
-
-template <int PASSES>
-__global__ void __launch_bounds__(kThreads, 1) k_conv_tc(ConvParams p) {
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_affine[2 * 256];
+    __shared__ float s_colsum[2 * 256];
 
     const int Vq = p.vq_dev ? min(p.Vq, __ldg(p.vq_dev)) : p.Vq;
     const int Vx = p.vx_dev ? min(p.Vx, __ldg(p.vx_dev)) : p.Vx;
@@ -159,127 +186,159 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(ConvParams p) {
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(bar_full + 8 * s, kProducerThreads);
+            mbar_init(bar_full + 8 * s, kGroupThreads + 1);   // 128 gather threads + the TMA thread's expect_tx arrive
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    if (p.a_scale)
+    const bool affine = (p.a_scale != nullptr) || (p.gn_sums != nullptr);
+    if (p.gn_sums) {
+        // GroupNorm folded to scale = rstd*gamma, shift = beta - mean*scale (statistics over all Vx rows)
+        for (int c = tid; c < p.C; c += kThreads) {
+            const int g = c / p.gn_cpg;
+            const double n = (double)Vx * p.gn_cpg;
+            const double mean = p.gn_sums[2 * g] / n;
+            double var = p.gn_sums[2 * g + 1] / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)p.gn_eps));
+            const float a = rstd * (p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.0f);
+            s_affine[c] = a;
+            s_affine[256 + c] = (p.gn_beta ? __ldg(p.gn_beta + c) : 0.0f) - (float)mean * a;
+        }
+    } else if (p.a_scale) {
         for (int c = tid; c < p.C; c += kThreads) {
             s_affine[c] = __ldg(p.a_scale + c);
             s_affine[256 + c] = __ldg(p.a_shift + c);
         }
+    }
+    if (p.out_sums)
+        for (int c = tid; c < 2 * 256; c += kThreads) s_colsum[c] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp < 4) {
-        // ===================== producers: gather A rows, stream B rows =====================
-        const int r = tid;                 // tile row
-        const int v = row0 + r;            // query vertex
-        const bool row_ok = v < Vq;
-        const bool affine = p.a_scale != nullptr;
-        int stage = 0;
-        uint32_t phase = 0;
-        int src = -1, cur_slot = -1;
-        for (int kb = 0; kb < num_kb; ++kb) {
+    if (warp < 8) {
+        // ===================== producers: gather A rows (two warpgroups, alternate k-blocks) ==========
+        // Quarter-warp per row: 8 lanes fetch the 8 16-byte chunks of one 128-byte row segment, so one
+        // warp-wide LDG.128 touches 4 whole cache lines (not 32 partial ones) and the swizzled stores of a
+        // quarter-warp cover one 128-byte shared-memory row conflict-free.  A warp owns 32 tile rows and
+        // walks them 4 at a time (8 loads in flight per thread); the loads of the NEXT k-block are issued
+        // before the current one is converted, so the L2 latency of the gather overlaps the staging work.
+        const int group = warp >> 2;
+        const int wrow0 = (warp & 3) * 32;         // first tile row of this warp
+        const int chunk = lane & 7, sub = lane >> 3;
+        const int my_v = row0 + wrow0 + lane;      // the row whose neighbour id this lane looks up
+        int cur_slot = -1, src_lane = -1;
+        float4 nxt[8];
+        int nxt_src[8];
+        auto issue = [&](int kb) {
             const int slot = kb / kb_per_slot;
             const int c0 = (kb - slot * kb_per_slot) * kBlockK;
             if (slot != cur_slot) {
                 cur_slot = slot;
-                src = -1;
-                if (row_ok) {
-                    src = p.nbr ? __ldg(p.nbr + (size_t)v * p.S + slot) : v;
-                    if (src >= Vx) src = -1;
+                src_lane = -1;
+                if (my_v < Vq) {
+                    src_lane = p.nbr ? __ldg(p.nbr + (size_t)my_v * p.S + slot) : my_v;
+                    if (src_lane >= Vx) src_lane = -1;
                 }
             }
-            // issue the global loads before waiting for the stage to drain
-            float4 a[8];
-            if (src >= 0) {
-                const float4* g = reinterpret_cast<const float4*>(p.x + (size_t)src * p.C + c0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = __ldg(g + j);
+            for (int j = 0; j < 8; ++j) {
+                const int s = __shfl_sync(0xffffffffu, src_lane, sub + 4 * j);
+                nxt_src[j] = s;
+                if (s >= 0) nxt[j] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)s * p.C + c0) + chunk);
             }
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            uint8_t* st = smem + (size_t)stage * stage_bytes;
-            uint8_t* a_hi = st + r * 128;
-            uint8_t* a_lo = a_hi + a_bytes;
-            if (src >= 0) {
+        };
+        if (group < num_kb) issue(group);
+        for (int kb = group; kb < num_kb; kb += kGroups) {
+            const int stage = kb % stages;
+            const uint32_t parity = ((kb / stages) & 1) ^ 1;
+            const int c0 = (kb % kb_per_slot) * kBlockK;
+            float4 cur[8];
+            int cur_src[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 t = a[j];
+            for (int j = 0; j < 8; ++j) { cur[j] = nxt[j]; cur_src[j] = nxt_src[j]; }
+            if (kb + kGroups < num_kb) issue(kb + kGroups);
+            mbar_wait(bar_empty + 8 * stage, parity);
+            uint8_t* a_hi0 = smem + (size_t)stage * stage_bytes;
+            const float* sc = s_affine + c0 + 4 * chunk;
+            const float* sh = sc + 256;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = wrow0 + sub + 4 * j;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cur_src[j] >= 0) {
+                    t = cur[j];
                     if (affine) {
-                        const float* sc = s_affine + c0 + 4 * j;
-                        const float* sh = sc + 256;
                         t.x = fmaf(t.x, sc[0], sh[0]); t.y = fmaf(t.y, sc[1], sh[1]);
                         t.z = fmaf(t.z, sc[2], sh[2]); t.w = fmaf(t.w, sc[3], sh[3]);
                     }
                     if (p.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-                    stage_chunk<PASSES>(a_hi, a_lo, r, j, t);
                 }
-            } else {
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    *reinterpret_cast<float4*>(a_hi + (j << 4)) = z;
-                    if (PASSES == 3) *reinterpret_cast<float4*>(a_lo + (j << 4)) = z;
-                }
-            }
-            // B: weight rows n0 + r (and + 128) of this k-block
-            uint8_t* b_base = st + (PASSES == 3 ? 2 : 1) * a_bytes;
-            for (int n = r; n < p.n_tile; n += kProducerThreads) {
-                uint8_t* b_hi = b_base + n * 128;
-                uint8_t* b_lo = b_hi + b_bytes;
-                if (n < N) {
-                    const float4* g = reinterpret_cast<const float4*>(p.wt + (size_t)(n0 + n) * K + (size_t)kb * kBlockK);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) stage_chunk<PASSES>(b_hi, b_lo, n, j, __ldg(g + j));
-                }
+                const float4 h = make_float4(tf32_hi(t.x), tf32_hi(t.y), tf32_hi(t.z), tf32_hi(t.w));
+                uint8_t* dst = a_hi0 + r * 128 + ((chunk ^ (r & 7)) << 4);
+                *reinterpret_cast<float4*>(dst) = h;
+                if (PASSES == 3)
+                    *reinterpret_cast<float4*>(dst + a_bytes) = make_float4(t.x - h.x, t.y - h.y, t.z - h.z, t.w - h.w);
             }
             fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(bar_full + 8 * stage);
-            if (++stage == stages) { stage = 0; phase ^= 1; }
         }
 
-        // ===================== epilogue: TMEM -> registers -> global =====================
+        // ===================== epilogue: TMEM -> registers -> global (8 warps, alternate 32-column chunks) ====
         mbar_wait(bar_acc, 0);
         tc_fence_after();
-        const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int cb = 0; cb < N; cb += 32) {
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const int er = (warp & 3) * 32 + lane;     // accumulator row = TMEM lane
+        const int ev = row0 + er;
+        const bool erow_ok = ev < Vq;
+        for (int cb = group * 32; cb < N; cb += 64) {
             float acc[32];
             tmem_ld32(t_lane + (uint32_t)cb, acc);   // warp-collective: executed by every lane
-            if (row_ok) {
-                const int ncol = min(32, N - cb);
-                float* o = p.out + (size_t)v * p.ldo + n0 + cb;
-                const float* rs = p.res ? p.res + (size_t)v * p.F + n0 + cb : nullptr;
-                const float* bs = p.bias ? p.bias + n0 + cb : nullptr;
+            const int ncol = min(32, N - cb);
+            const float* rs = (p.res && erow_ok) ? p.res + (size_t)ev * p.F + n0 + cb : nullptr;
+            const float* bs = p.bias ? p.bias + n0 + cb : nullptr;
+            float* o = p.out + (size_t)ev * p.ldo + n0 + cb;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (j < ncol) {   // N is a multiple of 16, so whole float4 groups
-                        float4 t = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-                        if (bs) { float4 b = __ldg(reinterpret_cast<const float4*>(bs + j)); t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w; }
-                        if (rs) { float4 q = __ldg(reinterpret_cast<const float4*>(rs + j)); t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
-                        *reinterpret_cast<float4*>(o + j) = t;
-                    }
+            for (int j = 0; j < 32; j += 4) {
+                if (j < ncol) {   // N is a multiple of 16, so whole float4 groups
+                    float4 t = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                    if (bs) { float4 b = __ldg(reinterpret_cast<const float4*>(bs + j)); t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w; }
+                    if (rs) { float4 q = __ldg(reinterpret_cast<const float4*>(rs + j)); t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+                    if (erow_ok) *reinterpret_cast<float4*>(o + j) = t;
+                    acc[j] = t.x; acc[j + 1] = t.y; acc[j + 2] = t.z; acc[j + 3] = t.w;
+                }
+            }
+            if (p.out_sums) {
+                float sq[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (!erow_ok || j >= ncol) acc[j] = 0.f;
+                    sq[j] = acc[j] * acc[j];
+                }
+                const float cs = warp_column_sums(acc, lane);
+                const float cq = warp_column_sums(sq, lane);
+                if (lane < ncol) {
+                    atomicAdd(&s_colsum[cb + lane], cs);
+                    atomicAdd(&s_colsum[256 + cb + lane], cq);
                 }
             }
         }
         tc_fence_before();
-    } else {
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer: one thread =====================
         if (lane == 0) {
             // instruction descriptor: D = F32 [4,6), A = B = TF32 [7,10) [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-            int stage = 0;
-            uint32_t phase = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(bar_full + 8 * stage, phase);
+                const int stage = kb % stages;
+                mbar_wait(bar_full + 8 * stage, (kb / stages) & 1);
                 tc_fence_after();
                 const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + a_bytes);
@@ -295,68 +354,113 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(ConvParams p) {
                     }
                 }
                 umma_commit(bar_empty + 8 * stage);   // stage reusable once these MMAs have read it
-                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
             umma_commit(bar_acc);                      // accumulator complete -> epilogue
         }
         __syncwarp();
+    } else {
+        // ===================== TMA warp: stream the pre-split weight tiles =====================
+        if (lane == 0) {
+            const uint32_t tx = (PASSES == 3 ? 2u : 1u) * b_bytes;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int stage = kb % stages;
+                mbar_wait(bar_empty + 8 * stage, ((kb / stages) & 1) ^ 1);
+                const uint32_t bb = smem_u32(smem + (size_t)stage * stage_bytes) + (PASSES == 3 ? 2 : 1) * a_bytes;
+                mbar_arrive_expect_tx(bar_full + 8 * stage, tx);
+                tma_load_2d(bb, &map_hi, bar_full + 8 * stage, kb * kBlockK, n0);
+                if (PASSES == 3) tma_load_2d(bb + b_bytes, &map_lo, bar_full + 8 * stage, kb * kBlockK, n0);
+            }
+        }
+        __syncwarp();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
     }
+    if (p.out_sums) {
+        // per-CTA column sums -> group sums -> one double atomic per group
+        const int g0 = n0 / p.out_cpg, g1 = (n0 + N) / p.out_cpg;   // n_tile is a multiple of out_cpg (checked on the host)
+        for (int g = g0 + tid; g < g1; g += kThreads) {
+            float a = 0.f, b = 0.f;
+            for (int c = g * p.out_cpg - n0; c < (g + 1) * p.out_cpg - n0; ++c) { a += s_colsum[c]; b += s_colsum[256 + c]; }
+            atomicAdd(p.out_sums + 2 * g, (double)a);
+            atomicAdd(p.out_sums + 2 * g + 1, (double)b);
+        }
+    }
 }
 
-// [K, F] row-major -> [F, K] row-major (K-major operand for the tensor core)
-__global__ void k_transpose(const float* __restrict__ in, int K, int F, float* __restrict__ out) {
+// weight -> K-major ([F,K]) copies split for the fp32-parity passes: hi = round-to-tf32(w), lo = w - hi.
+// transposed_in = 0: w is [K,F] (reference conv layout);  1: w is [F,K] already (nn.Linear layout)
+__global__ void k_split_tf32(const float* __restrict__ in, int K, int F, int transposed_in, float* __restrict__ hi,
+                             float* __restrict__ lo) {
     __shared__ float tile[32][33];
     int k0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        int k = k0 + i, f = f0 + threadIdx.x;
-        tile[i][threadIdx.x] = (k < K && f < F) ? in[(size_t)k * F + f] : 0.f;
+        if (transposed_in) {
+            int f = f0 + i, k = k0 + threadIdx.x;
+            tile[threadIdx.x][i] = (k < K && f < F) ? in[(size_t)f * K + k] : 0.f;
+        } else {
+            int k = k0 + i, f = f0 + threadIdx.x;
+            tile[i][threadIdx.x] = (k < K && f < F) ? in[(size_t)k * F + f] : 0.f;
+        }
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int f = f0 + i, k = k0 + threadIdx.x;
-        if (f < F && k < K) out[(size_t)f * K + k] = tile[threadIdx.x][i];
+        if (f < F && k < K) {
+            float w = tile[threadIdx.x][i];
+            float h = tf32_hi(w);
+            hi[(size_t)f * K + k] = h;
+            if (lo) lo[(size_t)f * K + k] = w - h;
+        }
     }
 }
 
-// GroupNorm statistics -> per-channel affine: scale = rstd*gamma, shift = beta - mean*scale
-__global__ void k_gn_affine(const double* __restrict__ sums, int V, const int* __restrict__ v_dev, int C, int cpg,
-                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                            float* __restrict__ scale, float* __restrict__ shift) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    if (v_dev) V = min(V, *v_dev);
-    int g = c / cpg;
-    double n = (double)V * cpg;
-    double mean = sums[2 * g] / n;
-    double var = sums[2 * g + 1] / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    float a = rstd * (gamma ? gamma[c] : 1.0f);
-    scale[c] = a;
-    shift[c] = (beta ? beta[c] : 0.0f) - (float)mean * a;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// [F rows, K cols] fp32, box = 32 (K) x n_tile (rows), 128-byte swizzle; rows beyond F read as zeros
+int lcm16(int a) {
+    int x = 16, y = a;
+    while (y) { int t = x % y; x = y; y = t; }
+    return 16 / x * a;
+}
+
+int make_weight_map(CUtensorMap* map, const float* w, int F, int K, int n_tile) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return -4;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)F};
+    cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)n_tile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -5;
 }
 
 }  // namespace
 
 extern "C" {
 
-int ltn_transpose(const float* in, int K, int F, float* out, void* stream) {
+int ltn_split_tf32(const float* w, int K, int F, int transposed_in, float* wt_hi, float* wt_lo, void* stream) {
     if (K <= 0 || F <= 0) return 0;
     dim3 grid((K + 31) / 32, (F + 31) / 32), block(32, 8);
-    k_transpose<<<grid, block, 0, (cudaStream_t)stream>>>(in, K, F, out);
-    LTN_CHECK_LAUNCH();
-    return 0;
-}
-
-int ltn_gn_affine(const double* sums, int V, const int* v_dev, int C, int G, const float* gamma, const float* beta,
-                  float eps, float* scale, float* shift, void* stream) {
-    if (G <= 0 || C % G) return -2;
-    k_gn_affine<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, V, v_dev, C, C / G, gamma, beta, eps, scale, shift);
+    k_split_tf32<<<grid, block, 0, (cudaStream_t)stream>>>(w, K, F, transposed_in, wt_hi, wt_lo);
     LTN_CHECK_LAUNCH();
     return 0;
 }
@@ -364,34 +468,54 @@ int ltn_gn_affine(const double* sums, int V, const int* v_dev, int C, int G, con
 // Fused gather + GEMM on tcgen05.  See the header of this file; the C ABI is documented in
 // include/latticenet_b200.h.  passes: 3 = fp32-parity split (default), 1 = single-pass TF32.
 int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int Vq, const int* vq_dev, int C, int S,
-                const float* wt, int F, const float* a_scale, const float* a_shift, int relu, const float* bias,
-                const float* res, float* out, int ldo, int passes, void* stream) {
+                const float* wt_hi, const float* wt_lo, int F, const float* a_scale, const float* a_shift,
+                const double* gn_sums, const float* gn_gamma, const float* gn_beta, float gn_eps, int gn_groups, int relu,
+                const float* bias, const float* res, float* out, int ldo, double* out_sums, int out_groups, int passes,
+                void* stream) {
     if (Vq <= 0) return 0;
-    if (C <= 0 || C % kBlockK || C > 256 || F <= 0 || F % 16 || S < 1 || (passes != 1 && passes != 3) || ldo % 4) return -2;
-    if ((a_scale == nullptr) != (a_shift == nullptr)) return -2;
+    const bool affine = a_scale || gn_sums;
+    if (C <= 0 || C % kBlockK || (affine && C > 256) || F <= 0 || F % 16 || S < 1 || (passes != 1 && passes != 3) || ldo % 4) return -2;
+    if ((a_scale == nullptr) != (a_shift == nullptr) || (a_scale && gn_sums)) return -2;
+    if (gn_sums && (gn_groups <= 0 || C % gn_groups)) return -2;
+    if (out_sums && (out_groups <= 0 || F % out_groups)) return -2;
+    if (passes == 3 && !wt_lo) return -2;
     ConvParams p;
-    p.x = x; p.nbr = nbr; p.wt = wt; p.a_scale = a_scale; p.a_shift = a_shift; p.bias = bias; p.res = res; p.out = out;
+    p.x = x; p.nbr = nbr; p.a_scale = a_scale; p.a_shift = a_shift; p.gn_sums = gn_sums; p.gn_gamma = gn_gamma; p.gn_beta = gn_beta;
+    p.gn_eps = gn_eps; p.gn_cpg = gn_sums ? C / gn_groups : 1; p.bias = bias; p.res = res; p.out = out; p.out_sums = out_sums;
+    p.out_cpg = out_sums ? F / out_groups : 1;
     p.vq_dev = vq_dev; p.vx_dev = vx_dev; p.Vq = Vq; p.Vx = Vx; p.C = C; p.S = nbr ? S : 1; p.F = F; p.ldo = ldo; p.relu = relu;
-    // output channels per CTA: all of them when they fit one accumulator, else the fewest equal tiles
+    // Output channels per CTA.  All of them when they fit one accumulator (A rows gathered once); when that
+    // leaves SMs idle (few row tiles) the channels are split further so the grid covers the 148 SMs.
+    const int row_tiles = (Vq + kBlockM - 1) / kBlockM;
+    const int unit = out_sums ? lcm16(p.out_cpg) : 16;   // tiles start on GroupNorm group boundaries
     int ny = (F + 255) / 256;
-    int n_tile = ((F + ny - 1) / ny + 15) / 16 * 16;
+    while (row_tiles * ny < 148 && (F / (ny + 1)) >= 32) ++ny;
+    int n_tile = ((F + ny - 1) / ny + unit - 1) / unit * unit;
+    if (n_tile > 256) n_tile = 256 / unit * unit;
+    if (n_tile <= 0) return -2;
+    ny = (F + n_tile - 1) / n_tile;
     p.n_tile = n_tile;
     size_t stage_bytes = (size_t)(passes == 3 ? 2 : 1) * (kBlockM * 128 + (size_t)n_tile * 128);
-    int stages = (int)((200 * 1024) / stage_bytes);
+    int stages = (int)((196 * 1024) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return -3;
     p.stages = stages;
     size_t smem = stage_bytes * stages + 1024;
-    dim3 grid((Vq + kBlockM - 1) / kBlockM, ny);
+    alignas(64) CUtensorMap map_hi, map_lo;
+    int rc = make_weight_map(&map_hi, wt_hi, F, p.S * C, n_tile);
+    if (rc) return rc;
+    rc = make_weight_map(&map_lo, passes == 3 ? wt_lo : wt_hi, F, p.S * C, n_tile);
+    if (rc) return rc;
+    dim3 grid(row_tiles, ny);
     cudaError_t e;
     if (passes == 3) {
         e = cudaFuncSetAttribute(k_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        k_conv_tc<3><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+        k_conv_tc<3><<<grid, kThreads, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
     } else {
         e = cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        k_conv_tc<1><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+        k_conv_tc<1><<<grid, kThreads, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
     }
     LTN_CHECK_LAUNCH();
     return 0;

@@ -54,40 +54,53 @@ k_scatter_add(const float* __restrict__ src, const int* __restrict__ idx, int R,
     }
 }
 
-// GroupNorm statistics over x [V,C]: per group sum and sum of squares in double.
-// One warp walks rows; each lane owns channels lane, lane+32, ... (C <= 512).
-constexpr int kMaxCPL = 16;
+// GroupNorm statistics over x [V,C]: per group sum and sum of squares in double (var = E[x^2]-mean^2
+// must not cancel in fp32).  One thread per float4 column and row phase: a warp reads whole rows with
+// 128-bit loads; per-thread double partials -> shared per-channel sums -> one global atomic per group
+// and block.  Grid = at most one block per SM.
 __global__ void __launch_bounds__(kThreads)
 k_gn_stats(const float* __restrict__ x, int V, const int* __restrict__ v_dev, int C, int cpg, double* sums /*[G,2]*/) {
-    extern __shared__ double sh[];  // [G*2]
+    extern __shared__ double sh[];  // [C][2]
     if (v_dev) V = min(V, *v_dev);
-    const int G = C / cpg;
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.0;
+    const int C4 = C >> 2;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.0;
     __syncthreads();
-    int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    double s1[kMaxCPL], s2[kMaxCPL];  // double accumulators: var = E[x^2]-mean^2 must not cancel in fp32
+    const int rpb = blockDim.x / C4;                      // rows in flight per block
+    const int col = threadIdx.x % C4, rph = threadIdx.x / C4;
+    const int rows_per_block = (V + gridDim.x - 1) / gridDim.x;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(V, r0 + rows_per_block);
+    if (rph < rpb) {
+        double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+        // fp32 partials over short runs, folded into double every 8 rows
+        for (int r = r0 + rph; r < r1; r += rpb * 8) {
+            float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < kMaxCPL; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
-    int row = blockIdx.x * wpb + (threadIdx.x >> 5);
-    int stride = gridDim.x * wpb;
-    for (int v = row; v < V; v += stride) {
-#pragma unroll
-        for (int j = 0; j < kMaxCPL; ++j) {
-            int c = lane + 32 * j;
-            if (c < C) {
-                double a = (double)__ldg(x + (size_t)v * C + c);
-                s1[j] += a;
-                s2[j] = fma(a, a, s2[j]);
+            for (int u = 0; u < 8; ++u) {
+                int rr = r + u * rpb;
+                if (rr < r1) {
+                    float4 a = __ldg(reinterpret_cast<const float4*>(x + (size_t)rr * C) + col);
+                    f1[0] += a.x; f1[1] += a.y; f1[2] += a.z; f1[3] += a.w;
+                    f2[0] = fmaf(a.x, a.x, f2[0]); f2[1] = fmaf(a.y, a.y, f2[1]);
+                    f2[2] = fmaf(a.z, a.z, f2[2]); f2[3] = fmaf(a.w, a.w, f2[3]);
+                }
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s1[q] += (double)f1[q]; s2[q] += (double)f2[q]; }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            atomicAdd(&sh[2 * (col * 4 + q)], s1[q]);
+            atomicAdd(&sh[2 * (col * 4 + q) + 1], s2[q]);
         }
     }
-#pragma unroll
-    for (int j = 0; j < kMaxCPL; ++j) {
-        int c = lane + 32 * j;
-        if (c < C) { atomicAdd(&sh[2 * (c / cpg)], s1[j]); atomicAdd(&sh[2 * (c / cpg) + 1], s2[j]); }
-    }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(sums + i, sh[i]);
+    const int G = C / cpg;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double a = 0.0, b = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += sh[2 * c]; b += sh[2 * c + 1]; }
+        atomicAdd(sums + 2 * g, a);
+        atomicAdd(sums + 2 * g + 1, b);
+    }
 }
 
 // y = relu?( (x - mean_g) * rstd_g * gamma_c + beta_c ), folded into per-channel a_c, b_c in smem
@@ -151,18 +164,18 @@ int ltn_scatter_add(const float* src, const int* idx, int R, int C, float* out, 
     return 0;
 }
 
-// sums: [G,2] double, zeroed here
+// sums: [G,2] double, zeroed here.  C % 4 == 0, C/4 <= 256
 int ltn_gn_stats(const float* x, int V, const int* v_dev, int C, int G, double* sums, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (G <= 0 || C % G || C > 32 * kMaxCPL) return -2;
+    if (G <= 0 || C % G || C % 4 || C / 4 > kThreads) return -2;
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)G, st);
     if (e != cudaSuccess) return (int)e;
     if (V <= 0) return 0;
-    int wpb = kThreads / 32;
-    int blocks = (V + wpb * 16 - 1) / (wpb * 16);
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    int rpb = kThreads / (C / 4);
+    int blocks = (V + rpb * 8 - 1) / (rpb * 8);
+    if (blocks > 148) blocks = 148;
     if (blocks < 1) blocks = 1;
-    k_gn_stats<<<blocks, kThreads, sizeof(double) * 2 * G, st>>>(x, V, v_dev, C, C / G, sums);
+    k_gn_stats<<<blocks, kThreads, sizeof(double) * 2 * C, st>>>(x, V, v_dev, C, C / G, sums);
     LTN_CHECK_LAUNCH();
     return 0;
 }

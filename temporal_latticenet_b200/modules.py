@@ -63,6 +63,14 @@ class GroupNormLatticeModule(torch.nn.Module):
         ls.set_values(lv)
         return lv, ls
 
+    def affine(self, lv):
+        """(sums, gamma, beta, eps) of this normalisation on `lv`, folded into the next fused kernel's gather"""
+        return (ops.gn_sums(lv, self.groups), self.gn.weight.detach(), self.gn.bias.detach(), self.gn.eps)
+
+    def fusable(self, lv, nr_out):
+        return (ops.no_grad_path(lv, self.gn.weight) and ops.conv_tc_supported(lv.shape[1], nr_out) and lv.shape[0] > 0
+                and self.gn.weight is not None)
+
 
 class Gn(torch.nn.Module):
     def __init__(self):
@@ -94,12 +102,18 @@ class GnRelu1x1(torch.nn.Module):
         self.out_channels, self.use_bias = out_channels, bias
         self.norm, self.linear = None, None
 
-    def forward(self, lv, ls):
+    def forward(self, lv, ls, res=None):
         if self.norm is None:
             self.norm = GroupNormLatticeModule(lv.shape[1])
             self.linear = _linear(lv.shape[1], self.out_channels, self.use_bias)
-        lv, ls = self.norm(lv, ls, relu=True)
-        lv = ops.linear(lv, self.linear.weight, self.linear.bias)
+        if self.norm.fusable(lv, self.out_channels):  # GN + ReLU folded into the tensor-core kernel's A operand
+            lv = ops.conv_tc(lv, None, ops.k_major(self.linear.weight, transposed=True), gn=self.norm.affine(lv), relu=True,
+                             bias=None if self.linear.bias is None else self.linear.bias.detach(), res=res)
+        else:
+            lv, ls = self.norm(lv, ls, relu=True)
+            lv = ops.linear(lv, self.linear.weight, self.linear.bias)
+            if res is not None:
+                lv = lv + res
         ls.set_values(lv)
         return lv, ls
 
@@ -112,17 +126,30 @@ class ConvLatticeModule(torch.nn.Module):
         self.nr_filters, self.neighbourhood_size, self.dilation, self.use_bias = nr_filters, neighbourhood_size, dilation, bias
         self.weight, self.bias = None, None
 
-    def forward(self, lv, ls):
-        ls.set_values(lv)
+    def create(self, lv, ls):
         if self.weight is None:
             rows = ls.get_filter_extent(self.neighbourhood_size) * lv.shape[1]
             self.weight = _conv_weight(rows, self.nr_filters)
             if self.use_bias:
                 b = 1.0 / math.sqrt(rows)
                 self.bias = torch.nn.Parameter(torch.empty(self.nr_filters, device=_dev()).uniform_(-b, b))
-        out = F_.ConvIm2RowLattice.apply(lv, ls, self.weight, self.dilation)
-        if self.bias is not None:
-            out = out + self.bias
+
+    def forward(self, lv, ls, pre=None, res=None):
+        """pre = (sums, gamma, beta, eps): a GroupNorm+ReLU to fold into the gather (fused inference path only);
+        res: residual added in the epilogue."""
+        ls.set_values(lv)
+        self.create(lv, ls)
+        if ops.no_grad_path(lv, self.weight) and ops.conv_tc_supported(lv.shape[1], self.nr_filters) and lv.shape[0] > 0:
+            out = ops.conv_tc(lv, ls.neighbours(dilation=self.dilation), ops.k_major(self.weight),
+                              gn=pre, relu=pre is not None, bias=None if self.bias is None else self.bias.detach(), res=res)
+        else:
+            if pre is not None:
+                raise RuntimeError("a folded GroupNorm needs the fused kernel")
+            out = F_.ConvIm2RowLattice.apply(lv, ls, self.weight, self.dilation)
+            if self.bias is not None:
+                out = out + self.bias
+            if res is not None:
+                out = out + res
         ls.set_values(out)
         return out, ls
 
@@ -132,11 +159,18 @@ class CoarsenLatticeModule(torch.nn.Module):
         super().__init__()
         self.nr_filters, self.weight = nr_filters, None
 
-    def forward(self, lv, ls):
+    def forward(self, lv, ls, pre=None):
         ls.set_values(lv)
         if self.weight is None:
             self.weight = _conv_weight(ls.get_filter_extent(1) * lv.shape[1], self.nr_filters)
-        out, coarse = F_.CoarsenLattice.apply(lv, ls, self.weight)
+        if ops.no_grad_path(lv, self.weight) and ops.conv_tc_supported(lv.shape[1], self.nr_filters) and lv.shape[0] > 0:
+            coarse = ls.create_coarse_verts()
+            out = ops.conv_tc(lv, coarse.neighbours(ls, mode=1), ops.k_major(self.weight),
+                              gn=pre, relu=pre is not None)
+        else:
+            if pre is not None:
+                raise RuntimeError("a folded GroupNorm needs the fused kernel")
+            out, coarse = F_.CoarsenLattice.apply(lv, ls, self.weight)
         coarse.set_values(out)
         return out, coarse
 
@@ -146,11 +180,18 @@ class FinefyLatticeModule(torch.nn.Module):
         super().__init__()
         self.nr_filters, self.weight = nr_filters, None
 
-    def forward(self, lv_coarse, ls_coarse, ls_fine):
+    def forward(self, lv_coarse, ls_coarse, ls_fine, pre=None):
         ls_coarse.set_values(lv_coarse)
         if self.weight is None:
             self.weight = _conv_weight(ls_coarse.get_filter_extent(1) * lv_coarse.shape[1], self.nr_filters)
-        out = F_.FinefyLattice.apply(lv_coarse, ls_coarse, ls_fine, self.weight)
+        if (ops.no_grad_path(lv_coarse, self.weight) and ops.conv_tc_supported(lv_coarse.shape[1], self.nr_filters)
+                and lv_coarse.shape[0] > 0):
+            out = ops.conv_tc(lv_coarse, ls_fine.neighbours(ls_coarse, mode=2), ops.k_major(self.weight),
+                              gn=pre, relu=pre is not None)
+        else:
+            if pre is not None:
+                raise RuntimeError("a folded GroupNorm needs the fused kernel")
+            out = F_.FinefyLattice.apply(lv_coarse, ls_coarse, ls_fine, self.weight)
         ls_fine.set_values(out)
         return out, ls_fine
 
@@ -162,13 +203,15 @@ class GnReluConv(torch.nn.Module):
         self.conv = ConvLatticeModule(nr_filters, 1, dilation, bias)
         self.drop = torch.nn.Dropout(0.2) if with_dropout else None
 
-    def forward(self, lv, ls):
+    def forward(self, lv, ls, res=None):
         if self.norm is None:
             self.norm = GroupNormLatticeModule(lv.shape[1])
+        if self.norm.fusable(lv, self.conv.nr_filters) and (self.drop is None or not self.training):
+            return self.conv(lv, ls, pre=self.norm.affine(lv), res=res)
         lv, ls = self.norm(lv, ls, relu=True)
         if self.drop is not None:
             lv = self.drop(lv)
-        return self.conv(lv, ls)
+        return self.conv(lv, ls, res=res)
 
 
 class GnReluCoarsen(torch.nn.Module):
@@ -182,6 +225,8 @@ class GnReluCoarsen(torch.nn.Module):
     def forward(self, lv, ls):
         if self.norm is None:
             self.norm = GroupNormLatticeModule(lv.shape[1])
+        if self.norm.fusable(lv, self.coarse.nr_filters):
+            return self.coarse(lv, ls, pre=self.norm.affine(lv))
         lv, ls = self.norm(lv, ls, relu=True)
         return self.coarse(lv, ls)
 
@@ -197,6 +242,8 @@ class GnReluFinefy(torch.nn.Module):
     def forward(self, lv_coarse, ls_coarse, ls_fine):
         if self.norm is None:
             self.norm = GroupNormLatticeModule(lv_coarse.shape[1])
+        if self.norm.fusable(lv_coarse, self.fine.nr_filters):
+            return self.fine(lv_coarse, ls_coarse, ls_fine, pre=self.norm.affine(lv_coarse))
         lv_coarse, ls_coarse = self.norm(lv_coarse, ls_coarse, relu=True)
         return self.fine(lv_coarse, ls_coarse, ls_fine)
 
@@ -212,8 +259,7 @@ class ResnetBlock(torch.nn.Module):
     def forward(self, lv, ls):
         skip = lv
         lv, ls = self.conv1(lv, ls)
-        lv, ls = self.conv2(lv, ls)
-        lv = lv + skip
+        lv, ls = self.conv2(lv, ls, res=skip)  # identity added in the conv epilogue
         ls.set_values(lv)
         return lv, ls
 
@@ -231,8 +277,7 @@ class BottleneckBlock(torch.nn.Module):
         skip = lv
         lv, ls = self.contract(lv, ls)
         lv, ls = self.conv(lv, ls)
-        lv, ls = self.expand(lv, ls)
-        lv = lv + skip
+        lv, ls = self.expand(lv, ls, res=skip)
         ls.set_values(lv)
         return lv, ls
 

@@ -12,8 +12,20 @@ def matmul(a, b):
     return torch.mm(a, b)
 
 
-def linear(x, weight, bias=None):
-    return torch.nn.functional.linear(x, weight, bias)
+def no_grad_path(*tensors):
+    """True when nothing will be differentiated: the fused inference kernels may be used."""
+    return not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors))
+
+
+def linear(x, weight, bias=None, relu_out=False):
+    """x @ weight.T + bias.  Without autograd and for tensor-core friendly shapes this is the S = 1 case
+    of the fused tcgen05 kernel (nn.Linear weights are K-major already); otherwise cuBLAS fp32."""
+    if (x.dim() == 2 and x.is_cuda and no_grad_path(x, weight, bias) and conv_tc_supported(x.shape[1], weight.shape[0], False)
+            and x.shape[0] > 0):
+        out = conv_tc(x, None, k_major(weight, transposed=True), bias=None if bias is None else bias.detach())
+        return torch.relu_(out) if relu_out else out
+    out = torch.nn.functional.linear(x, weight, bias)
+    return torch.relu(out) if relu_out else out
 
 
 def gn_groups(nr_channels):
@@ -122,42 +134,66 @@ _WT_CACHE = {}
 TC_PASSES = 3  # 3 = fp32-parity split (default); 1 = single-pass TF32 (stated separately wherever used)
 
 
-def conv_tc_supported(C, F):
-    return C % 32 == 0 and 0 < C <= 256 and F % 16 == 0 and F > 0
+def conv_tc_supported(C, F, folded_norm=True):
+    return C % 32 == 0 and C > 0 and (C <= 256 or not folded_norm) and F % 16 == 0 and F > 0
 
 
 def k_major(weight, transposed=False):
-    """K-major ([F,K]) fp32 copy of a weight for the tensor-core kernel, cached per parameter version.
-    `transposed=True`: the tensor already is [F,K] (nn.Linear layout) and is used as it is."""
-    if transposed:
-        return weight.detach().contiguous()
-    key = id(weight)
+    """(hi, lo): K-major ([F,K]) tf32-split copies of a weight for the tensor-core kernel, cached per
+    parameter version.  `transposed=True`: the tensor is [F,K] already (nn.Linear layout)."""
+    key = (id(weight), bool(transposed))
     hit = _WT_CACHE.get(key)
     ver = weight._version
     if hit is not None and hit[0] == ver and hit[1] == weight.data_ptr():
         return hit[2]
-    K, F = weight.shape
-    wt = torch.empty(F, K, dtype=torch.float32, device=weight.device)
-    _lib.check(_lib.load().ltn_transpose(_lib.ptr(weight.detach().contiguous()), K, F, _lib.ptr(wt), _lib.stream()), "ltn_transpose")
-    _WT_CACHE[key] = (ver, weight.data_ptr(), wt)
-    return wt
+    w = weight.detach().contiguous().float()
+    if transposed:
+        F, K = w.shape
+    else:
+        K, F = w.shape
+    hi = torch.empty(F, K, dtype=torch.float32, device=w.device)
+    lo = torch.empty(F, K, dtype=torch.float32, device=w.device)
+    _lib.check(_lib.load().ltn_split_tf32(_lib.ptr(w), K, F, 1 if transposed else 0, _lib.ptr(hi), _lib.ptr(lo), _lib.stream()),
+               "ltn_split_tf32")
+    _WT_CACHE[key] = (ver, weight.data_ptr(), (hi, lo))
+    if len(_WT_CACHE) > 4096:
+        _WT_CACHE.clear()
+    return hi, lo
 
 
-def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, relu=False, bias=None, res=None, out=None, passes=None):
-    """out[v,:] = sum_s act(x[nbr[v,s],:]) @ W[s] (+bias) (+res); nbr None = plain row-wise GEMM.
-    wt is the K-major weight [F, S*C]."""
+def gn_sums(x, groups):
+    """[G,2] double: per-group sum and sum of squares of x [V,C] (GroupNorm over [1,C,V])"""
     x = x.contiguous()
+    sums = torch.empty(groups, 2, dtype=torch.float64, device=x.device)
+    _lib.check(_lib.load().ltn_gn_stats(_lib.ptr(x), x.shape[0], None, x.shape[1], groups, _lib.ptr(sums), _lib.stream()),
+               "ltn_gn_stats")
+    return sums
+
+
+def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, gn=None, relu=False, bias=None, res=None, out=None,
+            out_sums=None, passes=None):
+    """out[v,:] = sum_s act(x[nbr[v,s],:]) @ W[s] (+bias) (+res); nbr None = plain row-wise GEMM.
+    wt = k_major(weight).  gn = (sums [G,2], gamma, beta, eps): GroupNorm of x folded into the gather.
+    out_sums [Gout,2] (zeroed): receives the GroupNorm statistics of the output."""
+    x = x.contiguous()
+    hi, lo = wt
     C = x.shape[1]
     S = 1 if nbr is None else nbr.shape[1]
-    F = wt.shape[0]
-    if wt.shape[1] != S * C:
-        raise RuntimeError("weight is [%d,%d], expected [%d,%d]" % (wt.shape[0], wt.shape[1], F, S * C))
+    F = hi.shape[0]
+    if hi.shape[1] != S * C:
+        raise RuntimeError("weight is [%d,%d], expected [%d,%d]" % (hi.shape[0], hi.shape[1], F, S * C))
     Vq = (x.shape[0] if nbr is None else nbr.shape[0]) if nr_rows is None else nr_rows
     if out is None:
         out = torch.empty(Vq, F, dtype=torch.float32, device=x.device)
     p = _lib.ptr
-    rc = _lib.load().ltn_conv_tc(p(x), x.shape[0], None, p(nbr), Vq, None, C, S, p(wt), F, p(a_scale), p(a_shift),
-                                 1 if relu else 0, p(bias), p(res), p(out), out.stride(0), TC_PASSES if passes is None else passes,
-                                 _lib.stream())
+    g_sums = g_gamma = g_beta = None
+    g_eps, g_groups = 0.0, 0
+    if gn is not None:
+        g_sums, g_gamma, g_beta, g_eps = gn
+        g_groups = g_sums.shape[0]
+    rc = _lib.load().ltn_conv_tc(p(x), x.shape[0], None, p(nbr), Vq, None, C, S, p(hi), p(lo), F, p(a_scale), p(a_shift),
+                                 p(g_sums), p(g_gamma), p(g_beta), float(g_eps), int(g_groups), 1 if relu else 0, p(bias), p(res),
+                                 p(out), out.stride(0), p(out_sums), 0 if out_sums is None else out_sums.shape[0],
+                                 TC_PASSES if passes is None else passes, _lib.stream())
     _lib.check(rc, "ltn_conv_tc")
     return out

@@ -108,3 +108,34 @@ def test_cross_level_tables(dev, lattice):
     out = ops.conv_tc(xc.to(dev), ls.neighbours(coarse, mode=2), ops.k_major(W2.to(dev))).cpu().numpy()
     rows = O.im2row(tab.neighbours(tc, mode=2), xc.numpy()).astype(np.float64)
     _check(out, rows, W2.double().numpy(), np.zeros((tab.size(), C)), 2e-5)
+
+
+@pytest.mark.parametrize("C,F", [(64, 64), (192, 192), (128, 256)])
+def test_groupnorm_folded_from_sums_and_output_statistics(dev, lattice, C, F):
+    """GN(x)+ReLU folded into the gather from [G,2] sums, and the epilogue's statistics of the output
+    (what the next layer's GroupNorm needs) against float64."""
+    from temporal_latticenet_b200 import ops
+    ls, tab = lattice
+    V = tab.size()
+    g = torch.Generator().manual_seed(C + F)
+    x = torch.randn(V, C, generator=g) * 2 + 0.5
+    W = torch.randn(9 * C, F, generator=g) / (9 * C) ** 0.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    G, Gout = ops.gn_groups(C), ops.gn_groups(F)
+    xn = torch.relu(torch.nn.functional.group_norm(x.double().t().unsqueeze(0), G, gamma.double(), beta.double(), 1e-5).squeeze(0).t())
+    rows = O.im2row(tab.neighbours(), xn.float().numpy()).astype(np.float64)
+    xd = x.to(dev)
+    sums = ops.gn_sums(xd, G)
+    out_sums = torch.zeros(Gout, 2, dtype=torch.float64, device=dev)
+    out = ops.conv_tc(xd, ls.neighbours(), ops.k_major(W.to(dev)), gn=(sums, gamma.to(dev), beta.to(dev), 1e-5), relu=True,
+                      out_sums=out_sums).cpu().numpy()
+    _check(out, rows, W.double().numpy(), np.zeros((V, F)), 1e-4)   # + the normalisation's own fp32 rounding
+    cpg = F // Gout
+    o64 = out.astype(np.float64).reshape(V, Gout, cpg)
+    want = np.stack([o64.sum((0, 2)), (o64 ** 2).sum((0, 2))], 1)
+    got = out_sums.cpu().numpy()
+    np.testing.assert_allclose(got[:, 1], want[:, 1], rtol=1e-5)
+    np.testing.assert_allclose(got[:, 0], want[:, 0], rtol=1e-4, atol=1e-3 * np.sqrt(want[:, 1]).max())
+    # gn_stats kernel itself
+    s64 = x.double().reshape(V, G, C // G)
+    np.testing.assert_allclose(sums.cpu().numpy(), np.stack([s64.sum((0, 2)).numpy(), (s64 ** 2).sum((0, 2)).numpy()], 1), rtol=1e-6, atol=1e-6)

@@ -138,7 +138,7 @@ def test_training_step_gradients_match_oracle_autograd(tmp_path):
     with torch.no_grad():
         window_loss()  # lazy parameters
     model.load_state_dict(seeded_state({k: tuple(v.shape) for k, v in model.state_dict().items()}))
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-3, amsgrad=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-3, amsgrad=True)
     loss0 = window_loss()
     opt.zero_grad()
     loss0.backward()
