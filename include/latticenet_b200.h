@@ -126,6 +126,15 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
  * reference's conv layout [K,F] (lattice_modules.py:291); 1: w is [F,K] (nn.Linear) */
 int ltn_split_tf32(const float* w, int K, int F, int transposed_in, float* wt_hi, float* wt_lo, void* stream);
 
+/* PointNetSeqModule front end (lattice_modules.py:448-530) fused: MLP 4->16->32->64 per distributed row,
+ * segmented max per vertex (+arg-max), barycentric weight of the winning row (quirk Q3), concatenation
+ * and the min-4-rows mask.  rows [R, 5] = ltn_distribute's output, idx [R]; w*/b*: nn.Linear weights
+ * [out,in] / biases; packed [V,64] u64 scratch; vert_acc: ltn_distribute's accumulator; min_rows = 4
+ * (0 = no mask, the early max-pool variant); out [V,128].  r_dev / v_dev (nullable): device-side sizes. */
+int ltn_pointnet(const float* rows, int width, const int* idx, int R, const int* r_dev, const float* w1, const float* b1,
+                 const float* w2, const float* b2, const float* w3, const float* b3, int V, const int* v_dev,
+                 unsigned long long* packed, const double* vert_acc, int min_rows, float* out, void* stream);
+
 /* ---- temporal fusion (seq_lattice/lattice_modules.py:17-339) ------------------------------------ */
 
 /* GRUModule.forward pointwise stage (lattice_modules.py:58-63); rows >= Vh are the zero padding */

@@ -58,6 +58,10 @@ class PointNetSeq(torch.nn.Module):
     def forward(self, ls, distributed, indices):
         if self.last_conv is None:
             self._create(distributed.shape[1] - 1, distributed.device)
+        if (ops.no_grad_path(distributed, self.layers[0].weight) and self.layer_widths == [16, 32, 64]
+                and distributed.shape[1] == 5 and distributed.shape[0] > 0):
+            red = self._fused_front(ls, distributed, indices)
+            return self._fuse_and_conv(red, ls)
         bary = distributed[:, -1]
         x = distributed[:, :-1]
         for i, lin in enumerate(self.layers):
@@ -75,6 +79,25 @@ class PointNetSeq(torch.nn.Module):
         if self.fusion_kind != "maxpool":
             few = ls.rows_per_vertex(V) < _MIN_POINTS_PER_VERTEX
             red = red.masked_fill(few.unsqueeze(1), 0.0)
+        return self._fuse_and_conv(red, ls)
+
+    def _fused_front(self, ls, distributed, indices):
+        """MLP + segmented max + arg-max barycentric gather + concat + min-rows mask in two kernels
+        (csrc/ltn_pointnet.cu); inference only"""
+        from . import _lib
+        V, R = ls.nr_lattice_vertices(), distributed.shape[0]
+        dev = distributed.device
+        packed = torch.empty(V, 64, dtype=torch.int64, device=dev)
+        red = torch.empty(V, 128, dtype=torch.float32, device=dev)
+        p = _lib.ptr
+        l1, l2, l3 = self.layers
+        _lib.check(_lib.load().ltn_pointnet(p(distributed), 5, p(indices), R, None, p(l1.weight.detach()), p(l1.bias.detach()),
+                                            p(l2.weight.detach()), p(l2.bias.detach()), p(l3.weight.detach()), p(l3.bias.detach()),
+                                            V, None, p(packed), p(ls._vert_acc), 0 if self.fusion_kind == "maxpool" else
+                                            _MIN_POINTS_PER_VERTEX, p(red), _lib.stream()), "ltn_pointnet")
+        return red
+
+    def _fuse_and_conv(self, red, ls):
         ls.set_values(red)
         if self.fusion_kind == "maxpool":
             half = red.shape[1] // 2

@@ -65,7 +65,7 @@ class GroupNormLatticeModule(torch.nn.Module):
 
     def affine(self, lv):
         """(sums, gamma, beta, eps) of this normalisation on `lv`, folded into the next fused kernel's gather"""
-        return (ops.gn_sums(lv, self.groups), self.gn.weight.detach(), self.gn.bias.detach(), self.gn.eps)
+        return (ops.sums_of(lv, self.groups), self.gn.weight.detach(), self.gn.bias.detach(), self.gn.eps)
 
     def fusable(self, lv, nr_out):
         return (ops.no_grad_path(lv, self.gn.weight) and ops.conv_tc_supported(lv.shape[1], nr_out) and lv.shape[0] > 0
@@ -108,7 +108,8 @@ class GnRelu1x1(torch.nn.Module):
             self.linear = _linear(lv.shape[1], self.out_channels, self.use_bias)
         if self.norm.fusable(lv, self.out_channels):  # GN + ReLU folded into the tensor-core kernel's A operand
             lv = ops.conv_tc(lv, None, ops.k_major(self.linear.weight, transposed=True), gn=self.norm.affine(lv), relu=True,
-                             bias=None if self.linear.bias is None else self.linear.bias.detach(), res=res)
+                             bias=None if self.linear.bias is None else self.linear.bias.detach(), res=res,
+                             out_sums=ops.new_sums(self.out_channels, lv.device))
         else:
             lv, ls = self.norm(lv, ls, relu=True)
             lv = ops.linear(lv, self.linear.weight, self.linear.bias)
@@ -141,7 +142,8 @@ class ConvLatticeModule(torch.nn.Module):
         self.create(lv, ls)
         if ops.no_grad_path(lv, self.weight) and ops.conv_tc_supported(lv.shape[1], self.nr_filters) and lv.shape[0] > 0:
             out = ops.conv_tc(lv, ls.neighbours(dilation=self.dilation), ops.k_major(self.weight),
-                              gn=pre, relu=pre is not None, bias=None if self.bias is None else self.bias.detach(), res=res)
+                              gn=pre, relu=pre is not None, bias=None if self.bias is None else self.bias.detach(), res=res,
+                              out_sums=ops.new_sums(self.nr_filters, lv.device))
         else:
             if pre is not None:
                 raise RuntimeError("a folded GroupNorm needs the fused kernel")
@@ -166,7 +168,7 @@ class CoarsenLatticeModule(torch.nn.Module):
         if ops.no_grad_path(lv, self.weight) and ops.conv_tc_supported(lv.shape[1], self.nr_filters) and lv.shape[0] > 0:
             coarse = ls.create_coarse_verts()
             out = ops.conv_tc(lv, coarse.neighbours(ls, mode=1), ops.k_major(self.weight),
-                              gn=pre, relu=pre is not None)
+                              gn=pre, relu=pre is not None, out_sums=ops.new_sums(self.nr_filters, lv.device))
         else:
             if pre is not None:
                 raise RuntimeError("a folded GroupNorm needs the fused kernel")

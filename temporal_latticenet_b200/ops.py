@@ -1,5 +1,7 @@
 """Dense / reduction primitives shared by the lattice modules: fp32 matmul, GroupNorm(+ReLU) over
 lattice vertices, segmented max / add / mean.  GPU only."""
+import weakref
+
 import torch
 from torch.autograd import Function
 
@@ -144,7 +146,8 @@ def k_major(weight, transposed=False):
     key = (id(weight), bool(transposed))
     hit = _WT_CACHE.get(key)
     ver = weight._version
-    if hit is not None and hit[0] == ver and hit[1] == weight.data_ptr():
+    # the weak reference guards against a recycled id(): only the very same live tensor object hits
+    if hit is not None and hit[0] == ver and hit[1]() is weight and hit[3] == weight.data_ptr():
         return hit[2]
     w = weight.detach().contiguous().float()
     if transposed:
@@ -155,9 +158,10 @@ def k_major(weight, transposed=False):
     lo = torch.empty(F, K, dtype=torch.float32, device=w.device)
     _lib.check(_lib.load().ltn_split_tf32(_lib.ptr(w), K, F, 1 if transposed else 0, _lib.ptr(hi), _lib.ptr(lo), _lib.stream()),
                "ltn_split_tf32")
-    _WT_CACHE[key] = (ver, weight.data_ptr(), (hi, lo))
-    if len(_WT_CACHE) > 4096:
-        _WT_CACHE.clear()
+    if len(_WT_CACHE) > 1024:
+        for k in [k for k, v in _WT_CACHE.items() if v[1]() is None]:
+            del _WT_CACHE[k]
+    _WT_CACHE[key] = (ver, weakref.ref(weight), (hi, lo), weight.data_ptr())
     return hi, lo
 
 
@@ -196,4 +200,19 @@ def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, gn=None, relu=
                                  p(out), out.stride(0), p(out_sums), 0 if out_sums is None else out_sums.shape[0],
                                  TC_PASSES if passes is None else passes, _lib.stream())
     _lib.check(rc, "ltn_conv_tc")
+    if out_sums is not None:
+        out._ltn_gn_sums = out_sums   # travels with the tensor to the next layer's GroupNorm
     return out
+
+
+def new_sums(nr_channels, device):
+    """zeroed [G,2] accumulator for the epilogue statistics of a layer with `nr_channels` outputs"""
+    return torch.zeros(gn_groups(nr_channels), 2, dtype=torch.float64, device=device)
+
+
+def sums_of(x, groups):
+    """GroupNorm statistics of x: the ones its producing kernel left behind, else one pass over x"""
+    s = getattr(x, "_ltn_gn_sums", None)
+    if s is not None and s.shape[0] == groups:
+        return s
+    return gn_sums(x, groups)
