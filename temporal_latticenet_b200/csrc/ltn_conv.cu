@@ -186,7 +186,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(bar_full + 8 * s, kGroupThreads + 1);   // 128 gather threads + the TMA thread's expect_tx arrive
+            mbar_init(bar_full + 8 * s, kGroupThreads / 32 + 1);   // one arrive per gather warp + the TMA thread's expect_tx arrive
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
@@ -235,9 +235,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         const int chunk = lane & 7, sub = lane >> 3;
         const int my_v = row0 + wrow0 + lane;      // the row whose neighbour id this lane looks up
         int cur_slot = -1, src_lane = -1;
-        float4 nxt[8];
-        int nxt_src[8];
-        auto issue = [&](int kb) {
+        float4 buf[2][8];      // two register buffers, used with compile-time indices (loop unrolled by 2)
+        int bsrc[2][8];
+        auto issue = [&](int kb, float4* dst, int* dsrc) {
             const int slot = kb / kb_per_slot;
             const int c0 = (kb - slot * kb_per_slot) * kBlockK;
             if (slot != cur_slot) {
@@ -251,21 +251,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int s = __shfl_sync(0xffffffffu, src_lane, sub + 4 * j);
-                nxt_src[j] = s;
-                if (s >= 0) nxt[j] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)s * p.C + c0) + chunk);
+                dsrc[j] = s;
+                if (s >= 0) dst[j] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)s * p.C + c0) + chunk);
             }
         };
-        if (group < num_kb) issue(group);
-        for (int kb = group; kb < num_kb; kb += kGroups) {
+        auto consume = [&](int kb, const float4* cur, const int* cur_src) {
             const int stage = kb % stages;
             const uint32_t parity = ((kb / stages) & 1) ^ 1;
             const int c0 = (kb % kb_per_slot) * kBlockK;
-            float4 cur[8];
-            int cur_src[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { cur[j] = nxt[j]; cur_src[j] = nxt_src[j]; }
-            if (kb + kGroups < num_kb) issue(kb + kGroups);
-            mbar_wait(bar_empty + 8 * stage, parity);
+            if (lane == 0) mbar_wait(bar_empty + 8 * stage, parity);   // one waiter per warp
+            __syncwarp();
             uint8_t* a_hi0 = smem + (size_t)stage * stage_bytes;
             const float* sc = s_affine + c0 + 4 * chunk;
             const float* sh = sc + 256;
@@ -288,7 +283,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
                     *reinterpret_cast<float4*>(dst + a_bytes) = make_float4(t.x - h.x, t.y - h.y, t.z - h.z, t.w - h.w);
             }
             fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
-            mbar_arrive(bar_full + 8 * stage);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * stage);   // one arrival per warp, not 32 serialised ones
+        };
+        // software pipeline: the loads of the next k-block are in flight while the current one is staged
+        if (group < num_kb) issue(group, buf[0], bsrc[0]);
+        for (int kb = group; kb < num_kb; kb += 2 * kGroups) {
+            const int kb1 = kb + kGroups, kb2 = kb + 2 * kGroups;
+            if (kb1 < num_kb) issue(kb1, buf[1], bsrc[1]);
+            consume(kb, buf[0], bsrc[0]);
+            if (kb1 < num_kb) {
+                if (kb2 < num_kb) issue(kb2, buf[0], bsrc[0]);
+                consume(kb1, buf[1], bsrc[1]);
+            }
         }
 
         // ===================== epilogue: TMEM -> registers -> global (8 warps, alternate 32-column chunks) ====
@@ -485,11 +492,12 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     p.out_cpg = out_sums ? F / out_groups : 1;
     p.vq_dev = vq_dev; p.vx_dev = vx_dev; p.Vq = Vq; p.Vx = Vx; p.C = C; p.S = nbr ? S : 1; p.F = F; p.ldo = ldo; p.relu = relu;
     // Output channels per CTA.  All of them when they fit one accumulator (A rows gathered once); when that
-    // leaves SMs idle (few row tiles) the channels are split further so the grid covers the 148 SMs.
+    // leaves SMs idle (few row tiles) the channels are split further, but never beyond ONE wave of 148 CTAs
+    // (one CTA per SM: a second, partly filled wave would cost a whole extra tile time).
     const int row_tiles = (Vq + kBlockM - 1) / kBlockM;
     const int unit = out_sums ? lcm16(p.out_cpg) : 16;   // tiles start on GroupNorm group boundaries
     int ny = (F + 255) / 256;
-    while (row_tiles * ny < 148 && (F / (ny + 1)) >= 32) ++ny;
+    while (row_tiles * (ny + 1) <= 148 && (F / (ny + 1)) >= 32) ++ny;
     int n_tile = ((F + ny - 1) / ny + unit - 1) / unit * unit;
     if (n_tile > 256) n_tile = 256 / unit * unit;
     if (n_tile <= 0) return -2;
