@@ -178,6 +178,55 @@ class Probe:
         return out
 
 
+def run_train(args, rank, world, dev, devw, windows_np, lib, seeded_state):
+    """BASELINE config 4: the same 4-frame gru-gru-aflow-gru window as a TRAINING step (BPTT through the 4
+    frames, 0.5 Lovasz + 0.5 NLL, AdamW amsgrad), data-parallel over the ranks with one flattened
+    gradient all-reduce per step."""
+    import torch
+    import torch.distributed as dist
+    from temporal_latticenet_b200 import synthetic
+    from temporal_latticenet_b200.train import WindowTrainer
+    targets = [torch.from_numpy(synthetic.labels(w[-1][0].shape[0], NR_CLASSES, seed=i)).to(dev) for i, w in enumerate(windows_np)]
+    tr = WindowTrainer(CFG, NR_CLASSES, dev)
+    tr.materialise(devw[0], targets[0], seeded_state)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for i in range(max(args.warmup, 3)):
+        tr.step(devw[i % len(devw)], targets[i % len(devw)])
+    clocks = Clocks(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        clocks.start()
+    barrier()
+    l0 = lib.ltn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = tr.step(devw[i % len(devw)], targets[i % len(devw)])
+    e1.record()
+    barrier()
+    launches = lib.ltn_launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+    if rank == 0:
+        nparams = sum(p.numel() for p in tr.model.parameters())
+        print(json.dumps({"metric": "4-frame scans/sec (training step)", "value": FRAMES * args.steps * world / (ms * 1e-3), "unit": UNIT,
+                          "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "config4: same window, training step (BPTT, 0.5 Lovasz + 0.5 NLL, AdamW amsgrad), "
+                                                 "data-parallel over windows, one flattened gradient all-reduce per step",
+                                     "parameters": nparams, "allreduce_bytes_per_step": 4 * nparams,
+                                     "l2": "activations of a 4-frame window exceed L2"},
+                          "gpu_launches": int(launches), "clocks": clk, "final_loss": float(loss)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +236,8 @@ def main():
     ap.add_argument("--windows", type=int, default=2, help="distinct synthetic windows cycled through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="add a per-entry-point time breakdown (extra untimed pass)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer = BASELINE config 3 (headline); train = config 4 (BPTT + AdamW + NCCL gradient all-reduce)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -216,6 +267,8 @@ def main():
     devw = [[(p.to(dev), v.to(dev)) for p, v in w] for w in host]
     pts = [int(p.shape[0]) for p, _ in windows_np[0]]
 
+    if args.mode == "train":
+        return run_train(args, rank, world, dev, devw, windows_np, lib, seeded_state)
     runner = WindowRunner(CFG, NR_CLASSES, dev)
     runner.materialise_parameters(devw[0], seeded_state)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -279,10 +332,24 @@ def main():
             if name not in ("ltn_version", "ltn_launch_count"):
                 names[name] = None
     names["ltn_im2row"] = lambda vals, Vvals, vd, nbr, Vq, vqd, C, out, st: float(Vq) * (12 + 40 * C)
+    if args.breakdown:
+        shapes = {}
+
+        def conv_key(*a):  # (x, Vx, vx_dev, nbr, Vq, vq_dev, C, S, wt_hi, wt_lo, F, ...)
+            S = a[7] if a[3] is not None and getattr(a[3], "value", 1) else 1
+            return "conv_tc Vq~%dk C%d S%d F%d" % (round(a[4] / 1000.0), a[6], S, a[10])
+        orig_conv = lib.ltn_conv_tc
+
+        def conv_wrapped(*a):
+            return probe.wrap(conv_key(*a), orig_conv, lambda *b: 2.0 * b[4] * b[6] * (b[7] if b[3] is not None and getattr(b[3], "value", 1) else 1) * b[10])(*a)
+        names.pop("ltn_conv_tc", None)
     originals = {}
     for name, wf in names.items():
         originals[name] = getattr(lib, name)
         setattr(lib, name, probe.wrap(name, originals[name], wf))
+    if args.breakdown:
+        originals["ltn_conv_tc"] = orig_conv
+        lib.ltn_conv_tc = conv_wrapped
     import temporal_latticenet_b200.ops as ops
     mm_orig, lin_orig = ops.matmul, ops.linear
     ops.matmul = probe.wrap("torch.mm(cuBLAS sgemm)", mm_orig, lambda a, b: 2.0 * a.shape[0] * a.shape[1] * b.shape[1])
@@ -333,7 +400,8 @@ def main():
         line["breakdown_ms_per_step"] = {k: v["ms_total"] / min(args.steps, 4) for k, v in
                                          sorted(summ.items(), key=lambda kv: -kv[1]["ms_total"])}
         line["gemm_tflops"] = {k: v["work"] / (v["ms_total"] * 1e-3) / 1e12 for k, v in summ.items()
-                               if k.startswith("torch.") and v["ms_total"] > 0}
+                               if (k.startswith("torch.") or k.startswith("conv_tc")) and v["ms_total"] > 0}
+        line["launches_per_step"] = {k: v["launches"] / min(args.steps, 4) for k, v in summ.items()}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
