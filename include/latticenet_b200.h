@@ -14,6 +14,9 @@
  *  - return value: 0 on success, a cudaError_t (>0) from the launch, or <0 for an argument the
  *    kernels do not support (-2 shape, -3 shared memory);
  *  - no exceptions, no host synchronisation inside any call;
+ *  - sizes only the device knows: wherever a count comes with a nullable `*_dev` companion (n_dev, v_dev,
+ *    vq_dev, vx_dev, vh_dev, r_dev), the kernel uses min(host bound, *dev) -- launches are sized by the host
+ *    bound (a capacity), so whole frames replay from a CUDA graph without any host synchronisation;
  *  - pos_dim is 3 (4 simplex vertices per point, filter extent 9: lattice_modules.py:299,310-311);
  *  - rows are point-major: row = point*4 + r (models.py:452); indices are int32, -1 = absent.
  *
@@ -45,14 +48,14 @@ int ltn_hash_clear(uint64_t* slot_keys, int* slot_ids, int* slot_first, int nslo
  * and number NEW vertices in order of first appearance (append-only ids).  Used for the coarse
  * lattices of GnReluCoarsen (models.py:182,353).  row_slot [4N] and block_sums [ceil(4N/1024)+1]
  * are scratch; row_w [4N] (nullable) receives the barycentric weights. */
-int ltn_insert_points(const float* pos, int N, float sx, float sy, float sz, uint64_t* slot_keys, int* slot_ids,
-                      int* slot_first, int nslots, int* counters, int* keys, int capacity, int* row_slot,
+int ltn_insert_points(const float* pos, int N, const int* n_dev, float sx, float sy, float sz, uint64_t* slot_keys,
+                      int* slot_ids, int* slot_first, int nslots, int* counters, int* keys, int capacity, int* row_slot,
                       float* row_w, int* block_sums, void* stream);
 
 /* DistributeLatticeModule.forward (models.py:62,297-298): rows [4N, 3+val_dim+1] = [xyz, val, bary],
  * idx [4N], w [4N]; subtract_mean != 0 also subtracts the per-vertex mean position from rows[:,0:3].
  * vert_acc [capacity,4] double scratch; afterwards vert_acc[v,3] = number of rows on vertex v. */
-int ltn_distribute(const float* pos, const float* val, int N, int val_dim, float sx, float sy, float sz,
+int ltn_distribute(const float* pos, const float* val, int N, const int* n_dev, int val_dim, float sx, float sy, float sz,
                    uint64_t* slot_keys, int* slot_ids, int* slot_first, int nslots, int* counters, int* keys,
                    int capacity, int* row_slot, int* block_sums, double* vert_acc, float* rows, int* idx, float* w,
                    int subtract_mean, void* stream);
@@ -82,12 +85,14 @@ int ltn_slice(const float* vals, int V, int C, const int* idx, const float* w, i
 int ltn_slice_bwd(const float* grad_out, int N, int C, const int* idx, const float* w, float* grad_vals, int V,
                   void* stream);
 /* GatherLattice inside SliceFastCUDALatticeModule (models.py:232,465): out [N, 4*(C+1)] */
-int ltn_gather(const float* vals, int V, int C, const int* idx, const float* w, int N, float* out, void* stream);
+int ltn_gather(const float* vals, int V, const int* v_dev, int C, const int* idx, const float* w, int N, const int* n_dev,
+               float* out, void* stream);
 int ltn_gather_bwd(const float* grad_out, int N, int C, const int* idx, const float* w, float* grad_vals, int V,
                    void* stream);
 /* SliceClassifyLattice (models.py:465): out [N,K]; sliced [N,C] (nullable) saved for the weight grad */
-int ltn_slice_classify(const float* vals, int V, int C, const int* idx, const float* w, const float* dw, int N,
-                       const float* Wc, const float* bias, int K, float* out, float* sliced, void* stream);
+int ltn_slice_classify(const float* vals, int V, const int* v_dev, int C, const int* idx, const float* w, const float* dw,
+                       int N, const int* n_dev, const float* Wc, const float* bias, int K, float* out, float* sliced,
+                       void* stream);
 int ltn_slice_classify_bwd(const float* grad_logit, const float* vals, int V, int C, const int* idx, const float* w,
                            const float* dw, int N, const float* Wc, int K, float* grad_vals, float* grad_dw,
                            void* stream);
@@ -115,7 +120,7 @@ int ltn_gn_apply(const float* x, int V, const int* v_dev, int C, int G, const do
  * out_sums (nullable, caller-zeroed) [out_groups,2]: GroupNorm statistics of the OUTPUT, accumulated in
  * the epilogue for the next layer.  wt_hi / wt_lo: ltn_split_tf32 copies of the weight, [F, S*C]
  * (wt_lo may be NULL when passes == 1).  nbr == NULL means S = 1, identity rows.  vx_dev / vq_dev
- * (nullable): device-side row counts.  C % 32 == 0 (C <= 256 with an affine), F % 16 == 0, ldo % 4 == 0.
+ * (nullable): device-side row counts.  C % 32 == 0 (C <= 256 with an affine), F % 8 == 0, ldo % 4 == 0.
  * passes = 3: fp32-parity (hi/lo split, three tf32 tensor-core passes); passes = 1: plain TF32. */
 int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int Vq, const int* vq_dev, int C, int S,
                 const float* wt_hi, const float* wt_lo, int F, const float* a_scale, const float* a_shift,
@@ -138,16 +143,16 @@ int ltn_pointnet(const float* rows, int width, const int* idx, int R, const int*
 /* ---- temporal fusion (seq_lattice/lattice_modules.py:17-339) ------------------------------------ */
 
 /* GRUModule.forward pointwise stage (lattice_modules.py:58-63); rows >= Vh are the zero padding */
-int ltn_gru_pointwise(const float* gi, const float* gh, const float* h, const float* b_hh, int V, int Vh, int C,
-                      float* out, void* stream);
+int ltn_gru_pointwise(const float* gi, const float* gh, const float* h, const float* b_hh, int V, int Vh, const int* v_dev,
+                      const int* vh_dev, int C, float* out, void* stream);
 /* LSTMModule.forward pointwise stage with c_prev = 0 (lattice_modules.py:32-37) */
-int ltn_lstm_pointwise(const float* gi, const float* gh, const float* b_hh, int V, int Vh, int C, float* out,
-                       void* stream);
+int ltn_lstm_pointwise(const float* gi, const float* gh, const float* b_hh, int V, int Vh, const int* v_dev,
+                       const int* vh_dev, int C, float* out, void* stream);
 /* CustomKernelConvLatticeIm2RowModule.forward (lattice_modules.py:282-339) fused:
  * out [V,C], weights_out [V,9] (nullable) */
-int ltn_aflow(const float* lv, const float* h, int V, int Vh, int C, const int* nbr, const float* alpha,
-              const float* beta, const float* bias, float pad_value, int use_center, float* out, float* weights_out,
-              void* stream);
+int ltn_aflow(const float* lv, const float* h, int V, int Vh, const int* v_dev, const int* vh_dev, int C, const int* nbr,
+              const float* alpha, const float* beta, const float* bias, float pad_value, int use_center, float* out,
+              float* weights_out, void* stream);
 
 /* library version / build info */
 int ltn_version(void);

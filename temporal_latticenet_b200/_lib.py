@@ -58,7 +58,9 @@ def require_cuda():
 
 
 def stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """raw cudaStream_t of torch's current stream (the C accessor: torch.cuda.current_stream() builds a
+    Python Stream object per call, ~15 us, which adds up over the ~250 launches of a frame)"""
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def ptr(t):
@@ -74,3 +76,31 @@ def ptr(t):
 def check(rc, what):
     if rc != 0:
         raise RuntimeError("%s failed with code %d" % (what, rc))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Static-capacity mode (temporal_latticenet_b200/engine.py): every tensor's row count is a fixed
+# CAPACITY and the true count lives in device memory, so a whole frame can be captured in a CUDA graph.
+# The registry maps a capacity (= shape[0] of the tensors of that row class: points, rows, vertices
+# of each lattice level) to the device int32 holding the live count; kernel wrappers look their row
+# counts up here and pass the pointer as the `*_dev` companion of the host bound.
+# ---------------------------------------------------------------------------------------------------
+_static_rows = {}
+
+
+def set_static_rows(mapping):
+    global _static_rows
+    _static_rows = dict(mapping or {})
+
+
+def static_mode():
+    return bool(_static_rows)
+
+
+def rows_tensor(nr_rows):
+    return _static_rows.get(int(nr_rows))
+
+
+def rows_dev(nr_rows):
+    t = _static_rows.get(int(nr_rows))
+    return None if t is None else ctypes.c_void_p(t.data_ptr())

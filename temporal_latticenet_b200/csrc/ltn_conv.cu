@@ -166,7 +166,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
     const int row0 = blockIdx.x * kBlockM;
     if (row0 >= Vq) return;  // uniform per CTA, before any barrier / TMEM allocation
     const int n0 = blockIdx.y * p.n_tile;
-    const int N = min(p.n_tile, p.F - n0);
+    const int N = min(p.n_tile, p.F - n0);     // valid output channels of this CTA (multiple of 8)
+    const int Nmma = (N + 15) & ~15;           // MMA N (multiple of 16 at M = 128); the extra weight rows are TMA zero fill
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = p.S * p.C;
@@ -182,7 +183,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
 
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]), bar_acc = smem_u32(&bars[2 * kMaxStages]);
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)N) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)Nmma) tmem_cols <<= 1;
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -314,7 +315,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
             float* o = p.out + (size_t)ev * p.ldo + n0 + cb;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                if (j < ncol) {   // N is a multiple of 16, so whole float4 groups
+                if (j < ncol) {   // N is a multiple of 8, so whole float4 groups
                     float4 t = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
                     if (bs) { float4 b = __ldg(reinterpret_cast<const float4*>(bs + j)); t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w; }
                     if (rs) { float4 q = __ldg(reinterpret_cast<const float4*>(rs + j)); t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
@@ -342,7 +343,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         // ===================== MMA issuer: one thread =====================
         if (lane == 0) {
             // instruction descriptor: D = F32 [4,6), A = B = TF32 [7,10) [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nmma >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int stage = kb % stages;
                 mbar_wait(bar_full + 8 * stage, (kb / stages) & 1);
@@ -481,7 +482,7 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
                 void* stream) {
     if (Vq <= 0) return 0;
     const bool affine = a_scale || gn_sums;
-    if (C <= 0 || C % kBlockK || (affine && C > 256) || F <= 0 || F % 16 || S < 1 || (passes != 1 && passes != 3) || ldo % 4) return -2;
+    if (C <= 0 || C % kBlockK || (affine && C > 256) || F <= 0 || F % 8 || S < 1 || (passes != 1 && passes != 3) || ldo % 4) return -2;
     if ((a_scale == nullptr) != (a_shift == nullptr) || (a_scale && gn_sums)) return -2;
     if (gn_sums && (gn_groups <= 0 || C % gn_groups)) return -2;
     if (out_sums && (out_groups <= 0 || F % out_groups)) return -2;

@@ -17,7 +17,10 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 //   r = s(gi_r+gh_r) ; z = s(gi_z+gh_z) ; n = tanh(gi_n + r*gh_n) ; h' = (1-z)*n + z*h
 __global__ void __launch_bounds__(kThreads)
 k_gru_pointwise(const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ h,
-                const float* __restrict__ b_hh, int V, int Vh, int C, float* __restrict__ out) {
+                const float* __restrict__ b_hh, int V, int Vh, const int* __restrict__ v_dev,
+                const int* __restrict__ vh_dev, int C, float* __restrict__ out) {
+    if (v_dev) V = min(V, *v_dev);
+    if (vh_dev) Vh = min(Vh, *vh_dev);
     long long total = (long long)V * C;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         int v = (int)(t / C);
@@ -43,7 +46,9 @@ k_gru_pointwise(const float* __restrict__ gi, const float* __restrict__ gh, cons
 //   c' = s(i)*tanh(g) ; h' = s(o)*tanh(c')
 __global__ void __launch_bounds__(kThreads)
 k_lstm_pointwise(const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ b_hh, int V,
-                 int Vh, int C, float* __restrict__ out) {
+                 int Vh, const int* __restrict__ v_dev, const int* __restrict__ vh_dev, int C, float* __restrict__ out) {
+    if (v_dev) V = min(V, *v_dev);
+    if (vh_dev) Vh = min(Vh, *vh_dev);
     long long total = (long long)V * C;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         int v = (int)(t / C);
@@ -63,12 +68,14 @@ k_lstm_pointwise(const float* __restrict__ gi, const float* __restrict__ gh, con
 // masked.  NaN behaviour of the reference (0/0 when every masked distance is 0, quirk Q5) is kept.
 constexpr int kAflowMaxCPL = 8;  // C <= 256
 __global__ void __launch_bounds__(kThreads)
-k_aflow(const float* __restrict__ lv, const float* __restrict__ h, int V, int Vh, int C,
-        const int* __restrict__ nbr, const float* __restrict__ alpha_p, const float* __restrict__ beta_p,
+k_aflow(const float* __restrict__ lv, const float* __restrict__ h, int V, int Vh, const int* __restrict__ v_dev,
+        const int* __restrict__ vh_dev, int C, const int* __restrict__ nbr, const float* __restrict__ alpha_p, const float* __restrict__ beta_p,
         const float* __restrict__ bias, float pad_value, int use_center, float* __restrict__ out,
         float* __restrict__ weights_out) {
     int lane = threadIdx.x & 31;
     int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (v_dev) V = min(V, *v_dev);
+    if (vh_dev) Vh = min(Vh, *vh_dev);
     if (v >= V) return;
     const float alpha = __ldg(alpha_p), beta = __ldg(beta_p);
     float x[kAflowMaxCPL];
@@ -140,29 +147,31 @@ inline int grid_for(long long work_items, int threads) {
 
 extern "C" {
 
-int ltn_gru_pointwise(const float* gi, const float* gh, const float* h, const float* b_hh, int V, int Vh, int C,
-                      float* out, void* stream) {
+int ltn_gru_pointwise(const float* gi, const float* gh, const float* h, const float* b_hh, int V, int Vh, const int* v_dev,
+                      const int* vh_dev, int C, float* out, void* stream) {
     if (V <= 0) return 0;
-    k_gru_pointwise<<<grid_for((long long)V * C, kThreads), kThreads, 0, (cudaStream_t)stream>>>(gi, gh, h, b_hh, V, Vh, C, out);
+    k_gru_pointwise<<<grid_for((long long)V * C, kThreads), kThreads, 0, (cudaStream_t)stream>>>(gi, gh, h, b_hh, V, Vh, v_dev,
+                                                                                                  vh_dev, C, out);
     LTN_CHECK_LAUNCH();
     return 0;
 }
 
-int ltn_lstm_pointwise(const float* gi, const float* gh, const float* b_hh, int V, int Vh, int C, float* out,
-                       void* stream) {
+int ltn_lstm_pointwise(const float* gi, const float* gh, const float* b_hh, int V, int Vh, const int* v_dev,
+                       const int* vh_dev, int C, float* out, void* stream) {
     if (V <= 0) return 0;
-    k_lstm_pointwise<<<grid_for((long long)V * C, kThreads), kThreads, 0, (cudaStream_t)stream>>>(gi, gh, b_hh, V, Vh, C, out);
+    k_lstm_pointwise<<<grid_for((long long)V * C, kThreads), kThreads, 0, (cudaStream_t)stream>>>(gi, gh, b_hh, V, Vh, v_dev,
+                                                                                                   vh_dev, C, out);
     LTN_CHECK_LAUNCH();
     return 0;
 }
 
-int ltn_aflow(const float* lv, const float* h, int V, int Vh, int C, const int* nbr, const float* alpha,
-              const float* beta, const float* bias, float pad_value, int use_center, float* out, float* weights_out,
-              void* stream) {
+int ltn_aflow(const float* lv, const float* h, int V, int Vh, const int* v_dev, const int* vh_dev, int C, const int* nbr,
+              const float* alpha, const float* beta, const float* bias, float pad_value, int use_center, float* out,
+              float* weights_out, void* stream) {
     if (V <= 0) return 0;
     if (C > 32 * kAflowMaxCPL) return -2;
     k_aflow<<<ltn_blocks((long long)V * 32, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        lv, h, V, Vh, C, nbr, alpha, beta, bias, pad_value, use_center, out, weights_out);
+        lv, h, V, Vh, v_dev, vh_dev, C, nbr, alpha, beta, bias, pad_value, use_center, out, weights_out);
     LTN_CHECK_LAUNCH();
     return 0;
 }

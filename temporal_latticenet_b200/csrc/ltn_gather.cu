@@ -114,8 +114,10 @@ k_slice_bwd(const float* __restrict__ grad_out, int N, int C, const int* __restr
 
 // gather: out[p, r*(C+1) + c] = w*vals[id, c] ; out[p, r*(C+1) + C] = w ; absent -> zeros (conv. U6)
 __global__ void __launch_bounds__(kThreads)
-k_gather(const float* __restrict__ vals, int V, int C, const int* __restrict__ idx, const float* __restrict__ w, int N,
-         float* __restrict__ out) {
+k_gather(const float* __restrict__ vals, int V, const int* __restrict__ v_dev, int C, const int* __restrict__ idx,
+         const float* __restrict__ w, int N, const int* __restrict__ n_dev, float* __restrict__ out) {
+    if (v_dev) V = min(V, *v_dev);
+    if (n_dev) N = min(N, *n_dev);
     const int W1 = C + 1;
     long long total = (long long)N * 4 * W1;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -150,10 +152,13 @@ k_gather_bwd(const float* __restrict__ grad_out, int N, int C, const int* __rest
 //   logit[k]  = b[k] + sum_c Wc[k,c] * s[c]
 // Wc (K x C) is staged in shared memory once per block.
 __global__ void __launch_bounds__(kThreads)
-k_slice_classify(const float* __restrict__ vals, int V, int C, const int* __restrict__ idx,
-                 const float* __restrict__ w, const float* __restrict__ dw, int N, const float* __restrict__ Wc,
-                 const float* __restrict__ bias, int K, float* __restrict__ out, float* __restrict__ sliced) {
+k_slice_classify(const float* __restrict__ vals, int V, const int* __restrict__ v_dev, int C, const int* __restrict__ idx,
+                 const float* __restrict__ w, const float* __restrict__ dw, int N, const int* __restrict__ n_dev,
+                 const float* __restrict__ Wc, const float* __restrict__ bias, int K, float* __restrict__ out,
+                 float* __restrict__ sliced) {
     extern __shared__ float sW[];  // K*C
+    if (v_dev) V = min(V, *v_dev);
+    if (n_dev) N = min(N, *n_dev);
     for (int i = threadIdx.x; i < K * C; i += blockDim.x) sW[i] = __ldg(Wc + i);
     __syncthreads();
     int lane = threadIdx.x & 31;
@@ -293,10 +298,11 @@ int ltn_slice_bwd(const float* grad_out, int N, int C, const int* idx, const flo
     return 0;
 }
 
-int ltn_gather(const float* vals, int V, int C, const int* idx, const float* w, int N, float* out, void* stream) {
+int ltn_gather(const float* vals, int V, const int* v_dev, int C, const int* idx, const float* w, int N, const int* n_dev,
+               float* out, void* stream) {
     if (N <= 0) return 0;
     long long total = (long long)N * 4 * (C + 1);
-    k_gather<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(vals, V, C, idx, w, N, out);
+    k_gather<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(vals, V, v_dev, C, idx, w, N, n_dev, out);
     LTN_CHECK_LAUNCH();
     return 0;
 }
@@ -312,8 +318,9 @@ int ltn_gather_bwd(const float* grad_out, int N, int C, const int* idx, const fl
 }
 
 // sliced (nullable): [N,C] = sum_r (w+dw) vals[id_r] saved for the weight gradient
-int ltn_slice_classify(const float* vals, int V, int C, const int* idx, const float* w, const float* dw, int N,
-                       const float* Wc, const float* bias, int K, float* out, float* sliced, void* stream) {
+int ltn_slice_classify(const float* vals, int V, const int* v_dev, int C, const int* idx, const float* w, const float* dw,
+                       int N, const int* n_dev, const float* Wc, const float* bias, int K, float* out, float* sliced,
+                       void* stream) {
     if (N <= 0) return 0;
     size_t smem = sizeof(float) * (size_t)K * C;
     if (smem > 200 * 1024 || C > 256) return -3;
@@ -321,7 +328,8 @@ int ltn_slice_classify(const float* vals, int V, int C, const int* idx, const fl
     if (e != cudaSuccess) return (int)e;
     int blocks = (int)((N + 7) / 8);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_slice_classify<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(vals, V, C, idx, w, dw, N, Wc, bias, K, out, sliced);
+    k_slice_classify<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(vals, V, v_dev, C, idx, w, dw, N, n_dev, Wc, bias, K, out,
+                                                                       sliced);
     LTN_CHECK_LAUNCH();
     return 0;
 }

@@ -28,9 +28,10 @@ __global__ void k_hash_clear(uint64_t* slot_keys, int* slot_ids, int* slot_first
 
 // one thread per point; 4 dedupe rounds per warp
 __global__ void __launch_bounds__(kThreads)
-k_insert_points(const float* __restrict__ pos, int N, float sx, float sy, float sz, uint64_t* slot_keys,
-                const int* __restrict__ slot_ids, int* slot_first, int nslots, int* counters,
+k_insert_points(const float* __restrict__ pos, int N, const int* __restrict__ n_dev, float sx, float sy, float sz,
+                uint64_t* slot_keys, const int* __restrict__ slot_ids, int* slot_first, int nslots, int* counters,
                 int* __restrict__ row_slot, float* __restrict__ row_w) {
+    if (n_dev) N = min(N, *n_dev);
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = p < N;
     int key[LTN_D1][LTN_D];
@@ -72,9 +73,10 @@ __device__ __forceinline__ int is_first_row(int row, int R, const int* __restric
 }
 
 __global__ void __launch_bounds__(kScanBlock)
-k_number_count(const int* __restrict__ row_slot, int R, const int* __restrict__ slot_ids,
+k_number_count(const int* __restrict__ row_slot, int R, const int* __restrict__ n_dev, const int* __restrict__ slot_ids,
                const int* __restrict__ slot_first, int* __restrict__ block_sums) {
     __shared__ int warp_sums[kScanBlock / 32];
+    if (n_dev) R = min(R, *n_dev * LTN_D1);
     int row = blockIdx.x * kScanBlock + threadIdx.x;
     int f = is_first_row(row, R, row_slot, slot_ids, slot_first);
     unsigned b = __ballot_sync(0xffffffffu, f);
@@ -122,10 +124,11 @@ k_number_scan(int* block_sums, int nblocks, int* counters, int cap) {
 }
 
 __global__ void __launch_bounds__(kScanBlock)
-k_number_assign(const int* __restrict__ row_slot, int R, const uint64_t* __restrict__ slot_keys, int* slot_ids,
-                int* slot_first, const int* __restrict__ block_sums, const int* __restrict__ counters, int cap,
+k_number_assign(const int* __restrict__ row_slot, int R, const int* __restrict__ n_dev, const uint64_t* __restrict__ slot_keys,
+                int* slot_ids, int* slot_first, const int* __restrict__ block_sums, const int* __restrict__ counters, int cap,
                 int4* __restrict__ keys) {
     __shared__ int warp_off[kScanBlock / 32];
+    if (n_dev) R = min(R, *n_dev * LTN_D1);
     int row = blockIdx.x * kScanBlock + threadIdx.x;
     int f = is_first_row(row, R, row_slot, slot_ids, slot_first);
     unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -158,10 +161,11 @@ k_number_assign(const int* __restrict__ row_slot, int R, const uint64_t* __restr
 
 // distribute, second half: slot -> id, rows [4N, 3+vd+1], per-vertex position sums (double) + count
 __global__ void __launch_bounds__(kThreads)
-k_distribute_rows(const float* __restrict__ pos, const float* __restrict__ val, int N, int vd,
+k_distribute_rows(const float* __restrict__ pos, const float* __restrict__ val, int N, const int* __restrict__ n_dev, int vd,
                   const int* __restrict__ row_slot, const float* __restrict__ row_w,
                   const int* __restrict__ slot_ids, float* __restrict__ rows, int* __restrict__ idx,
                   double* vert_acc) {
+    if (n_dev) N = min(N, *n_dev);
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
     const int width = LTN_D + vd + 1;
@@ -189,8 +193,9 @@ k_distribute_rows(const float* __restrict__ pos, const float* __restrict__ val, 
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_local_mean_sub(float* __restrict__ rows, const int* __restrict__ idx, int R, int width,
+k_local_mean_sub(float* __restrict__ rows, const int* __restrict__ idx, int R, const int* __restrict__ n_dev, int width,
                  const double* __restrict__ vert_acc) {
+    if (n_dev) R = min(R, *n_dev * LTN_D1);
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     int id = idx[r];
@@ -260,21 +265,21 @@ int ltn_hash_clear(uint64_t* slot_keys, int* slot_ids, int* slot_first, int nslo
 // Inserts the 4 simplex vertices of N points and numbers the new vertices deterministically.
 // row_slot [4N] int32 (scratch, returned), row_w [4N] float (nullable), block_sums scratch of
 // ceil(4N/1024)+1 ints.  keys is [cap,4] int32.
-int ltn_insert_points(const float* pos, int N, float sx, float sy, float sz, uint64_t* slot_keys, int* slot_ids,
-                      int* slot_first, int nslots, int* counters, int* keys, int cap, int* row_slot, float* row_w,
-                      int* block_sums, void* stream) {
+int ltn_insert_points(const float* pos, int N, const int* n_dev, float sx, float sy, float sz, uint64_t* slot_keys,
+                      int* slot_ids, int* slot_first, int nslots, int* counters, int* keys, int cap, int* row_slot,
+                      float* row_w, int* block_sums, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return 0;
-    k_insert_points<<<ltn_blocks(N, kThreads), kThreads, 0, st>>>(pos, N, sx, sy, sz, slot_keys, slot_ids, slot_first,
+    k_insert_points<<<ltn_blocks(N, kThreads), kThreads, 0, st>>>(pos, N, n_dev, sx, sy, sz, slot_keys, slot_ids, slot_first,
                                                                   nslots, counters, row_slot, row_w);
     LTN_CHECK_LAUNCH();
     int R = N * LTN_D1;
     int nb = ltn_blocks(R, kScanBlock);
-    k_number_count<<<nb, kScanBlock, 0, st>>>(row_slot, R, slot_ids, slot_first, block_sums);
+    k_number_count<<<nb, kScanBlock, 0, st>>>(row_slot, R, n_dev, slot_ids, slot_first, block_sums);
     LTN_CHECK_LAUNCH();
     k_number_scan<<<1, 1024, 0, st>>>(block_sums, nb, counters, cap);
     LTN_CHECK_LAUNCH();
-    k_number_assign<<<nb, kScanBlock, 0, st>>>(row_slot, R, slot_keys, slot_ids, slot_first, block_sums, counters, cap,
+    k_number_assign<<<nb, kScanBlock, 0, st>>>(row_slot, R, n_dev, slot_keys, slot_ids, slot_first, block_sums, counters, cap,
                                               reinterpret_cast<int4*>(keys));
     LTN_CHECK_LAUNCH();
     return 0;
@@ -282,23 +287,23 @@ int ltn_insert_points(const float* pos, int N, float sx, float sy, float sz, uin
 
 // distribute = insert + rows/idx/w outputs (+ per-vertex position sums for the local mean).
 // vert_acc: [cap,4] double scratch, zeroed here.  subtract_mean: 0 keeps raw positions.
-int ltn_distribute(const float* pos, const float* val, int N, int val_dim, float sx, float sy, float sz,
+int ltn_distribute(const float* pos, const float* val, int N, const int* n_dev, int val_dim, float sx, float sy, float sz,
                    uint64_t* slot_keys, int* slot_ids, int* slot_first, int nslots, int* counters, int* keys, int cap,
                    int* row_slot, int* block_sums, double* vert_acc, float* rows, int* idx, float* w,
                    int subtract_mean, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return 0;
-    int rc = ltn_insert_points(pos, N, sx, sy, sz, slot_keys, slot_ids, slot_first, nslots, counters, keys, cap,
+    int rc = ltn_insert_points(pos, N, n_dev, sx, sy, sz, slot_keys, slot_ids, slot_first, nslots, counters, keys, cap,
                                row_slot, w, block_sums, stream);
     if (rc) return rc;
     cudaError_t e = cudaMemsetAsync(vert_acc, 0, sizeof(double) * 4 * (size_t)cap, st);
     if (e != cudaSuccess) return (int)e;
-    k_distribute_rows<<<ltn_blocks(N, kThreads), kThreads, 0, st>>>(pos, val, N, val_dim, row_slot, w, slot_ids, rows,
+    k_distribute_rows<<<ltn_blocks(N, kThreads), kThreads, 0, st>>>(pos, val, N, n_dev, val_dim, row_slot, w, slot_ids, rows,
                                                                     idx, vert_acc);
     LTN_CHECK_LAUNCH();
     if (subtract_mean) {
         int R = N * LTN_D1;
-        k_local_mean_sub<<<ltn_blocks(R, kThreads), kThreads, 0, st>>>(rows, idx, R, LTN_D + val_dim + 1, vert_acc);
+        k_local_mean_sub<<<ltn_blocks(R, kThreads), kThreads, 0, st>>>(rows, idx, R, n_dev, LTN_D + val_dim + 1, vert_acc);
         LTN_CHECK_LAUNCH();
     }
     return 0;

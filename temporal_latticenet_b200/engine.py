@@ -1,0 +1,188 @@
+"""Graph-replay window runner: the same model code as WindowRunner, executed in STATIC-CAPACITY mode so a
+whole frame is one CUDA graph launch.
+
+Why: the eager path issues ~250 launches per frame from Python and reads the vertex counters back three
+times per frame to size its tensors -- at ~10 ms of GPU work per window the host
+is as slow as the device.  Here every per-point / per-vertex tensor has a fixed capacity as its row
+count, the live counts stay in device memory (`*_dev` arguments of the C ABI, looked up by capacity in
+_lib's registry), nothing synchronises, and each KIND of frame (first / middle / last of a window) is
+captured once and replayed:  host work per frame = two input copies + one graph launch.
+
+Hidden states live in persistent buffers (fusion._HiddenState), the lattice objects of all levels are
+reused across windows (Lattice.reset empties them), so the captured addresses stay valid.
+
+Safety net: after each window the real vertex counts are compared with the capacities (they ride back
+with the labels); a window that outgrew them is re-run on the eager path, and so is any configuration
+whose fusion modules have no static-capacity implementation.
+"""
+import torch
+
+from . import _lib
+from .lattice import Lattice
+from .runner import WindowRunner
+
+_STATIC_FUSION = ("gru", "lstm", "aflow", "none")
+
+
+def _round_up(x, m):
+    return (int(x) + m - 1) // m * m
+
+
+class GraphWindowRunner(WindowRunner):
+    def __init__(self, cfg_path, nr_classes=26, device=None, headroom=1.35):
+        super().__init__(cfg_path, nr_classes, device)
+        self.headroom = headroom
+        self.graphs = {}
+        self.kernels = {}      # frame kind -> kernels of this library inside its graph (bench.py: gpu_launches)
+        self.caps = None
+        self.supported = all(k in _STATIC_FUSION for k in self.model.rnn_modules) and self.model.sequence_learning
+        self.fallbacks = 0
+        self._force_eager = False
+
+    # ---- capacities from an eager probe window ---------------------------------------------------------
+    def plan(self, frames_dev):
+        """runs one eager window to learn the sizes, then fixes the capacities (with headroom)"""
+        out = super().infer_window_device(frames_dev)
+        counts, lvl = [], self.lattice
+        while lvl is not None:
+            counts.append(lvl.nr_lattice_vertices())
+            lvl = lvl._coarse
+        n_max = max(p.shape[0] for p, _ in frames_dev)
+        caps = {"n": _round_up(n_max * 1.02 + 1024, 4096)}
+        vcaps = [_round_up(c * self.headroom + 512, 1024) for c in counts]
+        vcaps = [min(v, self.lattice.capacity) for v in vcaps]
+        # row classes must be told apart by their capacity alone
+        used = {caps["n"], 4 * caps["n"]}
+        for i, v in enumerate(vcaps):
+            while v in used:
+                v += 1024
+            used.add(v)
+            vcaps[i] = v
+        caps["v"] = vcaps
+        self.caps = caps
+        self._alloc_static()
+        return out
+
+    def _alloc_static(self):
+        dev, n = self.device, self.caps["n"]
+        self.pos_buf = torch.zeros(n, 3, dtype=torch.float32, device=dev)
+        self.val_buf = torch.zeros(n, 1, dtype=torch.float32, device=dev)
+        self.sizes = torch.zeros(2, dtype=torch.int32, device=dev)          # [n, 4n]
+        self._sizes_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self.static_lattice = Lattice.create(self.cfg_path, "lattice")
+        self.static_lattice.set_static(self.caps["v"])
+        # materialise the coarse levels now so their tables exist before any capture
+        lvl = self.static_lattice
+        for _ in range(len(self.caps["v"]) - 1):
+            lvl = lvl.coarse_level()
+        self._counts_host = torch.zeros(len(self.caps["v"]), dtype=torch.int32).pin_memory()
+        self.graphs = {}
+        self.pool = None
+
+    def _registry(self):
+        reg = {self.caps["n"]: self.sizes[0:1], 4 * self.caps["n"]: self.sizes[1:2]}
+        lvl = self.static_lattice
+        for cap in self.caps["v"]:
+            reg[cap] = lvl.hash_table.count_tensor()
+            lvl = lvl._coarse
+        return reg
+
+    # ---- one frame ---------------------------------------------------------------------------------------
+    def _frame(self, kind):
+        first, last = kind
+        if first:
+            self.model.reset_sequence()
+        out, _, _ = self.model(self.static_lattice, self.pos_buf, self.val_buf, not last, False)
+        return out
+
+    def _run_frame(self, kind, p, v):
+        n = p.shape[0]
+        if n > self.caps["n"]:
+            raise OverflowError("frame has more points than the static capacity")
+        self.pos_buf[:n].copy_(p, non_blocking=True)
+        self.val_buf[:n].copy_(v, non_blocking=True)
+        self._sizes_host[0], self._sizes_host[1] = n, 4 * n
+        self.sizes.copy_(self._sizes_host, non_blocking=True)
+        g = self.graphs.get(kind)
+        if g is None:
+            _lib.set_static_rows(self._registry())
+            try:
+                with torch.no_grad():
+                    # eager run in static mode first: creates the lazy buffers / weight splits outside the
+                    # capture and EXECUTES the frame (capturing records work without running it), so the
+                    # recurrent state is the one the next frame of this capture window expects
+                    self._frame(kind)
+                    torch.cuda.current_stream().synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    l0 = _lib.load().ltn_launch_count()
+                    with torch.cuda.graph(graph, pool=self.pool):
+                        out = self._frame(kind)
+                    self.kernels[kind] = _lib.load().ltn_launch_count() - l0
+                    if self.pool is None:
+                        self.pool = graph.pool()
+            finally:
+                _lib.set_static_rows(None)
+            self.graphs[kind] = (graph, out)
+            return None
+        g[0].replay()
+        return g[1]
+
+    def capture(self, frames_dev):
+        """Captures the graphs of every frame kind on a throw-away window.  Each kind is first run eagerly
+        in static mode (its outputs are discarded), which advances the recurrent state exactly like the
+        real frame would, so the following kinds see a consistent state; the captured graphs themselves
+        only record work and do not execute."""
+        if self.caps is None:
+            self.plan(frames_dev)
+        if not self.supported:
+            return self
+        T = len(frames_dev)
+        for t, (p, v) in enumerate(frames_dev):
+            self._run_frame((t == 0, t == T - 1), p, v)   # captures the kinds seen for the first time, replays the others
+        torch.cuda.synchronize()
+        return self
+
+    def infer_window_device(self, frames_dev):
+        if not self.supported or self.caps is None or self._force_eager:
+            return super().infer_window_device(frames_dev)
+        T = len(frames_dev)
+        kinds = [(t == 0, t == T - 1) for t in range(T)]
+        if any(k not in self.graphs for k in kinds):
+            self.capture(frames_dev)
+        out = None
+        for kind, (p, v) in zip(kinds, frames_dev):
+            out = self._run_frame(kind, p, v)
+        self._last_n = frames_dev[-1][0].shape[0]
+        return out[: self._last_n]
+
+    def kernels_per_window(self, nr_frames):
+        return sum(self.kernels.get((t == 0, t == nr_frames - 1), 0) for t in range(nr_frames))
+
+    def counts_ok(self):
+        """one small device->host read: did every level stay within its capacity?"""
+        lvl, i = self.static_lattice, 0
+        while lvl is not None and i < len(self.caps["v"]):
+            self._counts_host[i:i + 1].copy_(lvl.hash_table.count_tensor(), non_blocking=True)
+            lvl, i = lvl._coarse, i + 1
+        torch.cuda.current_stream().synchronize()
+        return all(int(c) < cap for c, cap in zip(self._counts_host.tolist(), self.caps["v"]))
+
+    def infer_window(self, frames_host):
+        if not self.supported or self.caps is None:
+            return super().infer_window(frames_host)
+        dev = self.device
+        frames = [(p.to(dev, non_blocking=True), v.to(dev, non_blocking=True)) for p, v in frames_host]
+        out = self.infer_window_device(frames)
+        labels = out.argmax(1)
+        if self._labels_host is None or self._labels_host.shape[0] < labels.shape[0]:
+            self._labels_host = torch.empty(labels.shape[0], dtype=torch.int64).pin_memory()
+        host = self._labels_host[: labels.shape[0]]
+        host.copy_(labels, non_blocking=True)
+        if not self.counts_ok():          # synchronises; the labels have landed too
+            self.fallbacks += 1
+            self._force_eager = True
+            try:
+                return super().infer_window(frames_host)
+            finally:
+                self._force_eager = False
+        return host

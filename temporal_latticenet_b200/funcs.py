@@ -148,7 +148,8 @@ class GatherLattice(Function):
         n, C = positions.shape[0], values.shape[1]
         out = torch.empty(n, 4 * (C + 1), dtype=torch.float32, device=values.device)
         p = _lib.ptr
-        _lib.check(_lib.load().ltn_gather(p(values), values.shape[0], C, p(indices), p(weights), n, p(out), _lib.stream()),
+        _lib.check(_lib.load().ltn_gather(p(values), values.shape[0], _lib.rows_dev(values.shape[0]), C, p(indices), p(weights), n,
+                                          _lib.rows_dev(n), p(out), _lib.stream()),
                    "ltn_gather")
         ctx.save_for_backward(indices, weights)
         ctx.shape = tuple(values.shape)
@@ -203,8 +204,9 @@ class SliceClassifyLattice(Function):
         need_grad = any(ctx.needs_input_grad)
         sliced = torch.empty(n, C, dtype=torch.float32, device=values.device) if need_grad else None
         p = _lib.ptr
-        _lib.check(_lib.load().ltn_slice_classify(p(values), values.shape[0], C, p(indices), p(weights), p(dw), n, p(W),
-                                                  p(b), K, p(out), p(sliced), _lib.stream()), "ltn_slice_classify")
+        _lib.check(_lib.load().ltn_slice_classify(p(values), values.shape[0], _lib.rows_dev(values.shape[0]), C, p(indices),
+                                                  p(weights), p(dw), n, _lib.rows_dev(n), p(W), p(b), K, p(out), p(sliced),
+                                                  _lib.stream()), "ltn_slice_classify")
         if need_grad:
             ctx.save_for_backward(values, dw, W, indices, weights, sliced)
         return out

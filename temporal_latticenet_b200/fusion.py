@@ -37,7 +37,29 @@ def _fused_ok(*tensors):
     return not (torch.is_grad_enabled() and any(t.requires_grad for t in tensors if t is not None))
 
 
-class GRUModule(torch.nn.Module):
+class _HiddenState:
+    """Hidden state h^{t-1} of a fusion module.  Eager mode: a reference to the previous frame's tensor.
+    Static-capacity mode (engine.py): a persistent [capacity, C] buffer plus the device-side row count of
+    the frame that wrote it, so every captured frame graph reads and writes the same addresses."""
+
+    def _store(self, lv):
+        if _lib.static_mode():
+            if getattr(self, "_h_buf", None) is None or self._h_buf.shape != lv.shape:
+                self._h_buf = torch.empty_like(lv)
+                self._h_rows = torch.zeros(1, dtype=torch.int32, device=lv.device)
+            self._h_buf.copy_(lv)
+            self._h_rows.copy_(_lib.rows_tensor(lv.shape[0]))
+            self.h_lv = self._h_buf
+        else:
+            self.h_lv = lv
+
+    def _rows_dev(self):
+        if _lib.static_mode() and getattr(self, "_h_rows", None) is not None:
+            return _lib.ptr(self._h_rows)
+        return None
+
+
+class GRUModule(torch.nn.Module, _HiddenState):
     """lattice_modules.py:42-66"""
 
     def __init__(self, nr_output_channels):
@@ -51,7 +73,7 @@ class GRUModule(torch.nn.Module):
 
     def forward(self, lv, ls):
         if self.h_lv is None:
-            self.h_lv = lv
+            self._store(lv)
             return lv, ls
         g = self.GRU
         h = ops.linear(self.h_lv, self.hidden_linear.weight, self.hidden_linear.bias)
@@ -63,16 +85,16 @@ class GRUModule(torch.nn.Module):
             gh = ops.linear(h, g.weight_hh, g.bias_hh)
             new_lv = torch.empty_like(lv)
             p = _lib.ptr
-            _lib.check(_lib.load().ltn_gru_pointwise(p(gi), p(gh), p(h.contiguous()), p(g.bias_hh), V, Vh, C, p(new_lv),
-                                                     _lib.stream()), "ltn_gru_pointwise")
+            _lib.check(_lib.load().ltn_gru_pointwise(p(gi), p(gh), p(h.contiguous()), p(g.bias_hh), V, Vh, _lib.rows_dev(V),
+                                                     self._rows_dev(), C, p(new_lv), _lib.stream()), "ltn_gru_pointwise")
         else:
             new_lv = g(lv, _pad_rows(h, V))
-        self.h_lv = new_lv
+        self._store(new_lv)
         ls.set_values(new_lv)
         return new_lv, ls
 
 
-class LSTMModule(torch.nn.Module):
+class LSTMModule(torch.nn.Module, _HiddenState):
     """lattice_modules.py:17-40 (the cell state is discarded: c_prev = 0 every frame)"""
 
     def __init__(self, nr_output_channels):
@@ -86,7 +108,7 @@ class LSTMModule(torch.nn.Module):
 
     def forward(self, lv, ls):
         if self.h_lv is None:
-            self.h_lv = lv
+            self._store(lv)
             return lv, ls
         c = self.lstm
         h = ops.linear(self.h_lv, self.hidden_linear.weight, self.hidden_linear.bias)
@@ -98,12 +120,12 @@ class LSTMModule(torch.nn.Module):
             gh = ops.linear(h, c.weight_hh, c.bias_hh)
             new_lv = torch.empty_like(lv)
             p = _lib.ptr
-            _lib.check(_lib.load().ltn_lstm_pointwise(p(gi), p(gh), p(c.bias_hh), V, Vh, C, p(new_lv), _lib.stream()),
-                       "ltn_lstm_pointwise")
+            _lib.check(_lib.load().ltn_lstm_pointwise(p(gi), p(gh), p(c.bias_hh), V, Vh, _lib.rows_dev(V), self._rows_dev(), C,
+                                                      p(new_lv), _lib.stream()), "ltn_lstm_pointwise")
         else:
             hp = _pad_rows(h, V)
             new_lv, _ = c(lv, (hp, torch.zeros_like(hp)))
-        self.h_lv = new_lv
+        self._store(new_lv)
         ls.set_values(new_lv)
         return new_lv, ls
 
@@ -212,7 +234,7 @@ class CustomKernelConvLatticeIm2RowModule(torch.nn.Module):
             b = 1.0 / math.sqrt(rows)
             self.bias = torch.nn.Parameter(torch.empty(self.nr_filters, device=device).uniform_(-b, b))
 
-    def forward(self, lattice_values, hidden_state, lattice_structure, nr_hidden_rows=None):
+    def forward(self, lattice_values, hidden_state, lattice_structure, nr_hidden_rows=None, hidden_rows_dev=None):
         """hidden_state: h^{t-1}, either already padded to V rows (reference call shape) or the
         unpadded [Vh,C] tensor with nr_hidden_rows=None meaning "all rows are real"."""
         ls, lv = lattice_structure, lattice_values
@@ -226,7 +248,8 @@ class CustomKernelConvLatticeIm2RowModule(torch.nn.Module):
             out = torch.empty_like(lv)
             weights = torch.empty(V, 9, dtype=torch.float32, device=lv.device)
             p = _lib.ptr
-            _lib.check(_lib.load().ltn_aflow(p(lv.contiguous()), p(hidden_state.contiguous()), V, Vh, C, p(nbr),
+            _lib.check(_lib.load().ltn_aflow(p(lv.contiguous()), p(hidden_state.contiguous()), V, Vh, _lib.rows_dev(V),
+                                             hidden_rows_dev, C, p(nbr),
                                              p(self.alpha.detach().reshape(1)), p(self.beta.detach().reshape(1)),
                                              p(self.bias) if self.bias is not None else None, AFLOW_PAD,
                                              1 if self.use_center else 0, p(out), p(weights), _lib.stream()), "ltn_aflow")
@@ -249,7 +272,7 @@ class CustomKernelConvLatticeIm2RowModule(torch.nn.Module):
         return out, weights, nbr
 
 
-class CrossframeLocalInterpolationModule(torch.nn.Module):
+class CrossframeLocalInterpolationModule(torch.nn.Module, _HiddenState):
     """AFlow wrapper, lattice_modules.py:188-235"""
 
     def __init__(self, nr_output_channels, train_alpha_beta=True, use_center=True):
@@ -270,12 +293,12 @@ class CrossframeLocalInterpolationModule(torch.nn.Module):
 
     def forward(self, lv, ls):
         if self.h_lv is None:
-            self.h_lv = lv
+            self._store(lv)
         else:
-            feat, weights, nbr = self.AFLOW(lv, self.h_lv, ls)
+            feat, weights, nbr = self.AFLOW(lv, self.h_lv, ls, hidden_rows_dev=self._rows_dev())
             self.h_lv_vis, self.weights_vis, self.lattice_neighbors_previous = self.h_lv.detach(), weights.detach(), nbr
             lv = torch.relu(ops.linear(torch.cat([feat, lv], 1), self.linear.weight, self.linear.bias))
-            self.h_lv = lv
+            self._store(lv)
         ls.set_values(lv)
         return lv, ls
 

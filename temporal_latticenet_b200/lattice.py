@@ -73,6 +73,7 @@ class HashTable:
         self.counters = torch.zeros(8, dtype=torch.int32, device=dev)
         self._host = torch.zeros(8, dtype=torch.int32).pin_memory()
         self._host_valid = False
+        self.static_rows = None
         self.clear()
 
     def capacity(self):
@@ -96,15 +97,22 @@ class HashTable:
         return self._host
 
     def nr_filled(self):
-        """Device -> host read of the vertex counter (one stream sync, cached until the next insert)."""
+        """Device -> host read of the vertex counter (one stream sync, cached until the next insert).
+        In static-capacity mode (engine.py) the answer is the level's fixed capacity and nothing syncs."""
+        if self.static_rows is not None:
+            return self.static_rows
         return int(self._sync_counters()[0])
+
+    def count_tensor(self):
+        """device int32 [1]: the live vertex count"""
+        return self.counters[0:1]
 
     def nr_overflowed(self):
         return int(self._sync_counters()[2])
 
     def keys(self):
         """[V,3] int32 keys in vertex-id order"""
-        return self.keys_tensor[: self.nr_filled(), :3]
+        return self.keys_tensor[: int(self._sync_counters()[0]), :3]
 
 
 class Lattice:
@@ -131,6 +139,7 @@ class Lattice:
         self._block_sums = None
         self._vert_acc = None
         self.vertex_counts = None
+        self.static_caps = None   # engine.py: per-level vertex capacities [V0cap, V1cap, ...]
 
     # ---- reference-visible API ---------------------------------------------------------------
     @staticmethod
@@ -190,8 +199,7 @@ class Lattice:
         if values.dim() != 2 or values.shape[0] != positions.shape[0]:
             raise RuntimeError("values must be [N, val_dim]")
         if reset_hashmap:
-            self.hash_table.clear()
-            self._coarse = None
+            self.reset()
         self._bump()
         self._positions = positions
         n, vd = positions.shape[0], values.shape[1]
@@ -202,7 +210,7 @@ class Lattice:
         sx, sy, sz = self.scale()
         ht = self.hash_table
         p = _lib.ptr
-        _lib.check(self.lib.ltn_distribute(p(positions), p(values), n, vd, sx, sy, sz, p(ht.slot_keys), p(ht.slot_ids),
+        _lib.check(self.lib.ltn_distribute(p(positions), p(values), n, _lib.rows_dev(n), vd, sx, sy, sz, p(ht.slot_keys), p(ht.slot_ids),
                                            p(ht.slot_first), ht.nslots, p(ht.counters), p(ht.keys_tensor), self.capacity,
                                            p(self._row_slot), p(self._block_sums), p(self._vert_acc), p(rows), p(idx),
                                            p(w), 1 if subtract_mean else 0, _lib.stream()), "ltn_distribute")
@@ -219,8 +227,7 @@ class Lattice:
     def just_create_verts(self, positions, reset_hashmap=True):
         positions = self._check_points(positions)
         if reset_hashmap:
-            self.hash_table.clear()
-            self._coarse = None
+            self.reset()
         self._bump()
         self._positions = positions
         n = positions.shape[0]
@@ -228,15 +235,38 @@ class Lattice:
         sx, sy, sz = self.scale()
         ht = self.hash_table
         p = _lib.ptr
-        _lib.check(self.lib.ltn_insert_points(p(positions), n, sx, sy, sz, p(ht.slot_keys), p(ht.slot_ids),
+        _lib.check(self.lib.ltn_insert_points(p(positions), n, _lib.rows_dev(n), sx, sy, sz, p(ht.slot_keys), p(ht.slot_ids),
                                               p(ht.slot_first), ht.nslots, p(ht.counters), p(ht.keys_tensor),
                                               self.capacity, p(self._row_slot), None, p(self._block_sums),
                                               _lib.stream()), "ltn_insert_points")
 
-    def create_coarse_verts(self):
-        """Coarser lattice (sigma x2) holding every coarse vertex touched by any frame so far."""
+    def reset(self):
+        """begin a new sequence: empty this level's table; the coarser levels are dropped (eager mode) or,
+        in static-capacity mode, kept as objects and emptied too so captured graphs keep their addresses"""
+        self.hash_table.clear()
+        if self.static_caps is None:
+            self._coarse = None
+        elif self._coarse is not None:
+            self._coarse.reset()
+        self._coarse_frame = -1
+
+    def set_static(self, caps):
+        """static-capacity mode: caps[level] = fixed row count of every per-vertex tensor of that level"""
+        self.static_caps = None if caps is None else list(caps)
+        self.hash_table.static_rows = None if caps is None else int(caps[self.level])
+        if self._coarse is not None:
+            self._coarse.set_static(caps)
+
+    def coarse_level(self):
+        """the (persistent) next-coarser lattice object, created empty on first use"""
         if self._coarse is None:
             self._coarse = Lattice(self.capacity, self.sigma * 2.0, self.level + 1, self.inv_std_dev, self.device)
+            self._coarse.set_static(self.static_caps)
+        return self._coarse
+
+    def create_coarse_verts(self):
+        """Coarser lattice (sigma x2) holding every coarse vertex touched by any frame so far."""
+        self.coarse_level()
         c = self._coarse
         if self._coarse_frame != self._frame:
             c.just_create_verts(self._positions, reset_hashmap=False)
@@ -254,7 +284,7 @@ class Lattice:
             t = torch.empty(v, FILTER_EXTENT, dtype=torch.int32, device=self.device)
             ht = other.hash_table
             p = _lib.ptr
-            _lib.check(self.lib.ltn_neighbours(p(self.hash_table.keys_tensor), v, None, p(ht.slot_keys), p(ht.slot_ids),
+            _lib.check(self.lib.ltn_neighbours(p(self.hash_table.keys_tensor), v, _lib.rows_dev(v), p(ht.slot_keys), p(ht.slot_ids),
                                                ht.nslots, mode, dilation, 1 if other is self else 0, p(t),
                                                _lib.stream()), "ltn_neighbours")
             self._nbr_cache[key] = t

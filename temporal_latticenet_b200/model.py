@@ -91,9 +91,9 @@ class PointNetSeq(torch.nn.Module):
         red = torch.empty(V, 128, dtype=torch.float32, device=dev)
         p = _lib.ptr
         l1, l2, l3 = self.layers
-        _lib.check(_lib.load().ltn_pointnet(p(distributed), 5, p(indices), R, None, p(l1.weight.detach()), p(l1.bias.detach()),
+        _lib.check(_lib.load().ltn_pointnet(p(distributed), 5, p(indices), R, _lib.rows_dev(R), p(l1.weight.detach()), p(l1.bias.detach()),
                                             p(l2.weight.detach()), p(l2.bias.detach()), p(l3.weight.detach()), p(l3.bias.detach()),
-                                            V, None, p(packed), p(ls._vert_acc), 0 if self.fusion_kind == "maxpool" else
+                                            V, _lib.rows_dev(V), p(packed), p(ls._vert_acc), 0 if self.fusion_kind == "maxpool" else
                                             _MIN_POINTS_PER_VERTEX, p(red), _lib.stream()), "ltn_pointnet")
         return red
 

@@ -48,8 +48,9 @@ class _GroupNormRelu(Function):
         p = _lib.ptr
         sums = torch.empty(groups, 2, dtype=torch.float64, device=x.device)
         y = torch.empty_like(x)
-        _lib.check(lib.ltn_gn_stats(p(x), V, None, C, groups, p(sums), _lib.stream()), "ltn_gn_stats")
-        _lib.check(lib.ltn_gn_apply(p(x), V, None, C, groups, p(sums), p(gamma), p(beta), float(eps), 1 if relu else 0,
+        vd = _lib.rows_dev(V)
+        _lib.check(lib.ltn_gn_stats(p(x), V, vd, C, groups, p(sums), _lib.stream()), "ltn_gn_stats")
+        _lib.check(lib.ltn_gn_apply(p(x), V, vd, C, groups, p(sums), p(gamma), p(beta), float(eps), 1 if relu else 0,
                                     p(y), _lib.stream()), "ltn_gn_apply")
         ctx.save_for_backward(x, gamma, sums, y)
         ctx.cfg = (groups, eps, relu)
@@ -137,7 +138,7 @@ TC_PASSES = 3  # 3 = fp32-parity split (default); 1 = single-pass TF32 (stated s
 
 
 def conv_tc_supported(C, F, folded_norm=True):
-    return C % 32 == 0 and C > 0 and (C <= 256 or not folded_norm) and F % 16 == 0 and F > 0
+    return C % 32 == 0 and C > 0 and (C <= 256 or not folded_norm) and F % 8 == 0 and F > 0
 
 
 def k_major(weight, transposed=False):
@@ -169,7 +170,7 @@ def gn_sums(x, groups):
     """[G,2] double: per-group sum and sum of squares of x [V,C] (GroupNorm over [1,C,V])"""
     x = x.contiguous()
     sums = torch.empty(groups, 2, dtype=torch.float64, device=x.device)
-    _lib.check(_lib.load().ltn_gn_stats(_lib.ptr(x), x.shape[0], None, x.shape[1], groups, _lib.ptr(sums), _lib.stream()),
+    _lib.check(_lib.load().ltn_gn_stats(_lib.ptr(x), x.shape[0], _lib.rows_dev(x.shape[0]), x.shape[1], groups, _lib.ptr(sums), _lib.stream()),
                "ltn_gn_stats")
     return sums
 
@@ -195,7 +196,8 @@ def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, gn=None, relu=
     if gn is not None:
         g_sums, g_gamma, g_beta, g_eps = gn
         g_groups = g_sums.shape[0]
-    rc = _lib.load().ltn_conv_tc(p(x), x.shape[0], None, p(nbr), Vq, None, C, S, p(hi), p(lo), F, p(a_scale), p(a_shift),
+    rc = _lib.load().ltn_conv_tc(p(x), x.shape[0], _lib.rows_dev(x.shape[0]), p(nbr), Vq, _lib.rows_dev(Vq), C, S, p(hi), p(lo), F,
+                                 p(a_scale), p(a_shift),
                                  p(g_sums), p(g_gamma), p(g_beta), float(g_eps), int(g_groups), 1 if relu else 0, p(bias), p(res),
                                  p(out), out.stride(0), p(out_sums), 0 if out_sums is None else out_sums.shape[0],
                                  TC_PASSES if passes is None else passes, _lib.stream())

@@ -1,0 +1,74 @@
+"""Graph-replay runner (static capacities, device-side sizes, one CUDA graph per frame kind) against the
+eager runner on the same windows: same vertex counts, same log-softmax within 1e-4 of abs-max (the two
+paths run the same kernels; only the order of the floating-point atomics of the GroupNorm statistics
+differs), same predicted labels."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import CFG, small_window
+
+pytestmark = pytest.mark.gpu
+
+
+def _window(seed, frames=4, n=6000):
+    return small_window(seed=seed, frames=frames, radius=9.0, max_points=n)
+
+
+def test_graph_runner_matches_eager_runner():
+    from temporal_latticenet_b200.engine import GraphWindowRunner
+    from temporal_latticenet_b200.runner import WindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    dev = torch.device("cuda:0")
+    wins = [_window(1), _window(2, n=5500), _window(3, n=5000)]
+    to_dev = lambda w: [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]  # noqa: E731
+    eager = WindowRunner(CFG, 26, dev).materialise_parameters(to_dev(wins[0]), seeded_state)
+    graph = GraphWindowRunner(CFG, 26, dev).materialise_parameters(to_dev(wins[0]), seeded_state)
+    assert graph.supported
+    graph.plan(to_dev(wins[0]))
+    graph.capture(to_dev(wins[0]))
+    assert len(graph.graphs) == 3  # first / middle / last
+    for rep in range(2):  # replaying twice checks that no state leaks between windows
+        for w in wins:
+            fd = to_dev(w)
+            want = eager.infer_window_device(fd).cpu().numpy()
+            got = graph.infer_window_device(fd).cpu().numpy()
+            assert graph.counts_ok()
+            counts = []
+            lvl = graph.static_lattice
+            while lvl is not None:
+                counts.append(int(lvl.hash_table.count_tensor().cpu()))
+                lvl = lvl._coarse
+            ecounts = []
+            lvl = eager.lattice
+            while lvl is not None:
+                ecounts.append(lvl.nr_lattice_vertices())
+                lvl = lvl._coarse
+            assert counts == ecounts
+            assert got.shape == want.shape
+            err = float(np.abs(got - want).max()) / float(np.abs(want).max())
+            assert err < 1e-4, err
+            assert (got.argmax(1) == want.argmax(1)).mean() > 0.999
+    # end-to-end entry point with pinned host buffers
+    host = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in wins[1]]
+    labels = graph.infer_window(host).clone()
+    want = eager.infer_window(host)
+    assert (labels == want).float().mean() > 0.999 and graph.fallbacks == 0
+
+
+def test_graph_runner_falls_back_when_capacity_is_exceeded():
+    from temporal_latticenet_b200.engine import GraphWindowRunner
+    from temporal_latticenet_b200.runner import WindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    dev = torch.device("cuda:0")
+    small = small_window(seed=4, frames=4, radius=5.0, max_points=2500)
+    big = small_window(seed=5, frames=4, radius=12.0, max_points=2500)   # same point count, far more vertices
+    to_dev = lambda w: [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]  # noqa: E731
+    eager = WindowRunner(CFG, 26, dev).materialise_parameters(to_dev(small), seeded_state)
+    graph = GraphWindowRunner(CFG, 26, dev, headroom=1.05).materialise_parameters(to_dev(small), seeded_state)
+    graph.plan(to_dev(small))
+    graph.capture(to_dev(small))
+    host = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in big]
+    labels = graph.infer_window(host).clone()
+    assert graph.fallbacks == 1
+    assert torch.equal(labels, eager.infer_window(host))
