@@ -237,6 +237,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="add a per-entry-point time breakdown (extra untimed pass)")
     ap.add_argument("--eager", action="store_true", help="eager per-op launches instead of CUDA-graph replay")
+    ap.add_argument("--lanes", type=int, default=3, help="independent windows in flight per GPU (one CUDA stream each)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer = BASELINE config 3 (headline); train = config 4 (BPTT + AdamW + NCCL gradient all-reduce)")
     args = ap.parse_args()
@@ -258,7 +259,7 @@ def main():
     import __graft_entry__ as G
     G.build()
     from temporal_latticenet_b200 import _lib
-    from temporal_latticenet_b200.engine import GraphWindowRunner
+    from temporal_latticenet_b200.engine import GraphWindowRunner, MultiWindowRunner
     from temporal_latticenet_b200.runner import WindowRunner
     from temporal_latticenet_b200.seeding import seeded_state
     lib = _lib.load()
@@ -277,12 +278,8 @@ def main():
     else:
         # default: static-capacity CUDA-graph replay of each frame (engine.py); capacities are planned on the
         # window with the most points and re-validated after every window (eager fallback when exceeded)
-        runner = GraphWindowRunner(CFG, NR_CLASSES, dev)
-        runner.materialise_parameters(devw[0], seeded_state)
-        for w in devw:
-            if runner.caps is None or max(p.shape[0] for p, _ in w) > runner.caps["n"]:
-                runner.plan(w)
-        runner.capture(devw[0])
+        multi = MultiWindowRunner(CFG, NR_CLASSES, dev, lanes=max(1, args.lanes)).prepare(devw[0], seeded_state, devw)
+        runner = multi.lanes[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -290,8 +287,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        runner.infer_window_device(devw[i % len(devw)])
+    lanes = 1 if args.eager or not runner.supported else max(1, args.lanes)
+
+    def run_group(i0, n):
+        """windows i0 .. i0+n-1 in flight together (one per lane); device-resident inputs"""
+        if lanes == 1:
+            for j in range(n):
+                runner.infer_window_device(devw[(i0 + j) % len(devw)])
+        else:
+            multi.infer_windows_device([devw[(i0 + j) % len(devw)] for j in range(n)])
+
+    def run_group_host(i0, n):
+        if lanes == 1:
+            out = None
+            for j in range(n):
+                out = runner.infer_window(host[(i0 + j) % len(host)])
+            return out
+        return multi.infer_windows([host[(i0 + j) % len(host)] for j in range(n)])[-1]
+
+    for i in range(0, max(args.warmup, 3), lanes):
+        run_group(i, min(lanes, max(args.warmup, 3) - i))
     torch.cuda.synchronize()
     lvl = runner.static_lattice if getattr(runner, "caps", None) and runner.supported else runner.lattice
     v_counts = []
@@ -306,11 +321,11 @@ def main():
     barrier()
     launches0 = lib.ltn_launch_count()
     evs = []
-    for i in range(args.steps):
+    for i in range(0, args.steps, lanes):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        runner.infer_window_device(devw[i % len(devw)])
+        run_group(i, min(lanes, args.steps - i))   # the lanes fork from / join into the current stream
         e1.record()
         evs.append((e0, e1))
     barrier()
@@ -318,7 +333,7 @@ def main():
     graph_mode = (not args.eager) and runner.supported
     if graph_mode:   # replayed graphs: the library's host-side counter saw the kernels once, at capture
         launches = args.steps * runner.kernels_per_window(FRAMES)
-        capacity_ok = runner.counts_ok()
+        capacity_ok = multi.counts_ok()
     ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -328,8 +343,8 @@ def main():
     # ---- timed region 2: end to end through the runner with pinned HOST buffers ----------------------
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        labels = runner.infer_window(host[i % len(host)])
+    for i in range(0, args.steps, lanes):
+        labels = run_group_host(i, min(lanes, args.steps - i))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -419,8 +434,9 @@ def main():
             "config": {"workload": WORKLOAD, "points_per_scan": pts, "frames": FRAMES, "vertices_per_level_after_4_frames": v_counts,
                        "l2": "256 MB flush between steps; per-step working set (im2row buffers) also exceeds L2",
                        "parallelism": "windows sharded over %d rank(s), no data-path collective" % world,
-                       "execution": ("CUDA-graph replay per frame kind, static capacities %s, capacities respected: %s"
-                                     % (runner.caps, capacity_ok)) if graph_mode else "eager op-by-op launches"},
+                       "execution": ("CUDA-graph replay per frame kind, %d window(s) in flight per GPU (one stream each), "
+                                     "static capacities %s, capacities respected: %s" % (lanes, runner.caps, capacity_ok))
+                       if graph_mode else "eager op-by-op launches"},
             "e2e": {"value": total_scans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
     if args.breakdown:

@@ -156,6 +156,8 @@ int ltn_aflow(const float* lv, const float* h, int V, int Vh, const int* v_dev, 
 
 /* library version / build info */
 int ltn_version(void);
+/* dst[0] = a, dst[1] = b on the stream (per-frame point counts of the graph engine; values travel in the launch) */
+int ltn_set_int2(int* dst, int a, int b, void* stream);
 /* kernels launched by this library since it was loaded, modulo 2^31 (bench.py: gpu_launches) */
 int ltn_launch_count(void);
 

@@ -32,7 +32,7 @@ struct MlpWeights {
     const float *w1, *b1, *w2, *b2, *w3, *b3;  // nn.Linear layout [out, in]
 };
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_pointnet_mlp_max(const float* __restrict__ rows, int width, const int* __restrict__ idx, int R,
                    const int* __restrict__ r_dev, MlpWeights w, int V, const int* __restrict__ v_dev,
                    unsigned long long* packed) {
@@ -79,27 +79,36 @@ k_pointnet_mlp_max(const float* __restrict__ rows, int width, const int* __restr
         for (int i = 0; i < D2; ++i) h2[i] = fmaxf(h2[i], 0.f);
         unsigned long long* dst = packed + (size_t)id * D3;
         const unsigned long long low = (unsigned long long)(0xFFFFFFFFu - (uint32_t)row);
-        // last layer in two halves of 32 outputs to bound the live registers
+        // last layer in four quarters of 16 outputs to bound the live registers (two blocks per SM).  The 16
+        // current maxima of a quarter are fetched with 8 independent 128-bit loads issued BEFORE its 512 FMAs
+        // (one overlapped L2 round trip instead of 16 dependent ones); afterwards an atomic is issued only
+        // where this row actually raises the maximum.
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float y[32];
+        for (int q = 0; q < 4; ++q) {
+            unsigned long long cur[16];
 #pragma unroll
-            for (int o = 0; o < 32; ++o) y[o] = sb3[half * 32 + o];
+            for (int o = 0; o < 16; o += 2) {
+                const ulonglong2 c2 = __ldcg(reinterpret_cast<const ulonglong2*>(dst + q * 16 + o));
+                cur[o] = c2.x;
+                cur[o + 1] = c2.y;
+            }
+            float y[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) y[o] = sb3[q * 16 + o];
 #pragma unroll
             for (int i = 0; i < D2; ++i) {
                 const float a = h2[i];
 #pragma unroll
-                for (int o = 0; o < 32; o += 4) {
-                    const float4 ww = *reinterpret_cast<const float4*>(s3 + i * D3 + half * 32 + o);
+                for (int o = 0; o < 16; o += 4) {
+                    const float4 ww = *reinterpret_cast<const float4*>(s3 + i * D3 + q * 16 + o);
                     y[o] = fmaf(a, ww.x, y[o]); y[o + 1] = fmaf(a, ww.y, y[o + 1]);
                     y[o + 2] = fmaf(a, ww.z, y[o + 2]); y[o + 3] = fmaf(a, ww.w, y[o + 3]);
                 }
             }
 #pragma unroll
-            for (int o = 0; o < 32; ++o) {
+            for (int o = 0; o < 16; ++o) {
                 const unsigned long long key = ((unsigned long long)ord_enc(y[o]) << 32) | low;
-                // skip the atomic when the slot already holds something at least as large
-                if (__ldcg(dst + half * 32 + o) < key) atomicMax(dst + half * 32 + o, key);
+                if (cur[o] < key) atomicMax(dst + q * 16 + o, key);
             }
         }
     }

@@ -68,7 +68,6 @@ class GraphWindowRunner(WindowRunner):
         self.pos_buf = torch.zeros(n, 3, dtype=torch.float32, device=dev)
         self.val_buf = torch.zeros(n, 1, dtype=torch.float32, device=dev)
         self.sizes = torch.zeros(2, dtype=torch.int32, device=dev)          # [n, 4n]
-        self._sizes_host = torch.zeros(2, dtype=torch.int32).pin_memory()
         self.static_lattice = Lattice.create(self.cfg_path, "lattice")
         self.static_lattice.set_static(self.caps["v"])
         # materialise the coarse levels now so their tables exist before any capture
@@ -101,8 +100,7 @@ class GraphWindowRunner(WindowRunner):
             raise OverflowError("frame has more points than the static capacity")
         self.pos_buf[:n].copy_(p, non_blocking=True)
         self.val_buf[:n].copy_(v, non_blocking=True)
-        self._sizes_host[0], self._sizes_host[1] = n, 4 * n
-        self.sizes.copy_(self._sizes_host, non_blocking=True)
+        _lib.check(_lib.load().ltn_set_int2(_lib.ptr(self.sizes), n, 4 * n, _lib.stream()), "ltn_set_int2")
         g = self.graphs.get(kind)
         if g is None:
             _lib.set_static_rows(self._registry())
@@ -186,3 +184,104 @@ class GraphWindowRunner(WindowRunner):
             finally:
                 self._force_eager = False
         return host
+
+
+class MultiWindowRunner:
+    """`lanes` independent windows in flight on one GPU, each on its own CUDA stream with its own
+    GraphWindowRunner (own lattice, hidden states, captured graphs; identical weights).
+
+    Windows are independent by construction (a fresh lattice per window, train_ln.py:236-239), and a single
+    window cannot fill a B200: the coarse-level kernels launch 17-60 CTAs on 148 SMs and every frame is a
+    strictly sequential chain.  Interleaving the frame graphs of two windows lets one window's small kernels
+    run on the SMs the other leaves idle -- the intra-GPU form of the sharding-by-window of SURVEY.md 8(e)."""
+
+    def __init__(self, cfg_path, nr_classes=26, device=None, lanes=2):
+        self.lanes = [GraphWindowRunner(cfg_path, nr_classes, device) for _ in range(lanes)]
+        self.device = self.lanes[0].device
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(lanes)]
+        self.supported = self.lanes[0].supported
+
+    def prepare(self, frames_dev, state_dict_fn, plan_windows=None):
+        for lane, s in zip(self.lanes, self.streams):
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                lane.materialise_parameters(frames_dev, state_dict_fn)
+                for w in (plan_windows or [frames_dev]):
+                    if lane.caps is None or max(p.shape[0] for p, _ in w) > lane.caps["n"]:
+                        lane.plan(w)
+                lane.capture(frames_dev)
+            torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        return self
+
+    def infer_windows_device(self, windows_dev):
+        """windows_dev: up to `lanes` windows (lists of (positions, values) CUDA tensors).  Frame t of every
+        window is issued before frame t+1 of any, so the streams interleave.  Returns the log-softmax of each
+        window's last frame; the caller's stream waits for all lanes."""
+        cur = torch.cuda.current_stream()
+        outs = [None] * len(windows_dev)
+        T = max(len(w) for w in windows_dev)
+        for s in self.streams[: len(windows_dev)]:
+            s.wait_stream(cur)
+        for t in range(T):
+            for i, w in enumerate(windows_dev):
+                if t < len(w):
+                    with torch.cuda.stream(self.streams[i]):
+                        lane = self.lanes[i]
+                        kind = (t == 0, t == len(w) - 1)
+                        if kind not in lane.graphs:
+                            lane.capture(w)
+                        outs[i] = lane._run_frame(kind, w[t][0], w[t][1])
+        for i, w in enumerate(windows_dev):
+            outs[i] = outs[i][: w[-1][0].shape[0]]
+            cur.wait_stream(self.streams[i])
+        return outs
+
+    def infer_windows(self, windows_host):
+        """pinned host buffers in, predicted labels (pinned host int64) out, synchronised"""
+        dev = self.device
+        cur = torch.cuda.current_stream()
+        labels = []
+        wins = []
+        for i, w in enumerate(windows_host):
+            self.streams[i].wait_stream(cur)
+            with torch.cuda.stream(self.streams[i]):
+                wins.append([(p.to(dev, non_blocking=True), v.to(dev, non_blocking=True)) for p, v in w])
+        T = max(len(w) for w in wins)
+        outs = [None] * len(wins)
+        for t in range(T):
+            for i, w in enumerate(wins):
+                if t < len(w):
+                    with torch.cuda.stream(self.streams[i]):
+                        outs[i] = self.lanes[i]._run_frame((t == 0, t == len(w) - 1), w[t][0], w[t][1])
+        for i, w in enumerate(wins):
+            lane = self.lanes[i]
+            with torch.cuda.stream(self.streams[i]):
+                lab = outs[i][: w[-1][0].shape[0]].argmax(1)
+                if lane._labels_host is None or lane._labels_host.shape[0] < lab.shape[0]:
+                    lane._labels_host = torch.empty(lab.shape[0], dtype=torch.int64).pin_memory()
+                host = lane._labels_host[: lab.shape[0]]
+                host.copy_(lab, non_blocking=True)
+                labels.append(host)
+        ok = True
+        for i in range(len(wins)):
+            with torch.cuda.stream(self.streams[i]):
+                ok = self.lanes[i].counts_ok() and ok      # synchronises the lane
+        if not ok:
+            out = []
+            for i, w in enumerate(windows_host):
+                lane = self.lanes[i]
+                lane.fallbacks += 1
+                lane._force_eager = True
+                try:
+                    out.append(WindowRunner.infer_window(lane, w))
+                finally:
+                    lane._force_eager = False
+            return out
+        return labels
+
+    def kernels_per_window(self, nr_frames):
+        return self.lanes[0].kernels_per_window(nr_frames)
+
+    def counts_ok(self):
+        return all(l.counts_ok() for l in self.lanes)

@@ -72,3 +72,30 @@ def test_graph_runner_falls_back_when_capacity_is_exceeded():
     labels = graph.infer_window(host).clone()
     assert graph.fallbacks == 1
     assert torch.equal(labels, eager.infer_window(host))
+
+
+def test_multi_window_runner_matches_eager_runner():
+    """three windows in flight on three streams give the results of running them one after the other"""
+    from temporal_latticenet_b200.engine import MultiWindowRunner
+    from temporal_latticenet_b200.runner import WindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    dev = torch.device("cuda:0")
+    wins = [_window(6), _window(7, n=5200), _window(8, n=4800)]
+    to_dev = lambda w: [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]  # noqa: E731
+    devw = [to_dev(w) for w in wins]
+    eager = WindowRunner(CFG, 26, dev).materialise_parameters(devw[0], seeded_state)
+    multi = MultiWindowRunner(CFG, 26, dev, lanes=3).prepare(devw[0], seeded_state, devw)
+    want = [eager.infer_window_device(w).cpu().numpy() for w in devw]
+    for rep in range(3):
+        order = devw[rep:] + devw[:rep]          # rotate which lane gets which window
+        outs = multi.infer_windows_device(order)
+        torch.cuda.synchronize()
+        assert multi.counts_ok()
+        for o, w in zip(outs, (want[rep:] + want[:rep])):
+            got = o.cpu().numpy()
+            assert got.shape == w.shape
+            assert float(np.abs(got - w).max()) / float(np.abs(w).max()) < 1e-4
+    host = [[(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in w] for w in wins]
+    labels = [l.clone() for l in multi.infer_windows(host)]
+    for l, w in zip(labels, want):
+        assert (l.numpy() == w.argmax(1)).mean() > 0.999
