@@ -149,14 +149,14 @@ struct ConvParams {
     int gn_cpg, out_cpg;
     int Vq, Vx, C, S, F, ldo, relu;
     int n_tile;            // output channels per CTA (<= 256, multiple of 16)
-    int stages;
+    int stages_a, stages_b; // depth of the A (gathered) and B (TMA) shared-memory rings
 };
 
 template <int PASSES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
+    __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 1];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_affine[2 * 256];
     __shared__ float s_colsum[2 * 256];
@@ -173,22 +173,30 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
     const int K = p.S * p.C;
     const int num_kb = K / kBlockK;
     const int kb_per_slot = p.C / kBlockK;
-    const int stages = p.stages;
+    const int SA = p.stages_a, SB = p.stages_b;
 
-    // shared-memory carve-up: per stage [A_hi | A_lo | B_hi | B_lo], every block 1024-byte aligned
+    // shared-memory carve-up: two INDEPENDENT rings, A stages [A_hi | A_lo] and B stages [B_hi | B_lo], every
+    // block 1024-byte aligned, so each ring can have the depth the shared-memory budget allows.
     const uint32_t a_bytes = kBlockM * 128;
     const uint32_t b_bytes = (uint32_t)p.n_tile * 128;
-    const uint32_t stage_bytes = (PASSES == 3 ? 2 : 1) * (a_bytes + b_bytes);
+    const uint32_t a_stage = (PASSES == 3 ? 2 : 1) * a_bytes, b_stage = (PASSES == 3 ? 2 : 1) * b_bytes;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smem_b = smem + (size_t)SA * a_stage;
 
-    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]), bar_acc = smem_u32(&bars[2 * kMaxStages]);
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]);
+    const uint32_t bar_fullb = smem_u32(&bars[2 * kMaxStages]), bar_emptyb = smem_u32(&bars[3 * kMaxStages]);
+    const uint32_t bar_acc = smem_u32(&bars[4 * kMaxStages]);
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)Nmma) tmem_cols <<= 1;
 
     if (tid == 0) {
-        for (int s = 0; s < stages; ++s) {
-            mbar_init(bar_full + 8 * s, kGroupThreads / 32 + 1);   // one arrive per gather warp + the TMA thread's expect_tx arrive
+        for (int s = 0; s < SA; ++s) {
+            mbar_init(bar_full + 8 * s, kGroupThreads / 32);   // one arrive per gather warp of the group that owns the k-block
             mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < SB; ++s) {
+            mbar_init(bar_fullb + 8 * s, 1);                   // the TMA thread's expect_tx arrive (+ the bytes)
+            mbar_init(bar_emptyb + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -257,12 +265,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
             }
         };
         auto consume = [&](int kb, const float4* cur, const int* cur_src) {
-            const int stage = kb % stages;
-            const uint32_t parity = ((kb / stages) & 1) ^ 1;
+            const int stage = kb % SA;
+            const uint32_t parity = ((kb / SA) & 1) ^ 1;
             const int c0 = (kb % kb_per_slot) * kBlockK;
             if (lane == 0) mbar_wait(bar_empty + 8 * stage, parity);   // one waiter per warp
             __syncwarp();
-            uint8_t* a_hi0 = smem + (size_t)stage * stage_bytes;
+            uint8_t* a_hi0 = smem + (size_t)stage * a_stage;
             const float* sc = s_affine + c0 + 4 * chunk;
             const float* sh = sc + 256;
 #pragma unroll
@@ -345,12 +353,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
             // instruction descriptor: D = F32 [4,6), A = B = TF32 [7,10) [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nmma >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int stage = kb % stages;
-                mbar_wait(bar_full + 8 * stage, (kb / stages) & 1);
+                const int sa = kb % SA, sb = kb % SB;
+                mbar_wait(bar_fullb + 8 * sb, (kb / SB) & 1);
+                mbar_wait(bar_full + 8 * sa, (kb / SA) & 1);
                 tc_fence_after();
-                const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t st = smem_u32(smem + (size_t)sa * a_stage);
                 const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + a_bytes);
-                const uint32_t bb = st + (PASSES == 3 ? 2 : 1) * a_bytes;
+                const uint32_t bb = smem_u32(smem_b + (size_t)sb * b_stage);
                 const uint64_t b_hi = make_desc(bb), b_lo = make_desc(bb + b_bytes);
 #pragma unroll
                 for (int k = 0; k < kBlockK / kUmmaK; ++k) {
@@ -361,7 +370,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
                         umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
                     }
                 }
-                umma_commit(bar_empty + 8 * stage);   // stage reusable once these MMAs have read it
+                umma_commit(bar_empty + 8 * sa);      // both stages reusable once these MMAs have read them
+                umma_commit(bar_emptyb + 8 * sb);
             }
             umma_commit(bar_acc);                      // accumulator complete -> epilogue
         }
@@ -371,12 +381,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         if (lane == 0) {
             const uint32_t tx = (PASSES == 3 ? 2u : 1u) * b_bytes;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int stage = kb % stages;
-                mbar_wait(bar_empty + 8 * stage, ((kb / stages) & 1) ^ 1);
-                const uint32_t bb = smem_u32(smem + (size_t)stage * stage_bytes) + (PASSES == 3 ? 2 : 1) * a_bytes;
-                mbar_arrive_expect_tx(bar_full + 8 * stage, tx);
-                tma_load_2d(bb, &map_hi, bar_full + 8 * stage, kb * kBlockK, n0);
-                if (PASSES == 3) tma_load_2d(bb + b_bytes, &map_lo, bar_full + 8 * stage, kb * kBlockK, n0);
+                const int sb = kb % SB;
+                mbar_wait(bar_emptyb + 8 * sb, ((kb / SB) & 1) ^ 1);
+                const uint32_t bb = smem_u32(smem_b + (size_t)sb * b_stage);
+                mbar_arrive_expect_tx(bar_fullb + 8 * sb, tx);
+                tma_load_2d(bb, &map_hi, bar_fullb + 8 * sb, kb * kBlockK, n0);
+                if (PASSES == 3) tma_load_2d(bb + b_bytes, &map_lo, bar_fullb + 8 * sb, kb * kBlockK, n0);
             }
         }
         __syncwarp();
@@ -504,12 +514,19 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     if (n_tile <= 0) return -2;
     ny = (F + n_tile - 1) / n_tile;
     p.n_tile = n_tile;
-    size_t stage_bytes = (size_t)(passes == 3 ? 2 : 1) * (kBlockM * 128 + (size_t)n_tile * 128);
-    int stages = (int)((196 * 1024) / stage_bytes);
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) return -3;
-    p.stages = stages;
-    size_t smem = stage_bytes * stages + 1024;
+    const size_t a_stage = (size_t)(passes == 3 ? 2 : 1) * kBlockM * 128, b_stage = (size_t)(passes == 3 ? 2 : 1) * n_tile * 128;
+    const size_t budget = 208 * 1024;
+    // the gather ring gets the depth first (measured: 3 A + 2 B stages beat 2 A + 3 B by 1.4x at N = 192), the
+    // TMA ring takes what is left, at least two stages each
+    int sa = (int)((budget - 2 * b_stage) / a_stage);
+    if (sa > kMaxStages) sa = kMaxStages;
+    if (sa < 2) return -3;
+    int sb = (int)((budget - sa * a_stage) / b_stage);
+    if (sb > kMaxStages) sb = kMaxStages;
+    if (sb < 2) return -3;
+    p.stages_a = sa;
+    p.stages_b = sb;
+    size_t smem = sa * a_stage + sb * b_stage + 1024;
     alignas(64) CUtensorMap map_hi, map_lo;
     int rc = make_weight_map(&map_hi, wt_hi, F, p.S * C, n_tile);
     if (rc) return rc;
