@@ -343,8 +343,17 @@ def main():
     # ---- timed region 2: end to end through the runner with pinned HOST buffers ----------------------
     barrier()
     t0 = time.perf_counter()
-    for i in range(0, args.steps, lanes):
-        labels = run_group_host(i, min(lanes, args.steps - i))
+    if lanes == 1:
+        for i in range(args.steps):
+            labels = run_group_host(i, 1)
+    else:   # one group of windows is always queued behind the one the host is waiting for
+        pending = None
+        for i in range(0, args.steps, lanes):
+            ticket = multi.submit([host[(i + j) % len(host)] for j in range(min(lanes, args.steps - i))])
+            if pending is not None:
+                labels = multi.collect(pending)[-1]
+            pending = ticket
+        labels = multi.collect(pending)[-1]
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

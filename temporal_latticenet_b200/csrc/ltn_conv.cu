@@ -32,6 +32,7 @@
 //    memory (vq_dev / vx_dev), so the launch needs no host synchronisation.
 #include "ltn_common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace {
 
@@ -76,6 +77,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
                  ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+// the same tile delivered to the same shared-memory offset of every CTA in `cta_mask` (one L2 read per cluster)
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                  uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -87,6 +104,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at this offset in EVERY CTA of the mask once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in bits
@@ -150,6 +172,7 @@ struct ConvParams {
     int Vq, Vx, C, S, F, ldo, relu;
     int n_tile;            // output channels per CTA (<= 256, multiple of 16)
     int stages_a, stages_b; // depth of the A (gathered) and B (TMA) shared-memory rings
+    int cluster;            // CTAs per cluster sharing the weight tiles by TMA multicast (1, 2 or 4)
 };
 
 template <int PASSES>
@@ -164,7 +187,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
     const int Vq = p.vq_dev ? min(p.Vq, __ldg(p.vq_dev)) : p.Vq;
     const int Vx = p.vx_dev ? min(p.Vx, __ldg(p.vx_dev)) : p.Vx;
     const int row0 = blockIdx.x * kBlockM;
-    if (row0 >= Vq) return;  // uniform per CTA, before any barrier / TMEM allocation
+    const int CL = p.cluster;
+    // uniform per CLUSTER, before any barrier / TMEM allocation: a CTA without rows still takes part in its
+    // cluster's weight multicast when a sibling has rows
+    if ((int)(blockIdx.x / CL * CL) * kBlockM >= Vq) return;
+    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cta_mask = (uint16_t)((1u << CL) - 1u);
     const int n0 = blockIdx.y * p.n_tile;
     const int N = min(p.n_tile, p.F - n0);     // valid output channels of this CTA (multiple of 8)
     const int Nmma = (N + 15) & ~15;           // MMA N (multiple of 16 at M = 128); the extra weight rows are TMA zero fill
@@ -195,8 +223,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (int s = 0; s < SB; ++s) {
-            mbar_init(bar_fullb + 8 * s, 1);                   // the TMA thread's expect_tx arrive (+ the bytes)
-            mbar_init(bar_emptyb + 8 * s, 1);
+            mbar_init(bar_fullb + 8 * s, 1);                   // the TMA thread's expect_tx arrive (+ the bytes of all CL slices)
+            mbar_init(bar_emptyb + 8 * s, CL);                 // every CTA of the cluster has finished reading the stage
         }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -230,6 +258,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (CL > 1) cluster_sync_all();   // sibling barriers are initialised before any remote arrive / multicast lands
     const uint32_t tmem_base = tmem_slot;
 
     if (warp < 8) {
@@ -261,7 +290,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
             for (int j = 0; j < 8; ++j) {
                 const int s = __shfl_sync(0xffffffffu, src_lane, sub + 4 * j);
                 dsrc[j] = s;
-                if (s >= 0) dst[j] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)s * p.C + c0) + chunk);
+                // unconditional load (row 0 stands in for an absent neighbour and is discarded at staging time): a
+                // predicated load would be followed by a predicated register move that waits for it on the spot
+                dst[j] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)(s >= 0 ? s : 0) * p.C + c0) + chunk);
             }
         };
         auto consume = [&](int kb, const float4* cur, const int* cur_src) {
@@ -371,7 +402,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
                     }
                 }
                 umma_commit(bar_empty + 8 * sa);      // both stages reusable once these MMAs have read them
-                umma_commit(bar_emptyb + 8 * sb);
+                if (CL > 1) umma_commit_mcast(bar_emptyb + 8 * sb, cta_mask);   // ... the weight stage in every sibling
+                else umma_commit(bar_emptyb + 8 * sb);
             }
             umma_commit(bar_acc);                      // accumulator complete -> epilogue
         }
@@ -384,14 +416,24 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
                 const int sb = kb % SB;
                 mbar_wait(bar_emptyb + 8 * sb, ((kb / SB) & 1) ^ 1);
                 const uint32_t bb = smem_u32(smem_b + (size_t)sb * b_stage);
-                mbar_arrive_expect_tx(bar_fullb + 8 * sb, tx);
-                tma_load_2d(bb, &map_hi, bar_fullb + 8 * sb, kb * kBlockK, n0);
-                if (PASSES == 3) tma_load_2d(bb + b_bytes, &map_lo, bar_fullb + 8 * sb, kb * kBlockK, n0);
+                mbar_arrive_expect_tx(bar_fullb + 8 * sb, tx);   // the whole stage: own slice + the siblings' multicasts
+                if (CL > 1) {
+                    // this CTA fetches rows [rank * n_tile/CL, +n_tile/CL) of the tile and delivers them to all siblings
+                    const int rows = p.n_tile / CL;
+                    const uint32_t off = cta_rank * (uint32_t)rows * 128u;
+                    tma_load_2d_mcast(bb + off, &map_hi, bar_fullb + 8 * sb, kb * kBlockK, n0 + (int)cta_rank * rows, cta_mask);
+                    if (PASSES == 3)
+                        tma_load_2d_mcast(bb + b_bytes + off, &map_lo, bar_fullb + 8 * sb, kb * kBlockK, n0 + (int)cta_rank * rows, cta_mask);
+                } else {
+                    tma_load_2d(bb, &map_hi, bar_fullb + 8 * sb, kb * kBlockK, n0);
+                    if (PASSES == 3) tma_load_2d(bb + b_bytes, &map_lo, bar_fullb + 8 * sb, kb * kBlockK, n0);
+                }
             }
         }
         __syncwarp();
     }
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // nobody leaves while a sibling may still signal its barriers / fill its stages
     if (warp == kMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
@@ -491,6 +533,7 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
                 const float* bias, const float* res, float* out, int ldo, double* out_sums, int out_groups, int passes,
                 void* stream) {
     if (Vq <= 0) return 0;
+    if (Vx <= 0) return -2;   // row 0 of x must be readable (stand-in address of absent neighbours)
     const bool affine = a_scale || gn_sums;
     if (C <= 0 || C % kBlockK || (affine && C > 256) || F <= 0 || F % 8 || S < 1 || (passes != 1 && passes != 3) || ldo % 4) return -2;
     if ((a_scale == nullptr) != (a_shift == nullptr) || (a_scale && gn_sums)) return -2;
@@ -527,22 +570,38 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     p.stages_a = sa;
     p.stages_b = sb;
     size_t smem = sa * a_stage + sb * b_stage + 1024;
+    // Row tiles that share a weight tile are grouped into thread-block clusters: each CTA fetches 1/CL of the
+    // tile and multicasts it, so the L2 -> SM weight traffic (3x the gather traffic at N = 192) drops by CL.
+    // Measured on B200 (bench_conv3, V = 13.7k): 192->192 72 us unclustered vs 78 us with clusters of 4, 128->128 on
+    // 4.6k vertices 39 us vs 75 us -- the siblings' stages free in lock-step, which costs more than the L2 traffic
+    // saves at these sizes.  Clusters therefore stay off unless LTN_CONV_CLUSTER asks for them.
+    int cl = 1;
+    static const int want_cl = []() { const char* e = getenv("LTN_CONV_CLUSTER"); return e ? atoi(e) : 1; }();
+    if (want_cl >= 4 && row_tiles >= 4 && n_tile % 32 == 0) cl = 4;
+    else if (want_cl >= 2 && row_tiles >= 2) cl = 2;
+    p.cluster = cl;
     alignas(64) CUtensorMap map_hi, map_lo;
-    int rc = make_weight_map(&map_hi, wt_hi, F, p.S * C, n_tile);
+    int rc = make_weight_map(&map_hi, wt_hi, F, p.S * C, n_tile / cl);
     if (rc) return rc;
-    rc = make_weight_map(&map_lo, passes == 3 ? wt_lo : wt_hi, F, p.S * C, n_tile);
+    rc = make_weight_map(&map_lo, passes == 3 ? wt_lo : wt_hi, F, p.S * C, n_tile / cl);
     if (rc) return rc;
-    dim3 grid(row_tiles, ny);
-    cudaError_t e;
-    if (passes == 3) {
-        e = cudaFuncSetAttribute(k_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        k_conv_tc<3><<<grid, kThreads, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
-    } else {
-        e = cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        k_conv_tc<1><<<grid, kThreads, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
-    }
+    cudaError_t e = cudaFuncSetAttribute(passes == 3 ? (const void*)k_conv_tc<3> : (const void*)k_conv_tc<1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((row_tiles + cl - 1) / cl * cl, ny);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = passes == 3 ? cudaLaunchKernelEx(&cfg, k_conv_tc<3>, map_hi, map_lo, p) : cudaLaunchKernelEx(&cfg, k_conv_tc<1>, map_hi, map_lo, p);
+    if (e != cudaSuccess) return (int)e;
     LTN_CHECK_LAUNCH();
     return 0;
 }

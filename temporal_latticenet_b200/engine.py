@@ -237,12 +237,17 @@ class MultiWindowRunner:
             cur.wait_stream(self.streams[i])
         return outs
 
-    def infer_windows(self, windows_host):
-        """pinned host buffers in, predicted labels (pinned host int64) out, synchronised"""
+    # ---- end to end: pinned host buffers in, labels out; submission and collection are decoupled so the next
+    # group of windows is already queued while the host waits for the previous one -----------------------------
+    def submit(self, windows_host):
+        """queues up to `lanes` windows (pinned host tensors); returns a ticket for collect()"""
         dev = self.device
         cur = torch.cuda.current_stream()
-        labels = []
-        wins = []
+        slot = getattr(self, "_slot", 0)
+        self._slot = slot ^ 1
+        if not hasattr(self, "_host_out"):
+            self._host_out = {}
+        wins, ticket = [], {"host": windows_host, "labels": [], "counts": [], "events": []}
         for i, w in enumerate(windows_host):
             self.streams[i].wait_stream(cur)
             with torch.cuda.stream(self.streams[i]):
@@ -255,30 +260,50 @@ class MultiWindowRunner:
                     with torch.cuda.stream(self.streams[i]):
                         outs[i] = self.lanes[i]._run_frame((t == 0, t == len(w) - 1), w[t][0], w[t][1])
         for i, w in enumerate(wins):
+            lane, n = self.lanes[i], w[-1][0].shape[0]
+            with torch.cuda.stream(self.streams[i]):
+                lab = outs[i][:n].argmax(1)
+                key = (i, slot)
+                buf = self._host_out.get(key)
+                if buf is None or buf[0].shape[0] < n:
+                    buf = (torch.empty(max(n, lane.caps["n"]), dtype=torch.int64).pin_memory(),
+                           torch.zeros(len(lane.caps["v"]), dtype=torch.int32).pin_memory())
+                    self._host_out[key] = buf
+                buf[0][:n].copy_(lab, non_blocking=True)
+                lvl, j = lane.static_lattice, 0
+                while lvl is not None and j < len(lane.caps["v"]):
+                    buf[1][j:j + 1].copy_(lvl.hash_table.count_tensor(), non_blocking=True)
+                    lvl, j = lvl._coarse, j + 1
+                ev = torch.cuda.Event()
+                ev.record()
+            ticket["labels"].append(buf[0][:n])
+            ticket["counts"].append(buf[1])
+            ticket["events"].append(ev)
+        return ticket
+
+    def collect(self, ticket):
+        """waits for a ticket's windows; returns their predicted labels (pinned host int64 tensors, valid until
+        the slot is reused two submissions later).  A window that outgrew the static capacities is re-run on
+        the eager path."""
+        out = []
+        for i, (lab, counts, ev) in enumerate(zip(ticket["labels"], ticket["counts"], ticket["events"])):
+            ev.synchronize()
             lane = self.lanes[i]
-            with torch.cuda.stream(self.streams[i]):
-                lab = outs[i][: w[-1][0].shape[0]].argmax(1)
-                if lane._labels_host is None or lane._labels_host.shape[0] < lab.shape[0]:
-                    lane._labels_host = torch.empty(lab.shape[0], dtype=torch.int64).pin_memory()
-                host = lane._labels_host[: lab.shape[0]]
-                host.copy_(lab, non_blocking=True)
-                labels.append(host)
-        ok = True
-        for i in range(len(wins)):
-            with torch.cuda.stream(self.streams[i]):
-                ok = self.lanes[i].counts_ok() and ok      # synchronises the lane
-        if not ok:
-            out = []
-            for i, w in enumerate(windows_host):
-                lane = self.lanes[i]
+            if all(int(c) < cap for c, cap in zip(counts.tolist(), lane.caps["v"])):
+                out.append(lab)
+            else:
                 lane.fallbacks += 1
                 lane._force_eager = True
                 try:
-                    out.append(WindowRunner.infer_window(lane, w))
+                    with torch.cuda.stream(self.streams[i]):
+                        out.append(WindowRunner.infer_window(lane, ticket["host"][i]).clone())
                 finally:
                     lane._force_eager = False
-            return out
-        return labels
+        return out
+
+    def infer_windows(self, windows_host):
+        """pinned host buffers in, predicted labels (pinned host int64) out, synchronised"""
+        return self.collect(self.submit(windows_host))
 
     def kernels_per_window(self, nr_frames):
         return self.lanes[0].kernels_per_window(nr_frames)
