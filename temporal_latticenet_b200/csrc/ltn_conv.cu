@@ -181,7 +181,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 1];
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_affine[2 * 256];
+    __shared__ __align__(16) float s_affine[2 * 256];
     __shared__ float s_colsum[2 * 256];
 
     const int Vq = p.vq_dev ? min(p.Vq, __ldg(p.vq_dev)) : p.Vq;
@@ -272,50 +272,60 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         const int wrow0 = (warp & 3) * 32;         // first tile row of this warp
         const int chunk = lane & 7, sub = lane >> 3;
         const int my_v = row0 + wrow0 + lane;      // the row whose neighbour id this lane looks up
-        int cur_slot = -1, src_lane = -1;
+        // All ring / k-block bookkeeping is incremental: no integer division in the loop.
+        const float4* x4 = reinterpret_cast<const float4*>(p.x);
+        const uint32_t c4 = (uint32_t)p.C >> 2;
         float4 buf[2][8];      // two register buffers, used with compile-time indices (loop unrolled by 2)
-        int bsrc[2][8];
-        auto issue = [&](int kb, float4* dst, int* dsrc) {
-            const int slot = kb / kb_per_slot;
-            const int c0 = (kb - slot * kb_per_slot) * kBlockK;
-            if (slot != cur_slot) {
-                cur_slot = slot;
-                src_lane = -1;
+        uint32_t bmask[2];     // bit j: row j of the buffer is a present neighbour
+        uint32_t rowidx[8];    // float4 index of (row j's source vertex, this lane's chunk), refreshed per slot
+        uint32_t rmask = 0;
+        int i_slot = group / kb_per_slot, i_c0 = (group - i_slot * kb_per_slot) * kBlockK, i_cur = -1;   // issue position
+        int c_c0 = i_c0, c_stage = group % SA;                                                          // consume position
+        uint32_t c_par = ((group / SA) & 1) ^ 1;
+        auto issue = [&](float4* dst, uint32_t& dmask) {
+            if (i_slot != i_cur) {
+                i_cur = i_slot;
+                int src_lane = -1;
                 if (my_v < Vq) {
-                    src_lane = p.nbr ? __ldg(p.nbr + (size_t)my_v * p.S + slot) : my_v;
+                    src_lane = p.nbr ? __ldg(p.nbr + (size_t)my_v * p.S + i_slot) : my_v;
                     if (src_lane >= Vx) src_lane = -1;
                 }
-            }
+                rmask = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int s = __shfl_sync(0xffffffffu, src_lane, sub + 4 * j);
-                dsrc[j] = s;
-                // unconditional load (row 0 stands in for an absent neighbour and is discarded at staging time): a
-                // predicated load would be followed by a predicated register move that waits for it on the spot
-                dst[j] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)(s >= 0 ? s : 0) * p.C + c0) + chunk);
+                for (int j = 0; j < 8; ++j) {
+                    const int sv = __shfl_sync(0xffffffffu, src_lane, sub + 4 * j);
+                    // row 0 stands in for an absent neighbour (loaded unconditionally, discarded at staging time): a
+                    // predicated load would be followed by a predicated register move that waits for it on the spot
+                    rowidx[j] = (uint32_t)(sv >= 0 ? sv : 0) * c4 + (uint32_t)chunk;
+                    rmask |= (sv >= 0 ? 1u : 0u) << j;
+                }
             }
+            dmask = rmask;
+            const uint32_t o = (uint32_t)i_c0 >> 2;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = __ldg(x4 + rowidx[j] + o);
+            i_c0 += kGroups * kBlockK;
+            while (i_c0 >= p.C) { i_c0 -= p.C; ++i_slot; }
         };
-        auto consume = [&](int kb, const float4* cur, const int* cur_src) {
-            const int stage = kb % SA;
-            const uint32_t parity = ((kb / SA) & 1) ^ 1;
-            const int c0 = (kb % kb_per_slot) * kBlockK;
-            if (lane == 0) mbar_wait(bar_empty + 8 * stage, parity);   // one waiter per warp
+        auto consume = [&](const float4* cur, uint32_t cmask) {
+            if (lane == 0) mbar_wait(bar_empty + 8 * c_stage, c_par);   // one waiter per warp
             __syncwarp();
-            uint8_t* a_hi0 = smem + (size_t)stage * a_stage;
-            const float* sc = s_affine + c0 + 4 * chunk;
-            const float* sh = sc + 256;
+            uint8_t* a_hi0 = smem + (size_t)c_stage * a_stage;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (affine) {
+                sc = *reinterpret_cast<const float4*>(s_affine + c_c0 + 4 * chunk);
+                sh = *reinterpret_cast<const float4*>(s_affine + 256 + c_c0 + 4 * chunk);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int r = wrow0 + sub + 4 * j;
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cur_src[j] >= 0) {
-                    t = cur[j];
-                    if (affine) {
-                        t.x = fmaf(t.x, sc[0], sh[0]); t.y = fmaf(t.y, sc[1], sh[1]);
-                        t.z = fmaf(t.z, sc[2], sh[2]); t.w = fmaf(t.w, sc[3], sh[3]);
-                    }
-                    if (p.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+                float4 t = cur[j];
+                if (affine) {
+                    t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y);
+                    t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
                 }
+                if (p.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+                if (!((cmask >> j) & 1u)) t = make_float4(0.f, 0.f, 0.f, 0.f);   // absent neighbour / row beyond the tile
                 const float4 h = make_float4(tf32_hi(t.x), tf32_hi(t.y), tf32_hi(t.z), tf32_hi(t.w));
                 uint8_t* dst = a_hi0 + r * 128 + ((chunk ^ (r & 7)) << 4);
                 *reinterpret_cast<float4*>(dst) = h;
@@ -324,17 +334,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
             }
             fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full + 8 * stage);   // one arrival per warp, not 32 serialised ones
+            if (lane == 0) mbar_arrive(bar_full + 8 * c_stage);   // one arrival per warp, not 32 serialised ones
+            c_c0 += kGroups * kBlockK;
+            while (c_c0 >= p.C) c_c0 -= p.C;
+            c_stage += kGroups;
+            if (c_stage >= SA) { c_stage -= SA; c_par ^= 1u; }
         };
         // software pipeline: the loads of the next k-block are in flight while the current one is staged
-        if (group < num_kb) issue(group, buf[0], bsrc[0]);
+        if (group < num_kb) issue(buf[0], bmask[0]);
         for (int kb = group; kb < num_kb; kb += 2 * kGroups) {
             const int kb1 = kb + kGroups, kb2 = kb + 2 * kGroups;
-            if (kb1 < num_kb) issue(kb1, buf[1], bsrc[1]);
-            consume(kb, buf[0], bsrc[0]);
+            if (kb1 < num_kb) issue(buf[1], bmask[1]);
+            consume(buf[0], bmask[0]);
             if (kb1 < num_kb) {
-                if (kb2 < num_kb) issue(kb2, buf[0], bsrc[0]);
-                consume(kb1, buf[1], bsrc[1]);
+                if (kb2 < num_kb) issue(buf[0], bmask[0]);
+                consume(buf[1], bmask[1]);
             }
         }
 
@@ -383,10 +397,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         if (lane == 0) {
             // instruction descriptor: D = F32 [4,6), A = B = TF32 [7,10) [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nmma >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int sa = kb % SA, sb = kb % SB;
-                mbar_wait(bar_fullb + 8 * sb, (kb / SB) & 1);
-                mbar_wait(bar_full + 8 * sa, (kb / SA) & 1);
+                mbar_wait(bar_fullb + 8 * sb, pb);
+                mbar_wait(bar_full + 8 * sa, pa);
                 tc_fence_after();
                 const uint32_t st = smem_u32(smem + (size_t)sa * a_stage);
                 const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + a_bytes);
@@ -404,6 +419,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
                 umma_commit(bar_empty + 8 * sa);      // both stages reusable once these MMAs have read them
                 if (CL > 1) umma_commit_mcast(bar_emptyb + 8 * sb, cta_mask);   // ... the weight stage in every sibling
                 else umma_commit(bar_emptyb + 8 * sb);
+                if (++sa == SA) { sa = 0; pa ^= 1u; }
+                if (++sb == SB) { sb = 0; pb ^= 1u; }
             }
             umma_commit(bar_acc);                      // accumulator complete -> epilogue
         }
@@ -412,9 +429,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         // ===================== TMA warp: stream the pre-split weight tiles =====================
         if (lane == 0) {
             const uint32_t tx = (PASSES == 3 ? 2u : 1u) * b_bytes;
+            int sb = 0;
+            uint32_t pb = 1;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int sb = kb % SB;
-                mbar_wait(bar_emptyb + 8 * sb, ((kb / SB) & 1) ^ 1);
+                mbar_wait(bar_emptyb + 8 * sb, pb);
                 const uint32_t bb = smem_u32(smem_b + (size_t)sb * b_stage);
                 mbar_arrive_expect_tx(bar_fullb + 8 * sb, tx);   // the whole stage: own slice + the siblings' multicasts
                 if (CL > 1) {
@@ -428,6 +446,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
                     tma_load_2d(bb, &map_hi, bar_fullb + 8 * sb, kb * kBlockK, n0);
                     if (PASSES == 3) tma_load_2d(bb + b_bytes, &map_lo, bar_fullb + 8 * sb, kb * kBlockK, n0);
                 }
+                if (++sb == SB) { sb = 0; pb ^= 1u; }
             }
         }
         __syncwarp();
