@@ -206,6 +206,7 @@ class LatticeNetSeq(torch.nn.Module):
 
     def forward(self, ls, positions, values, early_return=False, with_gradient=True, vis_aflow=False):
         seq, rnn = self.sequence_learning, self.rnn_modules
+        ops.begin_frame(self, positions.device)
         reset_hashmap = not (seq and not self.first_sequence)  # models.py:287-289
         with torch.no_grad():  # Q9
             ls, distributed, indices, weights = self.distribute(ls, positions, values, reset_hashmap)

@@ -203,18 +203,42 @@ def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, gn=None, relu=
                                  TC_PASSES if passes is None else passes, _lib.stream())
     _lib.check(rc, "ltn_conv_tc")
     if out_sums is not None:
-        out._ltn_gn_sums = out_sums   # travels with the tensor to the next layer's GroupNorm
+        out._ltn_gn_sums = (_FRAME["id"], out_sums)   # travels with the tensor to the next layer's GroupNorm
     return out
+
+
+_SUMS_SLOTS = 96   # accumulators handed out per frame before falling back to individual allocations
+_FRAME = {"arena": None, "used": 0, "id": 0}
+
+
+def begin_frame(owner, device):
+    """One memset for all of a frame's [G,2] statistics accumulators.  The arena belongs to `owner` (the
+    model instance: every window runner / graph lane has its own, so concurrently replayed graphs never
+    share accumulators); statistics attached to tensors are only trusted within the frame that made them."""
+    buf = getattr(owner, "_ltn_sums_arena", None)
+    if buf is None or buf.device != device:
+        buf = torch.zeros(_SUMS_SLOTS, 32, 2, dtype=torch.float64, device=device)
+        owner._ltn_sums_arena = buf
+    else:
+        buf.zero_()
+    _FRAME["arena"], _FRAME["used"] = buf, 0
+    _FRAME["id"] += 1
 
 
 def new_sums(nr_channels, device):
     """zeroed [G,2] accumulator for the epilogue statistics of a layer with `nr_channels` outputs"""
-    return torch.zeros(gn_groups(nr_channels), 2, dtype=torch.float64, device=device)
+    g = gn_groups(nr_channels)
+    buf = _FRAME["arena"]
+    if buf is not None and buf.device == device and _FRAME["used"] < _SUMS_SLOTS and g <= 32:
+        t = buf[_FRAME["used"], :g]
+        _FRAME["used"] += 1
+        return t
+    return torch.zeros(g, 2, dtype=torch.float64, device=device)
 
 
 def sums_of(x, groups):
     """GroupNorm statistics of x: the ones its producing kernel left behind, else one pass over x"""
     s = getattr(x, "_ltn_gn_sums", None)
-    if s is not None and s.shape[0] == groups:
-        return s
+    if s is not None and s[0] == _FRAME["id"] and s[1].shape[0] == groups:
+        return s[1]
     return gn_sums(x, groups)
