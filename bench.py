@@ -408,6 +408,14 @@ def main():
     ops.matmul, ops.linear = mm_orig, lin_orig
     summ = probe.summary()
     pk = peaks()
+    traffic, traffic_note = None, None
+    tpath = os.path.join(REPO, "profiles", "r1_conv_tc_ncu_full.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj["traffic_bytes"]
+        traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (%s) from ncu --set full: %.2f MB against %.2f MB "
+                        "algorithmic for that launch" % (tj["launch"], tj["traffic_bytes"] / 1e6, tj["algorithmic_bytes"] / 1e6))
     conv = [v for k, v in summ.items() if k.startswith("conv_tc") or k == "ltn_conv_tc"]
     roofline = None
     if conv and sum(v["ms_total"] for v in conv) > 0:
@@ -415,7 +423,7 @@ def main():
         achieved = fl_c / (ms_c * 1e-3) / 1e12
         roofline = {"kernel": "k_conv_tc<3> (fused gather + tcgen05 tf32 GEMM, fp32-parity 3-pass split)", "bound": "tensor",
                     "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " (bf16 sustained)",
+                    "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"] + " (bf16 sustained)",
                     "note": "achieved = algorithmic 2*V*S*C*F flop / CUDA-event time over every launch of the kernel in a repeat "
                             "of the timed steps (op-by-op launches); the parity mode issues 3 tf32 MMAs per product and tf32 "
                             "runs at half the bf16 rate, so 1/6 of the bf16 peak is this kernel's ceiling",
