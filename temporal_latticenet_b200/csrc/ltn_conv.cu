@@ -39,10 +39,10 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 8;          // tf32: 32 bytes per MMA
-constexpr int kGroups = 2;         // producer warpgroups (alternate k-blocks)
+constexpr int kGroups = 2;         // producer warpgroups (round-robin k-blocks); 3 measured slower (67 vs 60 us at 192->192)
 constexpr int kGroupThreads = 128;
-constexpr int kMmaWarp = 8, kTmaWarp = 9;
-constexpr int kThreads = 320;      // 8 producer/epilogue warps + MMA warp + TMA warp
+constexpr int kMmaWarp = 4 * kGroups, kTmaWarp = 4 * kGroups + 1;
+constexpr int kThreads = 32 * (4 * kGroups + 2);   // producer/epilogue warps + MMA warp + TMA warp
 constexpr int kMaxStages = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -261,7 +261,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
     if (CL > 1) cluster_sync_all();   // sibling barriers are initialised before any remote arrive / multicast lands
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp < 8) {
+    if (warp < 4 * kGroups) {
         // ===================== producers: gather A rows (two warpgroups, alternate k-blocks) ==========
         // Quarter-warp per row: 8 lanes fetch the 8 16-byte chunks of one 128-byte row segment, so one
         // warp-wide LDG.128 touches 4 whole cache lines (not 32 partial ones) and the swizzled stores of a
@@ -338,7 +338,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
             c_c0 += kGroups * kBlockK;
             while (c_c0 >= p.C) c_c0 -= p.C;
             c_stage += kGroups;
-            if (c_stage >= SA) { c_stage -= SA; c_par ^= 1u; }
+            while (c_stage >= SA) { c_stage -= SA; c_par ^= 1u; }
         };
         // software pipeline: the loads of the next k-block are in flight while the current one is staged
         if (group < num_kb) issue(buf[0], bmask[0]);
@@ -359,7 +359,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         const int er = (warp & 3) * 32 + lane;     // accumulator row = TMEM lane
         const int ev = row0 + er;
         const bool erow_ok = ev < Vq;
-        for (int cb = group * 32; cb < N; cb += 64) {
+        for (int cb = group * 32; cb < N; cb += 32 * kGroups) {
             float acc[32];
             tmem_ld32(t_lane + (uint32_t)cb, acc);   // warp-collective: executed by every lane
             const int ncol = min(32, N - cb);

@@ -166,6 +166,23 @@ def k_major(weight, transposed=False):
     return hi, lo
 
 
+def k_major_padded(weight, rows):
+    """k_major of an nn.Linear weight [F,K] zero-padded to `rows` output rows (F is not a multiple of 8)"""
+    key = (id(weight), "pad", int(rows))
+    hit = _WT_CACHE.get(key)
+    ver = weight._version
+    if hit is not None and hit[0] == ver and hit[1]() is weight and hit[3] == weight.data_ptr():
+        return hit[2]
+    F, K = weight.shape
+    wp = torch.zeros(rows, K, dtype=torch.float32, device=weight.device)
+    wp[:F] = weight.detach()
+    hi = torch.empty(rows, K, dtype=torch.float32, device=weight.device)
+    lo = torch.empty(rows, K, dtype=torch.float32, device=weight.device)
+    _lib.check(_lib.load().ltn_split_tf32(_lib.ptr(wp), K, rows, 1, _lib.ptr(hi), _lib.ptr(lo), _lib.stream()), "ltn_split_tf32")
+    _WT_CACHE[key] = (ver, weakref.ref(weight), (hi, lo), weight.data_ptr())
+    return hi, lo
+
+
 def gn_sums(x, groups):
     """[G,2] double: per-group sum and sum of squares of x [V,C] (GroupNorm over [1,C,V])"""
     x = x.contiguous()
