@@ -99,3 +99,59 @@ def test_multi_window_runner_matches_eager_runner():
     labels = [l.clone() for l in multi.infer_windows(host)]
     for l, w in zip(labels, want):
         assert (l.numpy() == w.argmax(1)).mean() > 0.999
+
+
+@pytest.mark.parametrize("rnn", [["aflow", "aflow", "aflow", "aflow"], ["lstm", "none", "none", "gru"], ["gru", "gru", "aflow", "gru"]])
+def test_graph_runner_other_fusion_configs(rnn, tmp_path):
+    """static-capacity graphs for every fusion kind that has a device-side-size implementation (BASELINE config 5
+    uses aflow x4); 3-frame windows exercise first / middle / last graphs"""
+    import hjson
+    import os
+    from temporal_latticenet_b200.engine import GraphWindowRunner
+    from temporal_latticenet_b200.runner import WindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    with open(CFG) as f:
+        cfg = hjson.loads(f.read())
+    cfg["model"]["rnn_modules"] = rnn
+    path = os.path.join(str(tmp_path), "cfg_%s.cfg" % "_".join(rnn))
+    with open(path, "w") as f:
+        f.write(hjson.dumps(cfg))
+    dev = torch.device("cuda:0")
+    wins = [_window(11, frames=3, n=4000), _window(12, frames=3, n=3600)]
+    to_dev = lambda w: [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]  # noqa: E731
+    eager = WindowRunner(path, 26, dev).materialise_parameters(to_dev(wins[0]), seeded_state)
+    graph = GraphWindowRunner(path, 26, dev).materialise_parameters(to_dev(wins[0]), seeded_state)
+    assert graph.supported
+    graph.plan(to_dev(wins[0]))
+    graph.capture(to_dev(wins[0]))
+    for rep in range(2):
+        for w in wins:
+            fd = to_dev(w)
+            want = eager.infer_window_device(fd).cpu().numpy()
+            got = graph.infer_window_device(fd).cpu().numpy()
+            assert graph.counts_ok()
+            finite = np.isfinite(want)
+            assert np.array_equal(finite, np.isfinite(got))   # AFlow's 0/0 rows (quirk Q5) stay where the eager path has them
+            err = float(np.abs(got[finite] - want[finite]).max()) / float(np.abs(want[finite]).max())
+            assert err < 1e-4, err
+
+
+def test_unsupported_fusion_falls_back_to_eager(tmp_path):
+    import hjson
+    import os
+    from temporal_latticenet_b200.engine import GraphWindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    with open(CFG) as f:
+        cfg = hjson.loads(f.read())
+    cfg["model"]["rnn_modules"] = ["maxpool", "cga", "linear", "gru"]
+    path = os.path.join(str(tmp_path), "cfg_unsupported.cfg")
+    with open(path, "w") as f:
+        f.write(hjson.dumps(cfg))
+    dev = torch.device("cuda:0")
+    w = _window(13, frames=3, n=3000)
+    fd = [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]
+    g = GraphWindowRunner(path, 26, dev).materialise_parameters(fd, seeded_state)
+    assert not g.supported
+    g.capture(fd)
+    out = g.infer_window_device(fd)
+    assert out.shape == (w[-1][0].shape[0], 26) and len(g.graphs) == 0
