@@ -178,6 +178,82 @@ class Probe:
         return out
 
 
+def hbm_kernels(dev, window_np, pk):
+    """The metric's second half: splat / slice / im2row (and distribute) HBM GB/s against the measured copy peak.
+    One scan moves too few bytes to say anything about bandwidth (distribute on 125k points = 16 MB = 2.4 us at
+    peak), so these are timed on the window's 4 scans ACCUMULATED into one cloud (~500k points, the
+    accumulate_clouds shape of BASELINE config 5), 20 back-to-back launches inside a CUDA graph, CUDA events around
+    the replay.  Algorithmic bytes per SURVEY.md 8(d): compulsory traffic only."""
+    import numpy as np
+    import torch
+    from temporal_latticenet_b200 import _lib, funcs
+    from temporal_latticenet_b200.lattice import Lattice
+    lib = _lib.load()
+    p = _lib.ptr
+    pos = torch.from_numpy(np.concatenate([f[0] for f in window_np], 0)).to(dev)
+    val = torch.from_numpy(np.concatenate([f[1] for f in window_np], 0)).to(dev)
+    N = pos.shape[0]
+    ls = Lattice(100000, 0.6, device=dev)
+    rows, idx, w = ls.distribute(pos, val, True)
+    V = ls.nr_lattice_vertices()
+    nbr = ls.neighbours()
+
+    def graph_ms(fn, n=20):
+        fn()
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(n):
+                    fn()
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = []
+
+    def add(name, ms, nbytes, note):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out.append({"kernel": name, "us": 1e3 * ms, "algorithmic_mb": nbytes / 1e6, "achieved": gbs, "unit": "GB/s", "peak": pk["hbm_gbs"],
+                    "frac": gbs / pk["hbm_gbs"], "shape": note})
+    C = 64
+    feat = torch.randn(V, C, device=dev)
+    rows_out = torch.empty(V, 9 * C, device=dev)
+    add("k_im2row", graph_ms(lambda: lib.ltn_im2row(p(feat), V, None, p(nbr), V, None, C, p(rows_out), _lib.stream())),
+        V * (12 + 40 * C), "V=%d C=%d" % (V, C))
+    C = 192
+    feat = torch.randn(V, C, device=dev)
+    rows_out = torch.empty(V, 9 * C, device=dev)
+    add("k_im2row", graph_ms(lambda: lib.ltn_im2row(p(feat), V, None, p(nbr), V, None, C, p(rows_out), _lib.stream())),
+        V * (12 + 40 * C), "V=%d C=%d" % (V, C))
+    Cs = 32
+    vals = torch.randn(V, Cs, device=dev)
+    sl = torch.empty(N, Cs, device=dev)
+    add("k_slice", graph_ms(lambda: lib.ltn_slice(p(vals), V, Cs, p(idx), p(w), N, p(sl), _lib.stream())),
+        4 * N * 8 + V * 4 * Cs + N * 4 * Cs, "N=%d V=%d C=%d" % (N, V, Cs))
+    Cin = 1
+    acc = torch.zeros(V, Cin + 1, device=dev)
+    add("k_splat", graph_ms(lambda: lib.ltn_splat(p(val), N, Cin, p(idx), p(w), p(acc), V, _lib.stream())),
+        N * (4 * Cin) + 4 * N * 8 + V * 4 * (Cin + 1), "N=%d V=%d C_in=%d (atomics on ~%d rows per vertex)" % (N, V, Cin, 4 * N // max(V, 1)))
+    ht = ls.hash_table
+
+    def dist():
+        lib.ltn_hash_clear(p(ht.slot_keys), p(ht.slot_ids), p(ht.slot_first), ht.nslots, p(ht.counters), _lib.stream())
+        sx, sy, sz = ls.scale()
+        lib.ltn_distribute(p(pos), p(val), N, None, 1, sx, sy, sz, p(ht.slot_keys), p(ht.slot_ids), p(ht.slot_first), ht.nslots,
+                           p(ht.counters), p(ht.keys_tensor), ls.capacity, p(ls._row_slot), p(ls._block_sums), p(ls._vert_acc),
+                           p(rows), p(idx), p(w), 1, _lib.stream())
+    add("ltn_distribute (hash build + rows + local mean, 6 kernels incl. table clear)", graph_ms(dist), 128 * N, "N=%d -> V=%d" % (N, V))
+    return out
+
+
 def run_train(args, rank, world, dev, devw, windows_np, lib, seeded_state):
     """BASELINE config 4: the same 4-frame gru-gru-aflow-gru window as a TRAINING step (BPTT through the 4
     frames, 0.5 Lovasz + 0.5 NLL, AdamW amsgrad), data-parallel over the ranks with one flattened
@@ -435,6 +511,11 @@ def main():
             dist.destroy_process_group()
         return
 
+    hbm = None
+    try:
+        hbm = hbm_kernels(dev, windows_np[0], pk)
+    except Exception as e:
+        hbm = [{"failed": repr(e)}]
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
@@ -455,7 +536,7 @@ def main():
                                      "static capacities %s, capacities respected: %s" % (lanes, runner.caps, capacity_ok))
                        if graph_mode else "eager op-by-op launches"},
             "e2e": {"value": total_scans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "hbm_kernels": hbm, "cpu_baseline": cpu}
     if args.breakdown:
         line["breakdown_ms_per_step"] = {k: v["ms_total"] / min(args.steps, 4) for k, v in
                                          sorted(summ.items(), key=lambda kv: -kv[1]["ms_total"])}

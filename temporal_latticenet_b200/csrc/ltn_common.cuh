@@ -132,3 +132,30 @@ __device__ __forceinline__ void ltn_simplex(float px, float py, float pz, float 
         bary[r] = b[r];
     }
 }
+
+// Warp-aggregated accumulation: lanes that hold the same key (vertex id) first add their K floats together
+// inside the warp, then ONE lane per distinct key issues the global atomics.  Neighbouring LiDAR points land
+// on the same lattice vertices (40-400 rows per vertex), so this removes most of the same-address contention
+// a per-row atomicAdd has.  Returns true on the leader lane of each group, with the group's sums in v[] and
+// the group size in count.  All 32 lanes must call it (key < 0 = this lane has nothing to add).
+template <int K>
+__device__ __forceinline__ bool ltn_warp_group_sum(int key, float (&v)[K], int& count) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned peers = __match_any_sync(0xffffffffu, key < 0 ? -1 - (int)lane : key);
+    const bool leader = (int)lane == __ffs(peers) - 1;
+    unsigned rest = peers & ~(1u << lane);   // the other lanes of my group, visited one per round
+    count = __popc(peers);
+    float mine[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) mine[k] = v[k];   // peers read the ORIGINAL values
+    while (__any_sync(0xffffffffu, rest != 0u)) {
+        const int src = rest ? __ffs(rest) - 1 : (int)lane;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float o = __shfl_sync(0xffffffffu, mine[k], src);
+            if (rest) v[k] += o;
+        }
+        rest &= rest - 1u;
+    }
+    return leader && key >= 0;
+}

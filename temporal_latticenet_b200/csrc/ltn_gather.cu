@@ -53,21 +53,40 @@ k_row2im(const float* __restrict__ grad_rows, int Vrows, const int* __restrict__
     }
 }
 
-// splat: out[idx, 0:C] += w * val[p] ; out[idx, C] += w.   One warp per point, lanes over channels.
+// splat: out[idx, 0:C] += w * val[p] ; out[idx, C] += w.   One thread per point; the four simplex rows of the
+// 32 points of a warp are aggregated per vertex inside the warp (scan neighbours share vertices), so one lane
+// per distinct vertex issues the atomics instead of every row hammering the same address.
 __global__ void __launch_bounds__(kThreads)
 k_splat(const float* __restrict__ val, int N, int C, const int* __restrict__ idx, const float* __restrict__ w,
         float* out, int V) {
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= N) return;
-    int4 i4 = __ldg(reinterpret_cast<const int4*>(idx) + warp);
-    float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + warp);
-    int ids[4] = {i4.x, i4.y, i4.z, i4.w};
-    float ws[4] = {w4.x, w4.y, w4.z, w4.w};
-    for (int c = lane; c <= C; c += 32) {
-        float x = (c < C) ? __ldg(val + (size_t)warp * C + c) : 1.0f;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < N;
+    int ids[4] = {-1, -1, -1, -1};
+    float ws[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+        int4 i4 = __ldg(reinterpret_cast<const int4*>(idx) + p);
+        float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + p);
+        ids[0] = i4.x; ids[1] = i4.y; ids[2] = i4.z; ids[3] = i4.w;
+        ws[0] = w4.x; ws[1] = w4.y; ws[2] = w4.z; ws[3] = w4.w;
+    }
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-            if (ids[r] >= 0 && ids[r] < V) atomicAdd(out + (size_t)ids[r] * (C + 1) + c, ws[r] * x);
+    for (int r = 0; r < 4; ++r) {
+        const int id = (valid && ids[r] >= 0 && ids[r] < V) ? ids[r] : -1;
+        int cnt;
+        {   // homogeneous coordinate
+            float s[1] = {ws[r]};
+            if (ltn_warp_group_sum<1>(id, s, cnt)) atomicAdd(out + (size_t)id * (C + 1) + C, s[0]);
+        }
+        for (int c = 0; c < C; c += 4) {   // values, four channels per aggregation round
+            float s[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[q] = (valid && c + q < C) ? ws[r] * __ldg(val + (size_t)p * C + c + q) : 0.f;
+            if (ltn_warp_group_sum<4>(id, s, cnt)) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (c + q < C) atomicAdd(out + (size_t)id * (C + 1) + c + q, s[q]);
+            }
+        }
     }
 }
 
@@ -273,7 +292,7 @@ int ltn_row2im(const float* grad_rows, int Vrows, const int* nbrT, int Vu, int C
 // out [V, C+1] must be zeroed by the caller
 int ltn_splat(const float* val, int N, int C, const int* idx, const float* w, float* out, int V, void* stream) {
     if (N <= 0) return 0;
-    k_splat<<<ltn_blocks((long long)N * 32, kThreads), kThreads, 0, (cudaStream_t)stream>>>(val, N, C, idx, w, out, V);
+    k_splat<<<ltn_blocks(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(val, N, C, idx, w, out, V);
     LTN_CHECK_LAUNCH();
     return 0;
 }

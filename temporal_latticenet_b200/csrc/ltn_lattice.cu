@@ -159,7 +159,9 @@ k_number_assign(const int* __restrict__ row_slot, int R, const int* __restrict__
     }
 }
 
-// distribute, second half: slot -> id, rows [4N, 3+vd+1], per-vertex position sums (double) + count
+// distribute, second half: slot -> id, rows [4N, 3+vd+1], per-vertex position sums (double) + count.
+// The sums are warp-aggregated: the 32 points of a warp are scan neighbours and mostly share their simplex
+// vertices, so lanes with the same vertex id add up inside the warp and one lane issues the double atomics.
 __global__ void __launch_bounds__(kThreads)
 k_distribute_rows(const float* __restrict__ pos, const float* __restrict__ val, int N, const int* __restrict__ n_dev, int vd,
                   const int* __restrict__ row_slot, const float* __restrict__ row_w,
@@ -167,29 +169,40 @@ k_distribute_rows(const float* __restrict__ pos, const float* __restrict__ val, 
                   double* vert_acc) {
     if (n_dev) N = min(N, *n_dev);
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
+    const bool valid = p < N;   // no early return: the warp-wide aggregation below needs every lane
     const int width = LTN_D + vd + 1;
-    float px = pos[(size_t)p * 3], py = pos[(size_t)p * 3 + 1], pz = pos[(size_t)p * 3 + 2];
-    int4 s4 = *reinterpret_cast<const int4*>(row_slot + (size_t)p * LTN_D1);
-    float4 w4 = *reinterpret_cast<const float4*>(row_w + (size_t)p * LTN_D1);
-    int s[4] = {s4.x, s4.y, s4.z, s4.w};
-    float w[4] = {w4.x, w4.y, w4.z, w4.w};
+    float px = 0.f, py = 0.f, pz = 0.f;
+    int s[4] = {-1, -1, -1, -1};
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+        px = pos[(size_t)p * 3]; py = pos[(size_t)p * 3 + 1]; pz = pos[(size_t)p * 3 + 2];
+        int4 s4 = *reinterpret_cast<const int4*>(row_slot + (size_t)p * LTN_D1);
+        float4 w4 = *reinterpret_cast<const float4*>(row_w + (size_t)p * LTN_D1);
+        s[0] = s4.x; s[1] = s4.y; s[2] = s4.z; s[3] = s4.w;
+        w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+    }
     int ids[4];
 #pragma unroll
     for (int r = 0; r < LTN_D1; ++r) {
         int id = (s[r] >= 0) ? __ldg(slot_ids + s[r]) : -1;
         ids[r] = id;
-        float* o = rows + ((size_t)p * LTN_D1 + r) * width;
-        o[0] = px; o[1] = py; o[2] = pz;
-        for (int i = 0; i < vd; ++i) o[LTN_D + i] = val[(size_t)p * vd + i];
-        o[LTN_D + vd] = w[r];
-        int a = id < 0 ? 0 : id;  // ids < 0 fold onto vertex 0 (lattice_modules.py:479-480)
-        atomicAdd(vert_acc + (size_t)a * 4 + 0, (double)px);
-        atomicAdd(vert_acc + (size_t)a * 4 + 1, (double)py);
-        atomicAdd(vert_acc + (size_t)a * 4 + 2, (double)pz);
-        atomicAdd(vert_acc + (size_t)a * 4 + 3, 1.0);
+        if (valid) {
+            float* o = rows + ((size_t)p * LTN_D1 + r) * width;
+            o[0] = px; o[1] = py; o[2] = pz;
+            for (int i = 0; i < vd; ++i) o[LTN_D + i] = val[(size_t)p * vd + i];
+            o[LTN_D + vd] = w[r];
+        }
+        const int a = valid ? (id < 0 ? 0 : id) : -1;  // ids < 0 fold onto vertex 0 (lattice_modules.py:479-480)
+        float sum[3] = {px, py, pz};
+        int cnt;
+        if (ltn_warp_group_sum<3>(a, sum, cnt)) {
+            atomicAdd(vert_acc + (size_t)a * 4 + 0, (double)sum[0]);
+            atomicAdd(vert_acc + (size_t)a * 4 + 1, (double)sum[1]);
+            atomicAdd(vert_acc + (size_t)a * 4 + 2, (double)sum[2]);
+            atomicAdd(vert_acc + (size_t)a * 4 + 3, (double)cnt);
+        }
     }
-    *reinterpret_cast<int4*>(idx + (size_t)p * LTN_D1) = make_int4(ids[0], ids[1], ids[2], ids[3]);
+    if (valid) *reinterpret_cast<int4*>(idx + (size_t)p * LTN_D1) = make_int4(ids[0], ids[1], ids[2], ids[3]);
 }
 
 __global__ void __launch_bounds__(kThreads)
