@@ -1,5 +1,7 @@
+"""Micro-benchmark of the fused tensor-core convolution against im2row + cuBLAS fp32 on the shapes of the model
+(20 launches inside a CUDA graph, CUDA events around the replay)."""
 import os, sys, time, torch
-sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from temporal_latticenet_b200 import ops, funcs, synthetic
 from temporal_latticenet_b200.lattice import Lattice
 dev = torch.device("cuda:0")
@@ -22,7 +24,7 @@ def graph_time(fn, n=20):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-print("V0", V, "V1", V1, "dbg", os.environ.get("LTN_CONV_DBG"))
+print("V0", V, "V1", V1)
 cases = [("conv V0 64->64", V, V, nbr, 64, 64), ("conv V0 128->64", V, V, nbr, 128, 64), ("conv V0 192->192", V, V, nbr, 192, 192),
          ("conv V1 128->128", V1, V1, nbr1, 128, 128), ("finefy V1->V0 256->128", V, V1, nbr_fin, 256, 128),
          ("1x1 V0 192->192", V, V, None, 192, 192), ("gru gates V0 192->576", V, V, None, 192, 576)]

@@ -1,5 +1,7 @@
+"""One representative launch of the dominant kernel for `ncu --set full` (profiles/README.md): the 192->192 lattice
+convolution on the V0 lattice of one synthetic scan."""
 import os, sys, torch
-sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from temporal_latticenet_b200 import ops, synthetic
 from temporal_latticenet_b200.lattice import Lattice
 dev = torch.device("cuda:0")

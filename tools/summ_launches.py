@@ -1,3 +1,4 @@
+"""Aggregates an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel: python tools/summ_launches.py <csv> [top]"""
 import csv, collections, sys
 path=sys.argv[1]
 lines=[l for l in open(path) if not l.startswith('==')]
