@@ -143,6 +143,9 @@ class GraphWindowRunner(WindowRunner):
     def infer_window_device(self, frames_dev):
         if not self.supported or self.caps is None or self._force_eager:
             return super().infer_window_device(frames_dev)
+        if any(p.shape[0] > self.caps["n"] for p, _ in frames_dev):   # more points than the static buffers hold
+            self.fallbacks += 1
+            return WindowRunner.infer_window_device(self, frames_dev)
         T = len(frames_dev)
         kinds = [(t == 0, t == T - 1) for t in range(T)]
         if any(k not in self.graphs for k in kinds):
@@ -248,11 +251,12 @@ class MultiWindowRunner:
         if not hasattr(self, "_host_out"):
             self._host_out = {}
         wins, ticket = [], {"host": windows_host, "labels": [], "counts": [], "events": []}
+        oversize = [any(p.shape[0] > self.lanes[i].caps["n"] for p, _ in w) for i, w in enumerate(windows_host)]
         for i, w in enumerate(windows_host):
             self.streams[i].wait_stream(cur)
             with torch.cuda.stream(self.streams[i]):
-                wins.append([(p.to(dev, non_blocking=True), v.to(dev, non_blocking=True)) for p, v in w])
-        T = max(len(w) for w in wins)
+                wins.append([] if oversize[i] else [(p.to(dev, non_blocking=True), v.to(dev, non_blocking=True)) for p, v in w])
+        T = max(len(w) for w in windows_host)
         outs = [None] * len(wins)
         for t in range(T):
             for i, w in enumerate(wins):
@@ -260,6 +264,11 @@ class MultiWindowRunner:
                     with torch.cuda.stream(self.streams[i]):
                         outs[i] = self.lanes[i]._run_frame((t == 0, t == len(w) - 1), w[t][0], w[t][1])
         for i, w in enumerate(wins):
+            if oversize[i]:   # collect() runs it on the eager path
+                ticket["labels"].append(None)
+                ticket["counts"].append(None)
+                ticket["events"].append(None)
+                continue
             lane, n = self.lanes[i], w[-1][0].shape[0]
             with torch.cuda.stream(self.streams[i]):
                 lab = outs[i][:n].argmax(1)
@@ -287,9 +296,10 @@ class MultiWindowRunner:
         the eager path."""
         out = []
         for i, (lab, counts, ev) in enumerate(zip(ticket["labels"], ticket["counts"], ticket["events"])):
-            ev.synchronize()
             lane = self.lanes[i]
-            if all(int(c) < cap for c, cap in zip(counts.tolist(), lane.caps["v"])):
+            if ev is not None:
+                ev.synchronize()
+            if ev is not None and all(int(c) < cap for c, cap in zip(counts.tolist(), lane.caps["v"])):
                 out.append(lab)
             else:
                 lane.fallbacks += 1

@@ -155,3 +155,23 @@ def test_unsupported_fusion_falls_back_to_eager(tmp_path):
     g.capture(fd)
     out = g.infer_window_device(fd)
     assert out.shape == (w[-1][0].shape[0], 26) and len(g.graphs) == 0
+
+
+def test_more_points_than_planned_runs_eagerly():
+    from temporal_latticenet_b200.engine import MultiWindowRunner
+    from temporal_latticenet_b200.runner import WindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    dev = torch.device("cuda:0")
+    small, big = _window(21, n=2000), _window(22, n=9000)
+    to_dev = lambda w: [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]  # noqa: E731
+    eager = WindowRunner(CFG, 26, dev).materialise_parameters(to_dev(small), seeded_state)
+    multi = MultiWindowRunner(CFG, 26, dev, lanes=2).prepare(to_dev(small), seeded_state)
+    assert big[0][0].shape[0] > multi.lanes[0].caps["n"]
+    host = [[(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in w] for w in (big, small)]
+    labels = [l.clone() for l in multi.infer_windows(host)]
+    assert multi.lanes[0].fallbacks == 1 and multi.lanes[1].fallbacks == 0
+    for l, w in zip(labels, (big, small)):
+        want = eager.infer_window_device(to_dev(w)).argmax(1).cpu()
+        assert (l == want).float().mean() > 0.999
+    out = multi.lanes[0].infer_window_device(to_dev(big))
+    assert out.shape[0] == big[-1][0].shape[0] and multi.lanes[0].fallbacks == 2
