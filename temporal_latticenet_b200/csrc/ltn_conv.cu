@@ -102,6 +102,27 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, A operand read from tensor memory (lane = row, 8 consecutive 32-bit columns = the K = 8 of one tf32 MMA)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 registers of this thread -> 32 consecutive TMEM columns of its lane (warp w%4 owns lanes 32(w%4)..+31)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+          "r"(r[30]), "r"(r[31])
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -175,7 +196,7 @@ struct ConvParams {
     int cluster;            // CTAs per cluster sharing the weight tiles by TMA multicast (1, 2 or 4)
 };
 
-template <int PASSES>
+template <int PASSES, bool ATMEM>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -209,13 +230,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
     const uint32_t b_bytes = (uint32_t)p.n_tile * 128;
     const uint32_t a_stage = (PASSES == 3 ? 2 : 1) * a_bytes, b_stage = (PASSES == 3 ? 2 : 1) * b_bytes;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* smem_b = smem + (size_t)SA * a_stage;
+    uint8_t* smem_b = smem + (ATMEM ? 0 : (size_t)SA * a_stage);   // ATMEM: the A ring lives in tensor memory
 
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]);
     const uint32_t bar_fullb = smem_u32(&bars[2 * kMaxStages]), bar_emptyb = smem_u32(&bars[3 * kMaxStages]);
     const uint32_t bar_acc = smem_u32(&bars[4 * kMaxStages]);
+    // tensor memory: accumulator columns [0, Nmma); ATMEM: A ring behind it, 64 columns per stage (hi | lo)
+    const uint32_t a_col0 = ((uint32_t)Nmma + 31u) & ~31u;
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)Nmma) tmem_cols <<= 1;
+    while (tmem_cols < (ATMEM ? a_col0 + (uint32_t)SA * 64u : (uint32_t)Nmma)) tmem_cols <<= 1;
 
     if (tid == 0) {
         for (int s = 0; s < SA; ++s) {
@@ -293,7 +316,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
                 rmask = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int sv = __shfl_sync(0xffffffffu, src_lane, sub + 4 * j);
+                    const int sv = __shfl_sync(0xffffffffu, src_lane, ATMEM ? 8 * sub + j : sub + 4 * j);
                     // row 0 stands in for an absent neighbour (loaded unconditionally, discarded at staging time): a
                     // predicated load would be followed by a predicated register move that waits for it on the spot
                     rowidx[j] = (uint32_t)(sv >= 0 ? sv : 0) * c4 + (uint32_t)chunk;
@@ -316,9 +339,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
                 sc = *reinterpret_cast<const float4*>(s_affine + c_c0 + 4 * chunk);
                 sh = *reinterpret_cast<const float4*>(s_affine + 256 + c_c0 + 4 * chunk);
             }
+            float4 tv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int r = wrow0 + sub + 4 * j;
                 float4 t = cur[j];
                 if (affine) {
                     t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y);
@@ -326,13 +349,51 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
                 }
                 if (p.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
                 if (!((cmask >> j) & 1u)) t = make_float4(0.f, 0.f, 0.f, 0.f);   // absent neighbour / row beyond the tile
-                const float4 h = make_float4(tf32_hi(t.x), tf32_hi(t.y), tf32_hi(t.z), tf32_hi(t.w));
-                uint8_t* dst = a_hi0 + r * 128 + ((chunk ^ (r & 7)) << 4);
-                *reinterpret_cast<float4*>(dst) = h;
-                if (PASSES == 3)
-                    *reinterpret_cast<float4*>(dst + a_bytes) = make_float4(t.x - h.x, t.y - h.y, t.z - h.z, t.w - h.w);
+                tv[j] = t;
             }
-            fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+            if (ATMEM) {
+                // The quarter-warp (lanes 8*sub .. 8*sub+7) holds an 8x8 block: register j = row 8*sub+j, lane c = chunk c.
+                // Three butterfly rounds transpose it in registers so that lane i of the warp owns ALL 32 floats of tile
+                // row wrow0 + i -- the layout tcgen05.st wants (thread = TMEM lane) -- without touching shared memory.
+#pragma unroll
+                for (int m = 4; m >= 1; m >>= 1) {
+                    const bool upper = (chunk & m) != 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j & m) continue;
+                        const float4 a = tv[j], b = tv[j | m];
+                        const float4 snd = upper ? a : b;
+                        float4 rcv;
+                        rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, m); rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, m);
+                        rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, m); rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, m);
+                        if (upper) tv[j] = rcv; else tv[j | m] = rcv;
+                    }
+                }
+                float hi[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    hi[4 * j] = tf32_hi(tv[j].x); hi[4 * j + 1] = tf32_hi(tv[j].y); hi[4 * j + 2] = tf32_hi(tv[j].z); hi[4 * j + 3] = tf32_hi(tv[j].w);
+                    lo[4 * j] = tv[j].x - hi[4 * j]; lo[4 * j + 1] = tv[j].y - hi[4 * j + 1];
+                    lo[4 * j + 2] = tv[j].z - hi[4 * j + 2]; lo[4 * j + 3] = tv[j].w - hi[4 * j + 3];
+                }
+                const uint32_t ta = tmem_base + ((uint32_t)wrow0 << 16) + a_col0 + (uint32_t)c_stage * 64u;
+                tmem_st32(ta, hi);
+                if (PASSES == 3) tmem_st32(ta + 32u, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = wrow0 + sub + 4 * j;
+                    const float4 t = tv[j];
+                    const float4 h = make_float4(tf32_hi(t.x), tf32_hi(t.y), tf32_hi(t.z), tf32_hi(t.w));
+                    uint8_t* dst = a_hi0 + r * 128 + ((chunk ^ (r & 7)) << 4);
+                    *reinterpret_cast<float4*>(dst) = h;
+                    if (PASSES == 3)
+                        *reinterpret_cast<float4*>(dst + a_bytes) = make_float4(t.x - h.x, t.y - h.y, t.z - h.z, t.w - h.w);
+                }
+                fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * c_stage);   // one arrival per warp, not 32 serialised ones
             c_c0 += kGroups * kBlockK;
@@ -407,13 +468,22 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
                 const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + a_bytes);
                 const uint32_t bb = smem_u32(smem_b + (size_t)sb * b_stage);
                 const uint64_t b_hi = make_desc(bb), b_lo = make_desc(bb + b_bytes);
+                const uint32_t ta = tmem_base + a_col0 + (uint32_t)sa * 64u;   // ATMEM: this stage's A columns (hi at +0, lo at +32)
 #pragma unroll
                 for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                     const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);  // 32 bytes per K step inside the swizzle row
-                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
-                    if (PASSES == 3) {
-                        umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
-                        umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+                    if (ATMEM) {
+                        umma_tf32_ts(tmem_base, ta + k * kUmmaK, b_hi + adv, idesc, (kb | k) != 0);
+                        if (PASSES == 3) {
+                            umma_tf32_ts(tmem_base, ta + 32u + k * kUmmaK, b_hi + adv, idesc, 1);
+                            umma_tf32_ts(tmem_base, ta + k * kUmmaK, b_lo + adv, idesc, 1);
+                        }
+                    } else {
+                        umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+                        if (PASSES == 3) {
+                            umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
+                            umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+                        }
                     }
                 }
                 umma_commit(bar_empty + 8 * sa);      // both stages reusable once these MMAs have read them
@@ -580,15 +650,35 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     const size_t budget = 208 * 1024;
     // the gather ring gets the depth first (measured: 3 A + 2 B stages beat 2 A + 3 B by 1.4x at N = 192), the
     // TMA ring takes what is left, at least two stages each
-    int sa = (int)((budget - 2 * b_stage) / a_stage);
-    if (sa > kMaxStages) sa = kMaxStages;
-    if (sa < 2) return -3;
-    int sb = (int)((budget - sa * a_stage) / b_stage);
-    if (sb > kMaxStages) sb = kMaxStages;
-    if (sb < 2) return -3;
+    // Measured (tools/bench_conv.py, 192->192 on 13.7k vertices): A staged in shared memory 60.6 us, A staged in tensor
+    // memory 111.7 us (1-pass: 40.8 vs 79.1 us) -- correct, but the register transpose + tcgen05.st/wait::st chain in
+    // the producers costs more than the tensor core's shared-memory reads it removes.  Off unless LTN_CONV_ATMEM=1.
+    static const int want_atmem = []() { const char* e = getenv("LTN_CONV_ATMEM"); return e ? atoi(e) : 0; }();
+    const bool atmem = want_atmem != 0;
+    int sa, sb;
+    size_t smem;
+    if (atmem) {
+        // A operand staged in TENSOR memory by the producers (tcgen05.st): shared memory only holds the weight ring,
+        // and the tensor core's A reads (40 % of its shared-memory wavefronts at N = 192) disappear
+        const int acc_cols = (((n_tile + 15) & ~15) + 31) & ~31;
+        sa = (512 - acc_cols) / 64;
+        if (sa > kMaxStages) sa = kMaxStages;
+        if (sa < 2) return -3;
+        sb = (int)(budget / b_stage);
+        if (sb > kMaxStages) sb = kMaxStages;
+        if (sb < 2) return -3;
+        smem = sb * b_stage + 1024;
+    } else {
+        sa = (int)((budget - 2 * b_stage) / a_stage);
+        if (sa > kMaxStages) sa = kMaxStages;
+        if (sa < 2) return -3;
+        sb = (int)((budget - sa * a_stage) / b_stage);
+        if (sb > kMaxStages) sb = kMaxStages;
+        if (sb < 2) return -3;
+        smem = sa * a_stage + sb * b_stage + 1024;
+    }
     p.stages_a = sa;
     p.stages_b = sb;
-    size_t smem = sa * a_stage + sb * b_stage + 1024;
     // Row tiles that share a weight tile are grouped into thread-block clusters: each CTA fetches 1/CL of the
     // tile and multicasts it, so the L2 -> SM weight traffic (3x the gather traffic at N = 192) drops by CL.
     // Measured on B200 (bench_conv3, V = 13.7k): 192->192 72 us unclustered vs 78 us with clusters of 4, 128->128 on
@@ -604,8 +694,9 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     if (rc) return rc;
     rc = make_weight_map(&map_lo, passes == 3 ? wt_lo : wt_hi, F, p.S * C, n_tile / cl);
     if (rc) return rc;
-    cudaError_t e = cudaFuncSetAttribute(passes == 3 ? (const void*)k_conv_tc<3> : (const void*)k_conv_tc<1>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const void* fn = passes == 3 ? (atmem ? (const void*)k_conv_tc<3, true> : (const void*)k_conv_tc<3, false>)
+                                 : (atmem ? (const void*)k_conv_tc<1, true> : (const void*)k_conv_tc<1, false>);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((row_tiles + cl - 1) / cl * cl, ny);
@@ -619,7 +710,8 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = passes == 3 ? cudaLaunchKernelEx(&cfg, k_conv_tc<3>, map_hi, map_lo, p) : cudaLaunchKernelEx(&cfg, k_conv_tc<1>, map_hi, map_lo, p);
+    void* args[3] = {(void*)&map_hi, (void*)&map_lo, (void*)&p};
+    e = cudaLaunchKernelExC(&cfg, fn, args);
     if (e != cudaSuccess) return (int)e;
     LTN_CHECK_LAUNCH();
     return 0;

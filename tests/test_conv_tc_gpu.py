@@ -139,3 +139,34 @@ def test_groupnorm_folded_from_sums_and_output_statistics(dev, lattice, C, F):
     # gn_stats kernel itself
     s64 = x.double().reshape(V, G, C // G)
     np.testing.assert_allclose(sums.cpu().numpy(), np.stack([s64.sum((0, 2)).numpy(), (s64 ** 2).sum((0, 2)).numpy()], 1), rtol=1e-6, atol=1e-6)
+
+
+def test_alternative_operand_paths_agree(dev, lattice):
+    """The two experimental operand paths (A staged in tensor memory for a TS-mode MMA; weight tiles multicast across
+    a thread-block cluster) are kept behind environment switches because they measured slower; they must still be
+    correct.  Each switch is read once per process, so they run in subprocesses."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from temporal_latticenet_b200 import ops\n"
+        "from temporal_latticenet_b200.lattice import Lattice\n"
+        "from tests.helpers import small_window\n"
+        "dev = torch.device('cuda:0')\n"
+        "p, v = small_window(seed=3, frames=1, radius=14.0, max_points=25000)[0]\n"
+        "ls = Lattice(60000, 0.6, device=dev)\n"
+        "ls.distribute(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev), True)\n"
+        "V = ls.nr_lattice_vertices(); g = torch.Generator().manual_seed(5)\n"
+        "for C, F in ((64, 64), (192, 192), (128, 48)):\n"
+        "    x = torch.randn(V, C, generator=g); W = torch.randn(9 * C, F, generator=g) / (9 * C) ** 0.5\n"
+        "    out = ops.conv_tc(x.to(dev), ls.neighbours(), ops.k_major(W.to(dev))).cpu().double()\n"
+        "    nbr = ls.neighbours().cpu().long(); pad = torch.cat([x, torch.zeros(1, C)], 0).double()\n"
+        "    rows = pad[torch.where(nbr < 0, torch.full_like(nbr, V), nbr).reshape(-1)].reshape(V, 9 * C)\n"
+        "    want = rows @ W.double(); bound = rows.abs() @ W.double().abs() + 1e-30\n"
+        "    assert float(((out - want).abs() / bound).max()) < 2e-5\n"
+        "print('ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env in ({"LTN_CONV_ATMEM": "1"}, {"LTN_CONV_CLUSTER": "4"}, {"LTN_CONV_CLUSTER": "2"}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
