@@ -175,3 +175,39 @@ def test_more_points_than_planned_runs_eagerly():
         assert (l == want).float().mean() > 0.999
     out = multi.lanes[0].infer_window_device(to_dev(big))
     assert out.shape[0] == big[-1][0].shape[0] and multi.lanes[0].fallbacks == 2
+
+
+def test_graph_runner_single_accumulated_frame(tmp_path):
+    """BASELINE config 5 shape: rnn_modules aflow x4 with accumulate_clouds -- the window's scans are concatenated into
+    ONE frame (kitti_dataloader.py:198-201), so every fusion module only takes its t == 0 branch and the engine has a
+    single frame kind (first AND last)."""
+    import hjson
+    import os
+    from temporal_latticenet_b200.engine import GraphWindowRunner
+    from temporal_latticenet_b200.runner import WindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    with open(CFG) as f:
+        cfg = hjson.loads(f.read())
+    cfg["model"]["rnn_modules"] = ["aflow", "aflow", "aflow", "aflow"]
+    cfg["loader_semantic_kitti"]["accumulate_clouds"] = True
+    path = os.path.join(str(tmp_path), "cfg_accum.cfg")
+    with open(path, "w") as f:
+        f.write(hjson.dumps(cfg))
+    dev = torch.device("cuda:0")
+
+    def accumulated(seed):
+        w = _window(seed, frames=4, n=3000)
+        return [(np.concatenate([p for p, _ in w], 0), np.concatenate([v for _, v in w], 0))]
+    wins = [accumulated(31), accumulated(32)]
+    to_dev = lambda w: [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]  # noqa: E731
+    eager = WindowRunner(path, 26, dev).materialise_parameters(to_dev(wins[0]), seeded_state)
+    graph = GraphWindowRunner(path, 26, dev).materialise_parameters(to_dev(wins[0]), seeded_state)
+    graph.plan(to_dev(wins[0]))
+    graph.capture(to_dev(wins[0]))
+    assert list(graph.graphs) == [(True, True)]
+    for w in wins + wins:
+        fd = to_dev(w)
+        want = eager.infer_window_device(fd).cpu().numpy()
+        got = graph.infer_window_device(fd).cpu().numpy()
+        assert graph.counts_ok() and got.shape == want.shape == (w[0][0].shape[0], 26)
+        assert float(np.abs(got - want).max()) / float(np.abs(want).max()) < 1e-4
