@@ -448,27 +448,32 @@ def main():
         for name, _ in _lib.declared_functions():
             if name not in ("ltn_version", "ltn_launch_count"):
                 names[name] = None
-    names["ltn_conv_tc"] = lambda *a: 2.0 * a[4] * a[6] * (a[7] if a[3] is not None and getattr(a[3], "value", 1) else 1) * a[10]
+    # fused convolution entry points: (x, Vx, vx_dev, nbr, Vq, vq_dev, C, S, wt_hi, wt_lo, [w_log2, a_log2,] F, ...)
+    conv_entries = {"ltn_conv_tc": 10, "ltn_conv_tc_f16": 12}
+
+    def conv_slots(a):
+        return a[7] if a[3] is not None and getattr(a[3], "value", 1) else 1
+
+    def conv_flops(f_idx):
+        return lambda *a: 2.0 * a[4] * a[6] * conv_slots(a) * a[f_idx]
+    for cname, f_idx in conv_entries.items():
+        names[cname] = conv_flops(f_idx)
     if graph_mode:
         runner._force_eager = True   # the probe brackets individual C-ABI calls, so this pass launches op by op
-    if args.breakdown:
-        shapes = {}
-
-        def conv_key(*a):  # (x, Vx, vx_dev, nbr, Vq, vq_dev, C, S, wt_hi, wt_lo, F, ...)
-            S = a[7] if a[3] is not None and getattr(a[3], "value", 1) else 1
-            return "conv_tc Vq~%dk C%d S%d F%d" % (round(a[4] / 1000.0), a[6], S, a[10])
-        orig_conv = lib.ltn_conv_tc
-
-        def conv_wrapped(*a):
-            return probe.wrap(conv_key(*a), orig_conv, lambda *b: 2.0 * b[4] * b[6] * (b[7] if b[3] is not None and getattr(b[3], "value", 1) else 1) * b[10])(*a)
-        names.pop("ltn_conv_tc", None)
     originals = {}
+    if args.breakdown:   # one probe entry per convolution shape
+        def per_shape(cname, f_idx, orig):
+            def wrapped(*a):
+                key = "conv_tc%s Vq~%dk C%d S%d F%d" % ("_f16" if cname.endswith("f16") else "", round(a[4] / 1000.0), a[6], conv_slots(a), a[f_idx])
+                return probe.wrap(key, orig, conv_flops(f_idx))(*a)
+            return wrapped
+        for cname, f_idx in conv_entries.items():
+            names.pop(cname, None)
+            originals[cname] = getattr(lib, cname)
+            setattr(lib, cname, per_shape(cname, f_idx, originals[cname]))
     for name, wf in names.items():
         originals[name] = getattr(lib, name)
         setattr(lib, name, probe.wrap(name, originals[name], wf))
-    if args.breakdown:
-        originals["ltn_conv_tc"] = orig_conv
-        lib.ltn_conv_tc = conv_wrapped
     import temporal_latticenet_b200.ops as ops
     mm_orig, lin_orig = ops.matmul, ops.linear
     ops.matmul = probe.wrap("torch.mm(cuBLAS sgemm)", mm_orig, lambda a, b: 2.0 * a.shape[0] * a.shape[1] * b.shape[1])
@@ -493,17 +498,20 @@ def main():
         traffic = tj["traffic_bytes"]
         traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (%s) from ncu --set full: %.2f MB against %.2f MB "
                         "algorithmic for that launch" % (tj["launch"], tj["traffic_bytes"] / 1e6, tj["algorithmic_bytes"] / 1e6))
-    conv = [v for k, v in summ.items() if k.startswith("conv_tc") or k == "ltn_conv_tc"]
+    conv = [v for k, v in summ.items() if k.startswith("conv_tc") or k.startswith("ltn_conv_tc")]
+    conv16 = [v for k, v in summ.items() if k.startswith("conv_tc_f16") or k == "ltn_conv_tc_f16"]
     roofline = None
     if conv and sum(v["ms_total"] for v in conv) > 0:
         ms_c, fl_c, n_c = sum(v["ms_total"] for v in conv), sum(v["work"] for v in conv), sum(v["launches"] for v in conv)
         achieved = fl_c / (ms_c * 1e-3) / 1e12
-        roofline = {"kernel": "k_conv_tc<3> (fused gather + tcgen05 tf32 GEMM, fp32-parity 3-pass split)", "bound": "tensor",
+        fl16 = sum(v["work"] for v in conv16)
+        roofline = {"kernel": "k_conv_tc (fused gather + GroupNorm/ReLU + tcgen05 GEMM, fp32-parity 3-pass hi/lo split; fp16 operands "
+                              "where C %% 64 == 0 [%.0f %% of the flop], tf32 operands otherwise)" % (100.0 * fl16 / max(fl_c, 1.0)), "bound": "tensor",
                     "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"] + " (bf16 sustained)",
                     "note": "achieved = algorithmic 2*V*S*C*F flop / CUDA-event time over every launch of the kernel in a repeat "
-                            "of the timed steps (op-by-op launches); the parity mode issues 3 tf32 MMAs per product and tf32 "
-                            "runs at half the bf16 rate, so 1/6 of the bf16 peak is this kernel's ceiling",
+                            "of the timed steps (op-by-op launches); the parity mode issues 3 MMAs per product (fp16 operands at the "
+                            "bf16 rate, tf32 at half of it), so 1/3 (fp16) resp. 1/6 (tf32) of the bf16 peak is this kernel's ceiling",
                     "tensor_flops_issued_tflops": 3 * achieved, "launches_per_step": n_c / min(args.steps, 4),
                     "avg_launch_us": 1e3 * ms_c / n_c, "share_of_step_ms": ms_c / min(args.steps, 4)}
 

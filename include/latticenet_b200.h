@@ -130,6 +130,23 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
 /* weight -> K-major [F,K] tf32 split: hi = round-to-tf32(w), lo = w - hi.  transposed_in = 0: w is the
  * reference's conv layout [K,F] (lattice_modules.py:291); 1: w is [F,K] (nn.Linear) */
 int ltn_split_tf32(const float* w, int K, int F, int transposed_in, float* wt_hi, float* wt_lo, void* stream);
+/* The same operation with fp16 hi/lo operands: the split keeps the same 11 + 11 significant bits per operand as
+ * the tf32 one in half the bytes (half the shared-memory traffic, twice the tensor rate).  fp16's exponent range
+ * is covered by exact power-of-two scaling: the weight copies hold w * 2^w_log2 (ltn_split_f16, w_log2 chosen by
+ * the caller from max|w|), activations are staged as act(x) * 2^a_log2, the epilogue multiplies by
+ * 2^-(w_log2 + a_log2).  *flag (int32, nullable) is OR-ed with 1 when a staged magnitude reaches 65504: the
+ * result is then unusable and the caller redoes the work with ltn_conv_tc.  C % 64 == 0; wt_hi / wt_lo are
+ * [F, S*C] fp16. */
+int ltn_conv_tc_f16(const float* x, int Vx, const int* vx_dev, const int* nbr, int Vq, const int* vq_dev, int C, int S,
+                    const void* wt_hi, const void* wt_lo, int w_log2, int a_log2, int F, const float* a_scale,
+                    const float* a_shift, const double* gn_sums, const float* gn_gamma, const float* gn_beta, float gn_eps,
+                    int gn_groups, int relu, const float* bias, const float* res, float* out, int ldo, double* out_sums,
+                    int out_groups, int* flag, void* stream);
+int ltn_split_f16(const float* w, int K, int F, int transposed_in, int w_log2, void* wt_hi, void* wt_lo, void* stream);
+/* phase tracing of the following ltn_conv_tc* launches (NULL switches it off): buf receives 8 globaltimer stamps (ns)
+ * per CTA in launch-grid order -- entry, set-up done, first operands staged, producers done, accumulator complete,
+ * epilogue stores issued, teardown, (unused) */
+int ltn_conv_trace(unsigned long long* buf);
 
 /* PointNetSeqModule front end (lattice_modules.py:448-530) fused: MLP 4->16->32->64 per distributed row,
  * segmented max per vertex (+arg-max), barycentric weight of the winning row (quirk Q3), concatenation

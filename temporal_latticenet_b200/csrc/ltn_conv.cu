@@ -32,6 +32,7 @@
 //    memory (vq_dev / vx_dev), so the launch needs no host synchronisation.
 #include "ltn_common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 
 namespace {
@@ -101,6 +102,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (F16) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
+    }
 }
 // same, A operand read from tensor memory (lane = row, 8 consecutive 32-bit columns = the K = 8 of one tf32 MMA)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -194,17 +208,41 @@ struct ConvParams {
     int n_tile;            // output channels per CTA (<= 256, multiple of 16)
     int stages_a, stages_b; // depth of the A (gathered) and B (TMA) shared-memory rings
     int cluster;            // CTAs per cluster sharing the weight tiles by TMA multicast (1, 2 or 4)
+    float a_mul, out_mul;   // fp16 operands: power-of-two scale applied to A, and its (and the weights') inverse for the output
+    int* flag;              // fp16 operands: set to 1 when a staged magnitude leaves the half range (nullable)
+    unsigned long long* trace;  // nullable: [CTA][8] globaltimer stamps of the phases (ltn_conv_trace)
 };
 
-template <int PASSES, bool ATMEM>
+__device__ __forceinline__ void trace_stamp(const ConvParams& p, int phase) {
+    if (p.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + phase] = t;
+    }
+}
+
+unsigned long long* g_trace = nullptr;
+
+// OPERANDS: F16 = false -> tf32 operands (4 bytes / element, 32 K-elements per 128-byte swizzle row, MMA K = 8)
+//           F16 = true  -> fp16 operands (2 bytes / element, 64 K-elements per row, MMA K = 16): the hi/lo split
+//                          carries the same 11 + 11 significant bits as the tf32 split in HALF the shared-memory
+//                          bytes and at twice the tensor rate.  fp16's narrow exponent is handled by exact
+//                          power-of-two scaling (a_mul on the activations, a per-tensor factor baked into the
+//                          weight copies, out_mul undoes both in the epilogue) and an overflow flag the caller
+//                          checks (ops.py falls back to the tf32 operands when it is raised).
+template <int PASSES, bool ATMEM, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, ConvParams p) {
+    static_assert(!(ATMEM && F16), "the tensor-memory A path exists for tf32 operands only");
+    constexpr int KB = F16 ? 64 : kBlockK;          // K elements per k-block
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 1];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_affine[2 * 256];
     __shared__ float s_colsum[2 * 256];
+    __shared__ int s_nbr[LTN_FEXT * kBlockM];   // [slot][tile row]: source vertex of every tap of the tile, -1 = absent
 
+    if (threadIdx.x == 0) trace_stamp(p, 0);   // entry
     const int Vq = p.vq_dev ? min(p.Vq, __ldg(p.vq_dev)) : p.Vq;
     const int Vx = p.vx_dev ? min(p.Vx, __ldg(p.vx_dev)) : p.Vx;
     const int row0 = blockIdx.x * kBlockM;
@@ -220,8 +258,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = p.S * p.C;
-    const int num_kb = K / kBlockK;
-    const int kb_per_slot = p.C / kBlockK;
+    const int num_kb = K / KB;
+    const int kb_per_slot = p.C / KB;
     const int SA = p.stages_a, SB = p.stages_b;
 
     // shared-memory carve-up: two INDEPENDENT rings, A stages [A_hi | A_lo] and B stages [B_hi | B_lo], every
@@ -257,6 +295,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     const bool affine = (p.a_scale != nullptr) || (p.gn_sums != nullptr);
+    const float a_mul = F16 ? p.a_mul : 1.0f;   // exact power of two, folded into the affine
     if (p.gn_sums) {
         // GroupNorm folded to scale = rstd*gamma, shift = beta - mean*scale (statistics over all Vx rows)
         for (int c = tid; c < p.C; c += kThreads) {
@@ -267,159 +306,236 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
             if (var < 0.0) var = 0.0;
             const float rstd = (float)(1.0 / sqrt(var + (double)p.gn_eps));
             const float a = rstd * (p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.0f);
-            s_affine[c] = a;
-            s_affine[256 + c] = (p.gn_beta ? __ldg(p.gn_beta + c) : 0.0f) - (float)mean * a;
+            const float sh = (p.gn_beta ? __ldg(p.gn_beta + c) : 0.0f) - (float)mean * a;
+            s_affine[c] = a * a_mul;
+            s_affine[256 + c] = sh * a_mul;
         }
     } else if (p.a_scale) {
         for (int c = tid; c < p.C; c += kThreads) {
-            s_affine[c] = __ldg(p.a_scale + c);
-            s_affine[256 + c] = __ldg(p.a_shift + c);
+            s_affine[c] = __ldg(p.a_scale + c) * a_mul;
+            s_affine[256 + c] = __ldg(p.a_shift + c) * a_mul;
         }
     }
     if (p.out_sums)
         for (int c = tid; c < 2 * 256; c += kThreads) s_colsum[c] = 0.f;
+    // The tile's slice of the neighbour table ([128, S] ints, contiguous in global memory) is fetched ONCE, coalesced,
+    // and kept slot-major in shared memory: a slot change in the gather loop then costs a shared-memory read instead
+    // of a dependent global load + warp shuffles in front of every row fetch.
+    for (int i = tid; i < kBlockM * p.S; i += kThreads) {
+        const int r = i / p.S, sl = i - r * p.S;
+        const int v = row0 + r;
+        int sv = -1;
+        if (v < Vq) {
+            sv = p.nbr ? __ldg(p.nbr + (size_t)row0 * p.S + i) : v;
+            if (sv >= Vx) sv = -1;
+        }
+        s_nbr[sl * kBlockM + r] = sv;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (CL > 1) cluster_sync_all();   // sibling barriers are initialised before any remote arrive / multicast lands
     const uint32_t tmem_base = tmem_slot;
+    if (tid == 0) trace_stamp(p, 1);   // set-up done
 
     if (warp < 4 * kGroups) {
         // ===================== producers: gather A rows (two warpgroups, alternate k-blocks) ==========
         // Quarter-warp per row: 8 lanes fetch the 8 16-byte chunks of one 128-byte row segment, so one
         // warp-wide LDG.128 touches 4 whole cache lines (not 32 partial ones) and the swizzled stores of a
-        // quarter-warp cover one 128-byte shared-memory row conflict-free.  A warp owns 32 tile rows and
-        // walks them 4 at a time (8 loads in flight per thread); the loads of the NEXT k-block are issued
-        // before the current one is converted, so the L2 latency of the gather overlaps the staging work.
+        // quarter-warp cover one shared-memory row conflict-free.  A warp owns 32 tile rows and walks them
+        // 4 at a time; a gather UNIT is 8 float4 per thread (tf32: 8 rows x 32 channels; fp16: 4 rows x 64
+        // channels, two units per k-block); the loads of the NEXT unit are issued before the current one is
+        // converted, so the L2 latency of the gather overlaps the staging work.
         const int group = warp >> 2;
         const int wrow0 = (warp & 3) * 32;         // first tile row of this warp
         const int chunk = lane & 7, sub = lane >> 3;
-        const int my_v = row0 + wrow0 + lane;      // the row whose neighbour id this lane looks up
         // All ring / k-block bookkeeping is incremental: no integer division in the loop.
         const float4* x4 = reinterpret_cast<const float4*>(p.x);
         const uint32_t c4 = (uint32_t)p.C >> 2;
-        float4 buf[2][8];      // two register buffers, used with compile-time indices (loop unrolled by 2)
-        uint32_t bmask[2];     // bit j: row j of the buffer is a present neighbour
+        float4 buf[2][8];      // two register buffers, used with compile-time indices
+        uint32_t bmask[2];     // bit j: tile row j of the warp's walk is a present neighbour
         uint32_t rowidx[8];    // float4 index of (row j's source vertex, this lane's chunk), refreshed per slot
         uint32_t rmask = 0;
-        int i_slot = group / kb_per_slot, i_c0 = (group - i_slot * kb_per_slot) * kBlockK, i_cur = -1;   // issue position
-        int c_c0 = i_c0, c_stage = group % SA;                                                          // consume position
+        float amax = 0.f;      // F16: largest scaled magnitude staged by this thread (range check)
+        int i_slot = group / kb_per_slot, i_c0 = (group - i_slot * kb_per_slot) * KB, i_cur = -1;   // issue position
+        int c_c0 = i_c0, c_stage = group % SA;                                                    // consume position
         uint32_t c_par = ((group / SA) & 1) ^ 1;
-        auto issue = [&](float4* dst, uint32_t& dmask) {
+        // part: which half of the warp's rows (fp16 operands only; compile-time at every call site)
+        auto issue = [&](float4* dst, uint32_t& dmask, const int part) {
             if (i_slot != i_cur) {
                 i_cur = i_slot;
-                int src_lane = -1;
-                if (my_v < Vq) {
-                    src_lane = p.nbr ? __ldg(p.nbr + (size_t)my_v * p.S + i_slot) : my_v;
-                    if (src_lane >= Vx) src_lane = -1;
-                }
+                const int* tap = s_nbr + i_slot * kBlockM + wrow0;
                 rmask = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int sv = __shfl_sync(0xffffffffu, src_lane, ATMEM ? 8 * sub + j : sub + 4 * j);
+                    const int sv = tap[ATMEM ? 8 * sub + j : sub + 4 * j];
                     // row 0 stands in for an absent neighbour (loaded unconditionally, discarded at staging time): a
                     // predicated load would be followed by a predicated register move that waits for it on the spot
                     rowidx[j] = (uint32_t)(sv >= 0 ? sv : 0) * c4 + (uint32_t)chunk;
                     rmask |= (sv >= 0 ? 1u : 0u) << j;
                 }
             }
-            dmask = rmask;
             const uint32_t o = (uint32_t)i_c0 >> 2;
+            if (F16) {
+                dmask = part ? (rmask >> 4) : rmask;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = __ldg(x4 + rowidx[j] + o);
-            i_c0 += kGroups * kBlockK;
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t ri = (part ? rowidx[4 + j] : rowidx[j]) + o;
+                    dst[2 * j] = __ldg(x4 + ri);          // channels c0 + 4*chunk .. (first 128-byte line of the segment)
+                    dst[2 * j + 1] = __ldg(x4 + ri + 8);  // channels c0 + 32 + 4*chunk .. (second line)
+                }
+                if (!part) return;
+            } else {
+                dmask = rmask;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = __ldg(x4 + rowidx[j] + o);
+            }
+            i_c0 += kGroups * KB;
             while (i_c0 >= p.C) { i_c0 -= p.C; ++i_slot; }
         };
-        auto consume = [&](const float4* cur, uint32_t cmask) {
-            if (lane == 0) mbar_wait(bar_empty + 8 * c_stage, c_par);   // one waiter per warp
-            __syncwarp();
+        auto consume = [&](const float4* cur, uint32_t cmask, const int part) {
+            if (!F16 || part == 0) {
+                if (lane == 0) mbar_wait(bar_empty + 8 * c_stage, c_par);   // one waiter per warp
+                __syncwarp();
+            }
             uint8_t* a_hi0 = smem + (size_t)c_stage * a_stage;
-            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (affine) {
-                sc = *reinterpret_cast<const float4*>(s_affine + c_c0 + 4 * chunk);
-                sh = *reinterpret_cast<const float4*>(s_affine + 256 + c_c0 + 4 * chunk);
-            }
-            float4 tv[8];
+            if (F16) {
+                // 4 rows x 2 float4: each float4 becomes 4 fp16 hi + 4 fp16 lo = one 8-byte store each; a quarter-warp
+                // covers channels [0,32) of its row with the even float4 and [32,64) with the odd one.
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 t = cur[j];
-                if (affine) {
-                    t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y);
-                    t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
-                }
-                if (p.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-                if (!((cmask >> j) & 1u)) t = make_float4(0.f, 0.f, 0.f, 0.f);   // absent neighbour / row beyond the tile
-                tv[j] = t;
-            }
-            if (ATMEM) {
-                // The quarter-warp (lanes 8*sub .. 8*sub+7) holds an 8x8 block: register j = row 8*sub+j, lane c = chunk c.
-                // Three butterfly rounds transpose it in registers so that lane i of the warp owns ALL 32 floats of tile
-                // row wrow0 + i -- the layout tcgen05.st wants (thread = TMEM lane) -- without touching shared memory.
+                for (int q = 0; q < 2; ++q) {
+                    float4 sc = make_float4(a_mul, a_mul, a_mul, a_mul), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (affine) {
+                        sc = *reinterpret_cast<const float4*>(s_affine + c_c0 + 32 * q + 4 * chunk);
+                        sh = *reinterpret_cast<const float4*>(s_affine + 256 + c_c0 + 32 * q + 4 * chunk);
+                    }
 #pragma unroll
-                for (int m = 4; m >= 1; m >>= 1) {
-                    const bool upper = (chunk & m) != 0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (j & m) continue;
-                        const float4 a = tv[j], b = tv[j | m];
-                        const float4 snd = upper ? a : b;
-                        float4 rcv;
-                        rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, m); rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, m);
-                        rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, m); rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, m);
-                        if (upper) tv[j] = rcv; else tv[j | m] = rcv;
+                    for (int j = 0; j < 4; ++j) {
+                        float4 t = cur[2 * j + q];
+                        t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y);
+                        t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
+                        if (p.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+                        if (!((cmask >> j) & 1u)) t = make_float4(0.f, 0.f, 0.f, 0.f);   // absent neighbour / row beyond the tile
+                        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+                        const __half2 h01 = __floats2half2_rn(t.x, t.y), h23 = __floats2half2_rn(t.z, t.w);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        const int r = wrow0 + sub + 4 * (4 * part + j);
+                        uint8_t* dst = a_hi0 + r * 128 + (((4 * q + (chunk >> 1)) ^ (r & 7)) << 4) + ((chunk & 1) << 3);
+                        uint2 hv, lv;
+                        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                        *reinterpret_cast<uint2*>(dst) = hv;
+                        if (PASSES == 3) {
+                            const __half2 l01 = __floats2half2_rn(t.x - f01.x, t.y - f01.y), l23 = __floats2half2_rn(t.z - f23.x, t.w - f23.y);
+                            lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                            *reinterpret_cast<uint2*>(dst + a_bytes) = lv;
+                        }
                     }
                 }
-                float hi[32], lo[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    hi[4 * j] = tf32_hi(tv[j].x); hi[4 * j + 1] = tf32_hi(tv[j].y); hi[4 * j + 2] = tf32_hi(tv[j].z); hi[4 * j + 3] = tf32_hi(tv[j].w);
-                    lo[4 * j] = tv[j].x - hi[4 * j]; lo[4 * j + 1] = tv[j].y - hi[4 * j + 1];
-                    lo[4 * j + 2] = tv[j].z - hi[4 * j + 2]; lo[4 * j + 3] = tv[j].w - hi[4 * j + 3];
-                }
-                const uint32_t ta = tmem_base + ((uint32_t)wrow0 << 16) + a_col0 + (uint32_t)c_stage * 64u;
-                tmem_st32(ta, hi);
-                if (PASSES == 3) tmem_st32(ta + 32u, lo);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int r = wrow0 + sub + 4 * j;
-                    const float4 t = tv[j];
-                    const float4 h = make_float4(tf32_hi(t.x), tf32_hi(t.y), tf32_hi(t.z), tf32_hi(t.w));
-                    uint8_t* dst = a_hi0 + r * 128 + ((chunk ^ (r & 7)) << 4);
-                    *reinterpret_cast<float4*>(dst) = h;
-                    if (PASSES == 3)
-                        *reinterpret_cast<float4*>(dst + a_bytes) = make_float4(t.x - h.x, t.y - h.y, t.z - h.z, t.w - h.w);
-                }
+                if (part == 0) return;
                 fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+            } else {
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (affine) {
+                    sc = *reinterpret_cast<const float4*>(s_affine + c_c0 + 4 * chunk);
+                    sh = *reinterpret_cast<const float4*>(s_affine + 256 + c_c0 + 4 * chunk);
+                }
+                float4 tv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 t = cur[j];
+                    if (affine) {
+                        t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y);
+                        t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
+                    }
+                    if (p.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+                    if (!((cmask >> j) & 1u)) t = make_float4(0.f, 0.f, 0.f, 0.f);   // absent neighbour / row beyond the tile
+                    tv[j] = t;
+                }
+                if (ATMEM) {
+                    // The quarter-warp (lanes 8*sub .. 8*sub+7) holds an 8x8 block: register j = row 8*sub+j, lane c = chunk c.
+                    // Three butterfly rounds transpose it in registers so that lane i of the warp owns ALL 32 floats of tile
+                    // row wrow0 + i -- the layout tcgen05.st wants (thread = TMEM lane) -- without touching shared memory.
+#pragma unroll
+                    for (int m = 4; m >= 1; m >>= 1) {
+                        const bool upper = (chunk & m) != 0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (j & m) continue;
+                            const float4 a = tv[j], b = tv[j | m];
+                            const float4 snd = upper ? a : b;
+                            float4 rcv;
+                            rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, m); rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, m);
+                            rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, m); rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, m);
+                            if (upper) tv[j] = rcv; else tv[j | m] = rcv;
+                        }
+                    }
+                    float hi[32], lo[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        hi[4 * j] = tf32_hi(tv[j].x); hi[4 * j + 1] = tf32_hi(tv[j].y); hi[4 * j + 2] = tf32_hi(tv[j].z); hi[4 * j + 3] = tf32_hi(tv[j].w);
+                        lo[4 * j] = tv[j].x - hi[4 * j]; lo[4 * j + 1] = tv[j].y - hi[4 * j + 1];
+                        lo[4 * j + 2] = tv[j].z - hi[4 * j + 2]; lo[4 * j + 3] = tv[j].w - hi[4 * j + 3];
+                    }
+                    const uint32_t ta = tmem_base + ((uint32_t)wrow0 << 16) + a_col0 + (uint32_t)c_stage * 64u;
+                    tmem_st32(ta, hi);
+                    if (PASSES == 3) tmem_st32(ta + 32u, lo);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int r = wrow0 + sub + 4 * j;
+                        const float4 t = tv[j];
+                        const float4 h = make_float4(tf32_hi(t.x), tf32_hi(t.y), tf32_hi(t.z), tf32_hi(t.w));
+                        uint8_t* dst = a_hi0 + r * 128 + ((chunk ^ (r & 7)) << 4);
+                        *reinterpret_cast<float4*>(dst) = h;
+                        if (PASSES == 3)
+                            *reinterpret_cast<float4*>(dst + a_bytes) = make_float4(t.x - h.x, t.y - h.y, t.z - h.z, t.w - h.w);
+                    }
+                    fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * c_stage);   // one arrival per warp, not 32 serialised ones
-            c_c0 += kGroups * kBlockK;
+            c_c0 += kGroups * KB;
             while (c_c0 >= p.C) c_c0 -= p.C;
             c_stage += kGroups;
             while (c_stage >= SA) { c_stage -= SA; c_par ^= 1u; }
         };
-        // software pipeline: the loads of the next k-block are in flight while the current one is staged
-        if (group < num_kb) issue(buf[0], bmask[0]);
-        for (int kb = group; kb < num_kb; kb += 2 * kGroups) {
-            const int kb1 = kb + kGroups, kb2 = kb + 2 * kGroups;
-            if (kb1 < num_kb) issue(buf[1], bmask[1]);
-            consume(buf[0], bmask[0]);
-            if (kb1 < num_kb) {
-                if (kb2 < num_kb) issue(buf[0], bmask[0]);
-                consume(buf[1], bmask[1]);
+        // software pipeline: the loads of the next unit are in flight while the current one is staged
+        if (F16) {
+            if (group < num_kb) issue(buf[0], bmask[0], 0);
+            for (int kb = group; kb < num_kb; kb += kGroups) {
+                issue(buf[1], bmask[1], 1);
+                consume(buf[0], bmask[0], 0);
+                if (kb + kGroups < num_kb) issue(buf[0], bmask[0], 0);
+                consume(buf[1], bmask[1], 1);
+            }
+            // range check of the fp16 operands: anything at or beyond the largest finite half raises the caller's flag
+            if (p.flag && !(amax < 65504.f)) atomicOr(p.flag, 1);
+        } else {
+            if (group < num_kb) issue(buf[0], bmask[0], 0);
+            for (int kb = group; kb < num_kb; kb += 2 * kGroups) {
+                const int kb1 = kb + kGroups, kb2 = kb + 2 * kGroups;
+                if (kb1 < num_kb) issue(buf[1], bmask[1], 0);
+                consume(buf[0], bmask[0], 0);
+                if (kb1 < num_kb) {
+                    if (kb2 < num_kb) issue(buf[0], bmask[0], 0);
+                    consume(buf[1], bmask[1], 0);
+                }
             }
         }
 
         // ===================== epilogue: TMEM -> registers -> global (8 warps, alternate 32-column chunks) ====
+        if (tid == 0) trace_stamp(p, 3);   // producers done
         mbar_wait(bar_acc, 0);
         tc_fence_after();
+        if (tid == 0) trace_stamp(p, 4);   // accumulator complete
         const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const int er = (warp & 3) * 32 + lane;     // accumulator row = TMEM lane
         const int ev = row0 + er;
         const bool erow_ok = ev < Vq;
+        const float out_mul = F16 ? p.out_mul : 1.0f;
         for (int cb = group * 32; cb < N; cb += 32 * kGroups) {
             float acc[32];
             tmem_ld32(t_lane + (uint32_t)cb, acc);   // warp-collective: executed by every lane
@@ -431,6 +547,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
             for (int j = 0; j < 32; j += 4) {
                 if (j < ncol) {   // N is a multiple of 8, so whole float4 groups
                     float4 t = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                    if (F16) { t.x *= out_mul; t.y *= out_mul; t.z *= out_mul; t.w *= out_mul; }   // exact: power of two
                     if (bs) { float4 b = __ldg(reinterpret_cast<const float4*>(bs + j)); t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w; }
                     if (rs) { float4 q = __ldg(reinterpret_cast<const float4*>(rs + j)); t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
                     if (erow_ok) *reinterpret_cast<float4*>(o + j) = t;
@@ -453,25 +570,29 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
             }
         }
         tc_fence_before();
+        if (tid == 0) trace_stamp(p, 5);   // epilogue stores issued
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer: one thread =====================
         if (lane == 0) {
-            // instruction descriptor: D = F32 [4,6), A = B = TF32 [7,10) [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nmma >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+            // instruction descriptor: D = F32 [4,6), A / B format [7,10) [10,13) (2 = TF32, 0 = F16), K-major both,
+            // N>>3 [17,23), M>>4 [24,29)
+            const uint32_t fmt = F16 ? 0u : 2u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Nmma >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(bar_fullb + 8 * sb, pb);
                 mbar_wait(bar_full + 8 * sa, pa);
                 tc_fence_after();
+                if (kb == 0) trace_stamp(p, 2);   // first operands staged
                 const uint32_t st = smem_u32(smem + (size_t)sa * a_stage);
                 const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + a_bytes);
                 const uint32_t bb = smem_u32(smem_b + (size_t)sb * b_stage);
                 const uint64_t b_hi = make_desc(bb), b_lo = make_desc(bb + b_bytes);
                 const uint32_t ta = tmem_base + a_col0 + (uint32_t)sa * 64u;   // ATMEM: this stage's A columns (hi at +0, lo at +32)
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                    const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);  // 32 bytes per K step inside the swizzle row
+                for (int k = 0; k < 4; ++k) {   // 4 MMAs of 32 bytes of K per 128-byte swizzle row (8 tf32 / 16 fp16 elements)
+                    const uint64_t adv = (uint64_t)((k * 32) >> 4);
                     if (ATMEM) {
                         umma_tf32_ts(tmem_base, ta + k * kUmmaK, b_hi + adv, idesc, (kb | k) != 0);
                         if (PASSES == 3) {
@@ -479,10 +600,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
                             umma_tf32_ts(tmem_base, ta + k * kUmmaK, b_lo + adv, idesc, 1);
                         }
                     } else {
-                        umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+                        umma_ss<F16>(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
                         if (PASSES == 3) {
-                            umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
-                            umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_ss<F16>(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
+                            umma_ss<F16>(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
                         }
                     }
                 }
@@ -509,12 +630,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
                     // this CTA fetches rows [rank * n_tile/CL, +n_tile/CL) of the tile and delivers them to all siblings
                     const int rows = p.n_tile / CL;
                     const uint32_t off = cta_rank * (uint32_t)rows * 128u;
-                    tma_load_2d_mcast(bb + off, &map_hi, bar_fullb + 8 * sb, kb * kBlockK, n0 + (int)cta_rank * rows, cta_mask);
+                    tma_load_2d_mcast(bb + off, &map_hi, bar_fullb + 8 * sb, kb * KB, n0 + (int)cta_rank * rows, cta_mask);
                     if (PASSES == 3)
-                        tma_load_2d_mcast(bb + b_bytes + off, &map_lo, bar_fullb + 8 * sb, kb * kBlockK, n0 + (int)cta_rank * rows, cta_mask);
+                        tma_load_2d_mcast(bb + b_bytes + off, &map_lo, bar_fullb + 8 * sb, kb * KB, n0 + (int)cta_rank * rows, cta_mask);
                 } else {
-                    tma_load_2d(bb, &map_hi, bar_fullb + 8 * sb, kb * kBlockK, n0);
-                    if (PASSES == 3) tma_load_2d(bb + b_bytes, &map_lo, bar_fullb + 8 * sb, kb * kBlockK, n0);
+                    tma_load_2d(bb, &map_hi, bar_fullb + 8 * sb, kb * KB, n0);
+                    if (PASSES == 3) tma_load_2d(bb + b_bytes, &map_lo, bar_fullb + 8 * sb, kb * KB, n0);
                 }
                 if (++sb == SB) { sb = 0; pb ^= 1u; }
             }
@@ -527,6 +648,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
     }
+    if (tid == 0) trace_stamp(p, 6);   // teardown
     if (p.out_sums) {
         // per-CTA column sums -> group sums -> one double atomic per group
         const int g0 = n0 / p.out_cpg, g1 = (n0 + N) / p.out_cpg;   // n_tile is a multiple of out_cpg (checked on the host)
@@ -541,8 +663,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
 
 // weight -> K-major ([F,K]) copies split for the fp32-parity passes: hi = round-to-tf32(w), lo = w - hi.
 // transposed_in = 0: w is [K,F] (reference conv layout);  1: w is [F,K] already (nn.Linear layout)
-__global__ void k_split_tf32(const float* __restrict__ in, int K, int F, int transposed_in, float* __restrict__ hi,
-                             float* __restrict__ lo) {
+// HALF: fp16 copies of w * mul (mul a power of two chosen by the caller so the largest weight sits high in the
+// half range): hi = half(w*mul), lo = half(w*mul - hi).
+template <bool HALF>
+__global__ void k_split(const float* __restrict__ in, int K, int F, int transposed_in, float mul, void* __restrict__ hi_v,
+                        void* __restrict__ lo_v) {
     __shared__ float tile[32][33];
     int k0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -559,9 +684,20 @@ __global__ void k_split_tf32(const float* __restrict__ in, int K, int F, int tra
         int f = f0 + i, k = k0 + threadIdx.x;
         if (f < F && k < K) {
             float w = tile[threadIdx.x][i];
-            float h = tf32_hi(w);
-            hi[(size_t)f * K + k] = h;
-            if (lo) lo[(size_t)f * K + k] = w - h;
+            if (HALF) {
+                __half* hi = reinterpret_cast<__half*>(hi_v);
+                __half* lo = reinterpret_cast<__half*>(lo_v);
+                w *= mul;
+                const __half h = __float2half_rn(w);
+                hi[(size_t)f * K + k] = h;
+                if (lo) lo[(size_t)f * K + k] = __float2half_rn(w - __half2float(h));
+            } else {
+                float* hi = reinterpret_cast<float*>(hi_v);
+                float* lo = reinterpret_cast<float*>(lo_v);
+                float h = tf32_hi(w);
+                hi[(size_t)f * K + k] = h;
+                if (lo) lo[(size_t)f * K + k] = w - h;
+            }
         }
     }
 }
@@ -582,49 +718,40 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// [F rows, K cols] fp32, box = 32 (K) x n_tile (rows), 128-byte swizzle; rows beyond F read as zeros
 int lcm16(int a) {
     int x = 16, y = a;
     while (y) { int t = x % y; x = y; y = t; }
     return 16 / x * a;
 }
 
-int make_weight_map(CUtensorMap* map, const float* w, int F, int K, int n_tile) {
+// [F rows, K cols] of fp32 (box 32 x n_tile) or fp16 (box 64 x n_tile): one 128-byte swizzle row of K per weight
+// row; rows beyond F read as zeros
+int make_weight_map(CUtensorMap* map, const void* w, int F, int K, int n_tile, bool half) {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) return -4;
+    const size_t esz = half ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)F};
-    cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)n_tile};
+    cuuint64_t strides[1] = {(cuuint64_t)K * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)n_tile};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(w), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -5;
 }
 
-}  // namespace
-
-extern "C" {
-
-int ltn_split_tf32(const float* w, int K, int F, int transposed_in, float* wt_hi, float* wt_lo, void* stream) {
-    if (K <= 0 || F <= 0) return 0;
-    dim3 grid((K + 31) / 32, (F + 31) / 32), block(32, 8);
-    k_split_tf32<<<grid, block, 0, (cudaStream_t)stream>>>(w, K, F, transposed_in, wt_hi, wt_lo);
-    LTN_CHECK_LAUNCH();
-    return 0;
-}
-
-// Fused gather + GEMM on tcgen05.  See the header of this file; the C ABI is documented in
-// include/latticenet_b200.h.  passes: 3 = fp32-parity split (default), 1 = single-pass TF32.
-int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int Vq, const int* vq_dev, int C, int S,
-                const float* wt_hi, const float* wt_lo, int F, const float* a_scale, const float* a_shift,
-                const double* gn_sums, const float* gn_gamma, const float* gn_beta, float gn_eps, int gn_groups, int relu,
-                const float* bias, const float* res, float* out, int ldo, double* out_sums, int out_groups, int passes,
-                void* stream) {
+// common launcher.  half: fp16 operands (wt_* are __half copies scaled by 2^w_log2, activations are scaled by 2^a_log2).
+int conv_launch(const float* x, int Vx, const int* vx_dev, const int* nbr, int Vq, const int* vq_dev, int C, int S,
+                const void* wt_hi, const void* wt_lo, int F, const float* a_scale, const float* a_shift, const double* gn_sums,
+                const float* gn_gamma, const float* gn_beta, float gn_eps, int gn_groups, int relu, const float* bias,
+                const float* res, float* out, int ldo, double* out_sums, int out_groups, int passes, bool half, int a_log2,
+                int w_log2, int* flag, void* stream) {
     if (Vq <= 0) return 0;
     if (Vx <= 0) return -2;   // row 0 of x must be readable (stand-in address of absent neighbours)
     const bool affine = a_scale || gn_sums;
-    if (C <= 0 || C % kBlockK || (affine && C > 256) || F <= 0 || F % 8 || S < 1 || (passes != 1 && passes != 3) || ldo % 4) return -2;
+    const int kb_elems = half ? 64 : kBlockK;
+    if (C <= 0 || C % kb_elems || (affine && C > 256) || F <= 0 || F % 8 || S < 1 || (passes != 1 && passes != 3) || ldo % 4) return -2;
+    if (half && passes != 3) return -2;
     if ((a_scale == nullptr) != (a_shift == nullptr) || (a_scale && gn_sums)) return -2;
     if (gn_sums && (gn_groups <= 0 || C % gn_groups)) return -2;
     if (out_sums && (out_groups <= 0 || F % out_groups)) return -2;
@@ -634,6 +761,10 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     p.gn_eps = gn_eps; p.gn_cpg = gn_sums ? C / gn_groups : 1; p.bias = bias; p.res = res; p.out = out; p.out_sums = out_sums;
     p.out_cpg = out_sums ? F / out_groups : 1;
     p.vq_dev = vq_dev; p.vx_dev = vx_dev; p.Vq = Vq; p.Vx = Vx; p.C = C; p.S = nbr ? S : 1; p.F = F; p.ldo = ldo; p.relu = relu;
+    p.a_mul = half ? ldexpf(1.0f, a_log2) : 1.0f;
+    p.out_mul = half ? ldexpf(1.0f, -(a_log2 + w_log2)) : 1.0f;
+    p.flag = half ? flag : nullptr;
+    p.trace = g_trace;
     // Output channels per CTA.  All of them when they fit one accumulator (A rows gathered once); when that
     // leaves SMs idle (few row tiles) the channels are split further, but never beyond ONE wave of 148 CTAs
     // (one CTA per SM: a second, partly filled wave would cost a whole extra tile time).
@@ -654,7 +785,7 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     // memory 111.7 us (1-pass: 40.8 vs 79.1 us) -- correct, but the register transpose + tcgen05.st/wait::st chain in
     // the producers costs more than the tensor core's shared-memory reads it removes.  Off unless LTN_CONV_ATMEM=1.
     static const int want_atmem = []() { const char* e = getenv("LTN_CONV_ATMEM"); return e ? atoi(e) : 0; }();
-    const bool atmem = want_atmem != 0;
+    const bool atmem = want_atmem != 0 && !half;
     int sa, sb;
     size_t smem;
     if (atmem) {
@@ -690,12 +821,13 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     else if (want_cl >= 2 && row_tiles >= 2) cl = 2;
     p.cluster = cl;
     alignas(64) CUtensorMap map_hi, map_lo;
-    int rc = make_weight_map(&map_hi, wt_hi, F, p.S * C, n_tile / cl);
+    int rc = make_weight_map(&map_hi, wt_hi, F, p.S * C, n_tile / cl, half);
     if (rc) return rc;
-    rc = make_weight_map(&map_lo, passes == 3 ? wt_lo : wt_hi, F, p.S * C, n_tile / cl);
+    rc = make_weight_map(&map_lo, passes == 3 ? wt_lo : wt_hi, F, p.S * C, n_tile / cl, half);
     if (rc) return rc;
-    const void* fn = passes == 3 ? (atmem ? (const void*)k_conv_tc<3, true> : (const void*)k_conv_tc<3, false>)
-                                 : (atmem ? (const void*)k_conv_tc<1, true> : (const void*)k_conv_tc<1, false>);
+    const void* fn = half ? (const void*)k_conv_tc<3, false, true>
+                   : passes == 3 ? (atmem ? (const void*)k_conv_tc<3, true, false> : (const void*)k_conv_tc<3, false, false>)
+                                 : (atmem ? (const void*)k_conv_tc<1, true, false> : (const void*)k_conv_tc<1, false, false>);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg = {};
@@ -715,6 +847,56 @@ int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     if (e != cudaSuccess) return (int)e;
     LTN_CHECK_LAUNCH();
     return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ltn_split_tf32(const float* w, int K, int F, int transposed_in, float* wt_hi, float* wt_lo, void* stream) {
+    if (K <= 0 || F <= 0) return 0;
+    dim3 grid((K + 31) / 32, (F + 31) / 32), block(32, 8);
+    k_split<false><<<grid, block, 0, (cudaStream_t)stream>>>(w, K, F, transposed_in, 1.0f, wt_hi, wt_lo);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+int ltn_split_f16(const float* w, int K, int F, int transposed_in, int w_log2, void* wt_hi, void* wt_lo, void* stream) {
+    if (K <= 0 || F <= 0) return 0;
+    dim3 grid((K + 31) / 32, (F + 31) / 32), block(32, 8);
+    k_split<true><<<grid, block, 0, (cudaStream_t)stream>>>(w, K, F, transposed_in, ldexpf(1.0f, w_log2), wt_hi, wt_lo);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+// Phase tracing of the NEXT ltn_conv_tc* launches: buf (device, nullable to switch off) receives 8 globaltimer stamps
+// per CTA: entry, set-up done, first operands staged, producers done, accumulator complete, epilogue stores issued, teardown.
+int ltn_conv_trace(unsigned long long* buf) {
+    g_trace = buf;
+    return 0;
+}
+
+// Fused gather + GEMM on tcgen05.  See the header of this file; the C ABI is documented in
+// include/latticenet_b200.h.  passes: 3 = fp32-parity split (default), 1 = single-pass TF32.
+int ltn_conv_tc(const float* x, int Vx, const int* vx_dev, const int* nbr, int Vq, const int* vq_dev, int C, int S,
+                const float* wt_hi, const float* wt_lo, int F, const float* a_scale, const float* a_shift,
+                const double* gn_sums, const float* gn_gamma, const float* gn_beta, float gn_eps, int gn_groups, int relu,
+                const float* bias, const float* res, float* out, int ldo, double* out_sums, int out_groups, int passes,
+                void* stream) {
+    return conv_launch(x, Vx, vx_dev, nbr, Vq, vq_dev, C, S, wt_hi, wt_lo, F, a_scale, a_shift, gn_sums, gn_gamma, gn_beta, gn_eps,
+                       gn_groups, relu, bias, res, out, ldo, out_sums, out_groups, passes, false, 0, 0, nullptr, stream);
+}
+
+// The same operation with fp16 hi/lo operands (fp32-parity, three passes): wt_hi / wt_lo from ltn_split_f16 with
+// the same w_log2; activations are scaled by 2^a_log2 before the split; *flag (nullable) is OR-ed with 1 when a
+// scaled activation reaches the end of the half range (the result is then unusable: redo with ltn_conv_tc).
+int ltn_conv_tc_f16(const float* x, int Vx, const int* vx_dev, const int* nbr, int Vq, const int* vq_dev, int C, int S,
+                    const void* wt_hi, const void* wt_lo, int w_log2, int a_log2, int F, const float* a_scale,
+                    const float* a_shift, const double* gn_sums, const float* gn_gamma, const float* gn_beta, float gn_eps,
+                    int gn_groups, int relu, const float* bias, const float* res, float* out, int ldo, double* out_sums,
+                    int out_groups, int* flag, void* stream) {
+    return conv_launch(x, Vx, vx_dev, nbr, Vq, vq_dev, C, S, wt_hi, wt_lo, F, a_scale, a_shift, gn_sums, gn_gamma, gn_beta, gn_eps,
+                       gn_groups, relu, bias, res, out, ldo, out_sums, out_groups, 3, true, a_log2, w_log2, flag, stream);
 }
 
 }  // extern "C"

@@ -17,7 +17,7 @@ whose fusion modules have no static-capacity implementation.
 """
 import torch
 
-from . import _lib
+from . import _lib, ops
 from .lattice import Lattice
 from .runner import WindowRunner
 
@@ -29,8 +29,8 @@ def _round_up(x, m):
 
 
 class GraphWindowRunner(WindowRunner):
-    def __init__(self, cfg_path, nr_classes=26, device=None, headroom=1.35):
-        super().__init__(cfg_path, nr_classes, device)
+    def __init__(self, cfg_path, nr_classes=26, device=None, headroom=1.35, operands="f16"):
+        super().__init__(cfg_path, nr_classes, device, operands)
         self.headroom = headroom
         self.graphs = {}
         self.kernels = {}      # frame kind -> kernels of this library inside its graph (bench.py: gpu_launches)
@@ -74,7 +74,7 @@ class GraphWindowRunner(WindowRunner):
         lvl = self.static_lattice
         for _ in range(len(self.caps["v"]) - 1):
             lvl = lvl.coarse_level()
-        self._counts_host = torch.zeros(len(self.caps["v"]), dtype=torch.int32).pin_memory()
+        self._counts_host = torch.zeros(len(self.caps["v"]) + 1, dtype=torch.int32).pin_memory()   # + the fp16 range flag
         self.graphs = {}
         self.pool = None
 
@@ -91,7 +91,8 @@ class GraphWindowRunner(WindowRunner):
         first, last = kind
         if first:
             self.model.reset_sequence()
-        out, _, _ = self.model(self.static_lattice, self.pos_buf, self.val_buf, not last, False)
+        with ops.tc_operands(self.operands, self.range_flag):   # the flag's address is baked into the captured graph
+            out, _, _ = self.model(self.static_lattice, self.pos_buf, self.val_buf, not last, False)
         return out
 
     def _run_frame(self, kind, p, v):
@@ -159,14 +160,28 @@ class GraphWindowRunner(WindowRunner):
     def kernels_per_window(self, nr_frames):
         return sum(self.kernels.get((t == 0, t == nr_frames - 1), 0) for t in range(nr_frames))
 
-    def counts_ok(self):
-        """one small device->host read: did every level stay within its capacity?"""
-        lvl, i = self.static_lattice, 0
-        while lvl is not None and i < len(self.caps["v"]):
-            self._counts_host[i:i + 1].copy_(lvl.hash_table.count_tensor(), non_blocking=True)
+    def _copy_checks(self, host):
+        """queues the device->host copies of the window's safety checks: vertex counts of every level + the fp16 range flag"""
+        lvl, i, nv = self.static_lattice, 0, len(self.caps["v"])
+        while lvl is not None and i < nv:
+            host[i:i + 1].copy_(lvl.hash_table.count_tensor(), non_blocking=True)
             lvl, i = lvl._coarse, i + 1
+        host[nv:nv + 1].copy_(self.range_flag, non_blocking=True)
+
+    def _checks_ok(self, host):
+        vals, nv = host.tolist(), len(self.caps["v"])
+        if vals[nv]:   # an activation left the fp16 range: clear the flag, the caller re-runs the window
+            self.range_flag.zero_()
+            self.range_fallbacks += 1
+            return False
+        return all(int(c) < cap for c, cap in zip(vals[:nv], self.caps["v"]))
+
+    def counts_ok(self):
+        """one small device->host read: did every level stay within its capacity, and every staged activation
+        within the fp16 range?"""
+        self._copy_checks(self._counts_host)
         torch.cuda.current_stream().synchronize()
-        return all(int(c) < cap for c, cap in zip(self._counts_host.tolist(), self.caps["v"]))
+        return self._checks_ok(self._counts_host)
 
     def infer_window(self, frames_host):
         if not self.supported or self.caps is None:
@@ -198,8 +213,8 @@ class MultiWindowRunner:
     strictly sequential chain.  Interleaving the frame graphs of two windows lets one window's small kernels
     run on the SMs the other leaves idle -- the intra-GPU form of the sharding-by-window of SURVEY.md 8(e)."""
 
-    def __init__(self, cfg_path, nr_classes=26, device=None, lanes=2):
-        self.lanes = [GraphWindowRunner(cfg_path, nr_classes, device) for _ in range(lanes)]
+    def __init__(self, cfg_path, nr_classes=26, device=None, lanes=2, operands="f16"):
+        self.lanes = [GraphWindowRunner(cfg_path, nr_classes, device, operands=operands) for _ in range(lanes)]
         self.device = self.lanes[0].device
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(lanes)]
         self.supported = self.lanes[0].supported
@@ -276,13 +291,10 @@ class MultiWindowRunner:
                 buf = self._host_out.get(key)
                 if buf is None or buf[0].shape[0] < n:
                     buf = (torch.empty(max(n, lane.caps["n"]), dtype=torch.int64).pin_memory(),
-                           torch.zeros(len(lane.caps["v"]), dtype=torch.int32).pin_memory())
+                           torch.zeros(len(lane.caps["v"]) + 1, dtype=torch.int32).pin_memory())
                     self._host_out[key] = buf
                 buf[0][:n].copy_(lab, non_blocking=True)
-                lvl, j = lane.static_lattice, 0
-                while lvl is not None and j < len(lane.caps["v"]):
-                    buf[1][j:j + 1].copy_(lvl.hash_table.count_tensor(), non_blocking=True)
-                    lvl, j = lvl._coarse, j + 1
+                lane._copy_checks(buf[1])
                 ev = torch.cuda.Event()
                 ev.record()
             ticket["labels"].append(buf[0][:n])
@@ -297,9 +309,12 @@ class MultiWindowRunner:
         out = []
         for i, (lab, counts, ev) in enumerate(zip(ticket["labels"], ticket["counts"], ticket["events"])):
             lane = self.lanes[i]
+            ok = False
             if ev is not None:
                 ev.synchronize()
-            if ev is not None and all(int(c) < cap for c, cap in zip(counts.tolist(), lane.caps["v"])):
+                with torch.cuda.stream(self.streams[i]):
+                    ok = lane._checks_ok(counts)
+            if ok:
                 out.append(lab)
             else:
                 lane.fallbacks += 1

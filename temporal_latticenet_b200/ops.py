@@ -135,52 +135,108 @@ def scatter_mean(src, index, dim_size=None, out=None):
 # ---------------------------------------------------------------------------------------------------
 _WT_CACHE = {}
 TC_PASSES = 3  # 3 = fp32-parity split (default); 1 = single-pass TF32 (stated separately wherever used)
+A_LOG2 = 5     # fp16 operands: activations are staged as x * 2^5 (overflow flag beyond |x| >= 2047, hi/lo floor 1e-9)
+
+# Operand type of the fp32-parity convolution.  "tf32": hi/lo split in tf32 (4 bytes / element) -- always safe.
+# "f16": the same 11 + 11 significant bits as fp16 hi/lo (2 bytes / element: half the shared-memory traffic, twice
+# the tensor rate).  fp16's exponent range is handled by exact power-of-two scaling plus a device-side range flag,
+# so "f16" is only selected by callers that CHECK the flag and redo the window with "tf32" when it is raised
+# (runner.py / engine.py); modules called directly stay on "tf32".
+_TC = {"mode": "tf32", "flag": None}
+
+
+class tc_operands:
+    """context manager: with ops.tc_operands("f16", flag_tensor): ...  (flag_tensor: int32 [1] on the device)"""
+
+    def __init__(self, mode, flag=None):
+        if mode not in ("tf32", "f16"):
+            raise ValueError("operand mode must be 'tf32' or 'f16'")
+        if mode == "f16" and flag is None:
+            raise ValueError("fp16 operands need a range flag the caller checks")
+        self.new = {"mode": mode, "flag": flag}
+
+    def __enter__(self):
+        self.old = dict(_TC)
+        _TC.update(self.new)
+        return self
+
+    def __exit__(self, *exc):
+        _TC.update(self.old)
+        return False
 
 
 def conv_tc_supported(C, F, folded_norm=True):
     return C % 32 == 0 and C > 0 and (C <= 256 or not folded_norm) and F % 8 == 0 and F > 0
 
 
-def k_major(weight, transposed=False):
-    """(hi, lo): K-major ([F,K]) tf32-split copies of a weight for the tensor-core kernel, cached per
-    parameter version.  `transposed=True`: the tensor is [F,K] already (nn.Linear layout)."""
-    key = (id(weight), bool(transposed))
+class SplitWeight:
+    """K-major ([F,K]) operand copies of one weight for the tensor-core kernel, built on demand per operand type:
+    tf32() -> (hi, lo) fp32 tensors; f16() -> (hi, lo, w_log2) fp16 tensors holding w * 2^w_log2."""
+
+    def __init__(self, w, transposed):
+        self.w = w                      # detached, contiguous fp32; [F,K] if transposed else [K,F]
+        self.transposed = bool(transposed)
+        self.F, self.K = (w.shape if transposed else (w.shape[1], w.shape[0]))
+        self._tf32 = None
+        self._f16 = None
+
+    def tf32(self):
+        if self._tf32 is None:
+            hi = torch.empty(self.F, self.K, dtype=torch.float32, device=self.w.device)
+            lo = torch.empty(self.F, self.K, dtype=torch.float32, device=self.w.device)
+            _lib.check(_lib.load().ltn_split_tf32(_lib.ptr(self.w), self.K, self.F, 1 if self.transposed else 0, _lib.ptr(hi),
+                                                  _lib.ptr(lo), _lib.stream()), "ltn_split_tf32")
+            self._tf32 = (hi, lo)
+        return self._tf32
+
+    def f16(self):
+        if self._f16 is None:
+            # largest |w| -> just below 2^14 (half overflows at 65504): one host read per weight version
+            m = float(self.w.abs().max().item()) if self.w.numel() else 0.0
+            log2 = 0
+            if m > 0.0 and m != float("inf") and m == m:
+                import math
+                log2 = max(-60, min(60, 13 - math.frexp(m)[1] + 1))
+            hi = torch.empty(self.F, self.K, dtype=torch.float16, device=self.w.device)
+            lo = torch.empty(self.F, self.K, dtype=torch.float16, device=self.w.device)
+            _lib.check(_lib.load().ltn_split_f16(_lib.ptr(self.w), self.K, self.F, 1 if self.transposed else 0, log2, _lib.ptr(hi),
+                                                 _lib.ptr(lo), _lib.stream()), "ltn_split_f16")
+            self._f16 = (hi, lo, log2)
+        return self._f16
+
+    def __iter__(self):   # `hi, lo = k_major(w)` keeps working
+        return iter(self.tf32())
+
+
+def _cached_split(weight, key, make):
     hit = _WT_CACHE.get(key)
     ver = weight._version
     # the weak reference guards against a recycled id(): only the very same live tensor object hits
     if hit is not None and hit[0] == ver and hit[1]() is weight and hit[3] == weight.data_ptr():
         return hit[2]
-    w = weight.detach().contiguous().float()
-    if transposed:
-        F, K = w.shape
-    else:
-        K, F = w.shape
-    hi = torch.empty(F, K, dtype=torch.float32, device=w.device)
-    lo = torch.empty(F, K, dtype=torch.float32, device=w.device)
-    _lib.check(_lib.load().ltn_split_tf32(_lib.ptr(w), K, F, 1 if transposed else 0, _lib.ptr(hi), _lib.ptr(lo), _lib.stream()),
-               "ltn_split_tf32")
+    sw = make()
     if len(_WT_CACHE) > 1024:
         for k in [k for k, v in _WT_CACHE.items() if v[1]() is None]:
             del _WT_CACHE[k]
-    _WT_CACHE[key] = (ver, weakref.ref(weight), (hi, lo), weight.data_ptr())
-    return hi, lo
+    _WT_CACHE[key] = (ver, weakref.ref(weight), sw, weight.data_ptr())
+    return sw
+
+
+def k_major(weight, transposed=False):
+    """SplitWeight of a weight, cached per parameter version.  `transposed=True`: the tensor is [F,K] already
+    (nn.Linear layout); otherwise the reference's conv layout [K,F]."""
+    return _cached_split(weight, (id(weight), bool(transposed)),
+                         lambda: SplitWeight(weight.detach().contiguous().float(), transposed))
 
 
 def k_major_padded(weight, rows):
     """k_major of an nn.Linear weight [F,K] zero-padded to `rows` output rows (F is not a multiple of 8)"""
-    key = (id(weight), "pad", int(rows))
-    hit = _WT_CACHE.get(key)
-    ver = weight._version
-    if hit is not None and hit[0] == ver and hit[1]() is weight and hit[3] == weight.data_ptr():
-        return hit[2]
-    F, K = weight.shape
-    wp = torch.zeros(rows, K, dtype=torch.float32, device=weight.device)
-    wp[:F] = weight.detach()
-    hi = torch.empty(rows, K, dtype=torch.float32, device=weight.device)
-    lo = torch.empty(rows, K, dtype=torch.float32, device=weight.device)
-    _lib.check(_lib.load().ltn_split_tf32(_lib.ptr(wp), K, rows, 1, _lib.ptr(hi), _lib.ptr(lo), _lib.stream()), "ltn_split_tf32")
-    _WT_CACHE[key] = (ver, weakref.ref(weight), (hi, lo), weight.data_ptr())
-    return hi, lo
+    def make():
+        F, K = weight.shape
+        wp = torch.zeros(rows, K, dtype=torch.float32, device=weight.device)
+        wp[:F] = weight.detach()
+        return SplitWeight(wp, True)
+    return _cached_split(weight, (id(weight), "pad", int(rows)), make)
 
 
 def gn_sums(x, groups):
@@ -193,17 +249,17 @@ def gn_sums(x, groups):
 
 
 def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, gn=None, relu=False, bias=None, res=None, out=None,
-            out_sums=None, passes=None):
+            out_sums=None, passes=None, operands=None, flag=None):
     """out[v,:] = sum_s act(x[nbr[v,s],:]) @ W[s] (+bias) (+res); nbr None = plain row-wise GEMM.
     wt = k_major(weight).  gn = (sums [G,2], gamma, beta, eps): GroupNorm of x folded into the gather.
-    out_sums [Gout,2] (zeroed): receives the GroupNorm statistics of the output."""
+    out_sums [Gout,2] (zeroed): receives the GroupNorm statistics of the output.
+    operands: "tf32" / "f16" (default: the mode set by ops.tc_operands); f16 needs C % 64 == 0 and `flag`."""
     x = x.contiguous()
-    hi, lo = wt
     C = x.shape[1]
     S = 1 if nbr is None else nbr.shape[1]
-    F = hi.shape[0]
-    if hi.shape[1] != S * C:
-        raise RuntimeError("weight is [%d,%d], expected [%d,%d]" % (hi.shape[0], hi.shape[1], F, S * C))
+    F = wt.F
+    if wt.K != S * C:
+        raise RuntimeError("weight is [%d,%d], expected [%d,%d]" % (F, wt.K, F, S * C))
     Vq = (x.shape[0] if nbr is None else nbr.shape[0]) if nr_rows is None else nr_rows
     if out is None:
         out = torch.empty(Vq, F, dtype=torch.float32, device=x.device)
@@ -213,12 +269,26 @@ def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, gn=None, relu=
     if gn is not None:
         g_sums, g_gamma, g_beta, g_eps = gn
         g_groups = g_sums.shape[0]
-    rc = _lib.load().ltn_conv_tc(p(x), x.shape[0], _lib.rows_dev(x.shape[0]), p(nbr), Vq, _lib.rows_dev(Vq), C, S, p(hi), p(lo), F,
-                                 p(a_scale), p(a_shift),
-                                 p(g_sums), p(g_gamma), p(g_beta), float(g_eps), int(g_groups), 1 if relu else 0, p(bias), p(res),
-                                 p(out), out.stride(0), p(out_sums), 0 if out_sums is None else out_sums.shape[0],
-                                 TC_PASSES if passes is None else passes, _lib.stream())
-    _lib.check(rc, "ltn_conv_tc")
+    passes = TC_PASSES if passes is None else passes
+    mode = _TC["mode"] if operands is None else operands
+    flag = _TC["flag"] if flag is None else flag
+    if mode == "f16" and passes == 3 and C % 64 == 0:
+        if flag is None:
+            raise RuntimeError("fp16 operands need a range flag")
+        hi, lo, w_log2 = wt.f16()
+        rc = _lib.load().ltn_conv_tc_f16(p(x), x.shape[0], _lib.rows_dev(x.shape[0]), p(nbr), Vq, _lib.rows_dev(Vq), C, S, p(hi), p(lo),
+                                         int(w_log2), int(A_LOG2), F, p(a_scale), p(a_shift), p(g_sums), p(g_gamma), p(g_beta),
+                                         float(g_eps), int(g_groups), 1 if relu else 0, p(bias), p(res), p(out), out.stride(0),
+                                         p(out_sums), 0 if out_sums is None else out_sums.shape[0], p(flag), _lib.stream())
+        _lib.check(rc, "ltn_conv_tc_f16")
+    else:
+        hi, lo = wt.tf32()
+        rc = _lib.load().ltn_conv_tc(p(x), x.shape[0], _lib.rows_dev(x.shape[0]), p(nbr), Vq, _lib.rows_dev(Vq), C, S, p(hi), p(lo), F,
+                                     p(a_scale), p(a_shift),
+                                     p(g_sums), p(g_gamma), p(g_beta), float(g_eps), int(g_groups), 1 if relu else 0, p(bias), p(res),
+                                     p(out), out.stride(0), p(out_sums), 0 if out_sums is None else out_sums.shape[0],
+                                     passes, _lib.stream())
+        _lib.check(rc, "ltn_conv_tc")
     if out_sums is not None:
         out._ltn_gn_sums = (_FRAME["id"], out_sums)   # travels with the tensor to the next layer's GroupNorm
     return out

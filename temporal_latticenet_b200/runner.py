@@ -6,19 +6,25 @@ This is the public entry point `bench.py` times end to end (host buffers in, hos
 """
 import torch
 
+from . import ops
 from .config import ConfigParser
 from .lattice import Lattice, ModelParams
 from .model import LatticeNetSeq
 
 
 class WindowRunner:
-    def __init__(self, cfg_path, nr_classes=26, device=None):
+    def __init__(self, cfg_path, nr_classes=26, device=None, operands="f16"):
         self.cfg_path = cfg_path
         self.device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
         self.model = LatticeNetSeq(nr_classes, ModelParams.create(cfg_path), ConfigParser(cfg_path)).to(self.device)
         self.model.train(False)
         self.lattice = None
         self._labels_host = None
+        # operand type of the fp32-parity tensor-core convolutions: fp16 hi/lo by default (ops.tc_operands), with the
+        # device-side range flag checked after every window and a tf32 re-run when it was raised
+        self.operands = operands
+        self.range_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.range_fallbacks = 0
 
     def new_lattice(self):
         """a fresh lattice per window (train_ln.py:236-239, test_ln.py:264)"""
@@ -40,14 +46,25 @@ class WindowRunner:
     def infer_window_device(self, frames_dev):
         """frames_dev: list of (positions [N,3], values [N,1]) CUDA tensors.  Returns the final
         frame's log-softmax [N, classes] (device)."""
-        ls = self.new_lattice()
-        out = None
-        last = len(frames_dev) - 1
-        with torch.no_grad():
-            for i, (p, v) in enumerate(frames_dev):
-                out, _, ls = self.model(ls, p, v, i != last, False)
-        self.lattice = ls
+        for operands in ((self.operands, "tf32") if self.operands != "tf32" else ("tf32",)):
+            ls = self.new_lattice()
+            out = None
+            last = len(frames_dev) - 1
+            with torch.no_grad(), ops.tc_operands(operands, self.range_flag):
+                for i, (p, v) in enumerate(frames_dev):
+                    out, _, ls = self.model(ls, p, v, i != last, False)
+            self.lattice = ls
+            if operands == "tf32" or not self.range_raised():
+                break
+            self.range_fallbacks += 1     # an activation left the fp16 range: the tf32 operands redo the window
         return out
+
+    def range_raised(self):
+        """reads (and clears) the fp16 range flag; synchronises the current stream"""
+        raised = bool(int(self.range_flag.item()))
+        if raised:
+            self.range_flag.zero_()
+        return raised
 
     def infer_window(self, frames_host):
         """frames_host: list of (positions, values) PINNED host tensors.  Returns predicted labels of

@@ -3,7 +3,8 @@ the same contraction over the oracle's neighbour table (oracle im2row, SURVEY B.
 
 Tolerance (stated, fp32-parity mode = 3-pass tf32 split): |err| <= 2e-5 * sum_k |a_k||w_k| per output
 -- fp32-class (plain fp32 accumulation of K = 576..2304 terms sits at the same level); the single-pass
-TF32 variant is checked separately at 2e-3.
+TF32 variant is checked separately at 2e-3.  The fp16-operand form of the same split (11 + 11 significant
+bits per operand in half the bytes, power-of-two scaled, range-flagged) is held to the SAME 2e-5 bound.
 """
 import numpy as np
 import pytest
@@ -57,6 +58,11 @@ def test_gather_conv_matches_float64(dev, lattice, C, F):
     # single-pass TF32 variant, stated separately
     out1 = ops.conv_tc(x.to(dev), nbr, wt, passes=1).cpu().numpy()
     _check(out1, rows, W.double().numpy(), np.zeros((V, F)), 2e-3)
+    if C % 64 == 0:   # fp16 hi/lo operands: same bound, and the range flag stays down
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        out16 = ops.conv_tc(x.to(dev), nbr, wt, operands="f16", flag=flag).cpu().numpy()
+        _check(out16, rows, W.double().numpy(), np.zeros((V, F)), 2e-5)
+        assert int(flag.item()) == 0
 
 
 def test_folded_groupnorm_relu_bias_residual_and_short_values(dev, lattice):
@@ -73,6 +79,11 @@ def test_folded_groupnorm_relu_bias_residual_and_short_values(dev, lattice):
     out = ops.conv_tc(x.to(dev), ls.neighbours(), ops.k_major(W.to(dev)), a_scale=sc.to(dev), a_shift=sh.to(dev), relu=True,
                       bias=bias.to(dev), res=res.to(dev)).cpu().numpy()
     _check(out, rows, W.double().numpy(), (bias + res).double().numpy(), 3e-5)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = ops.conv_tc(x.to(dev), ls.neighbours(), ops.k_major(W.to(dev)), a_scale=sc.to(dev), a_shift=sh.to(dev), relu=True,
+                      bias=bias.to(dev), res=res.to(dev), operands="f16", flag=flag).cpu().numpy()
+    _check(out, rows, W.double().numpy(), (bias + res).double().numpy(), 3e-5)
+    assert int(flag.item()) == 0
 
 
 @pytest.mark.parametrize("V,C,F", [(1, 64, 64), (127, 64, 48), (129, 96, 16), (5000, 128, 384), (3001, 192, 576), (777, 256, 256)])
@@ -85,6 +96,11 @@ def test_dense_rows_and_n_tiling(dev, V, C, F):
     b = torch.randn(F, generator=g)
     out = ops.conv_tc(x.to(dev), None, ops.k_major(W.to(dev), transposed=True), bias=b.to(dev)).cpu().numpy()
     _check(out, x.double().numpy(), W.double().numpy().T, np.broadcast_to(b.double().numpy(), (V, F)), 2e-5)
+    if C % 64 == 0:
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        out = ops.conv_tc(x.to(dev), None, ops.k_major(W.to(dev), transposed=True), bias=b.to(dev), operands="f16", flag=flag).cpu().numpy()
+        _check(out, x.double().numpy(), W.double().numpy().T, np.broadcast_to(b.double().numpy(), (V, F)), 2e-5)
+        assert int(flag.item()) == 0
 
 
 def test_cross_level_tables(dev, lattice):
@@ -130,6 +146,13 @@ def test_groupnorm_folded_from_sums_and_output_statistics(dev, lattice, C, F):
     out = ops.conv_tc(xd, ls.neighbours(), ops.k_major(W.to(dev)), gn=(sums, gamma.to(dev), beta.to(dev), 1e-5), relu=True,
                       out_sums=out_sums).cpu().numpy()
     _check(out, rows, W.double().numpy(), np.zeros((V, F)), 1e-4)   # + the normalisation's own fp32 rounding
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    out_sums16 = torch.zeros(Gout, 2, dtype=torch.float64, device=dev)
+    out16 = ops.conv_tc(xd, ls.neighbours(), ops.k_major(W.to(dev)), gn=(sums, gamma.to(dev), beta.to(dev), 1e-5), relu=True,
+                        out_sums=out_sums16, operands="f16", flag=flag).cpu().numpy()
+    _check(out16, rows, W.double().numpy(), np.zeros((V, F)), 1e-4)
+    np.testing.assert_allclose(out_sums16.cpu().numpy()[:, 1], out_sums.cpu().numpy()[:, 1], rtol=1e-5)
+    assert int(flag.item()) == 0
     cpg = F // Gout
     o64 = out.astype(np.float64).reshape(V, Gout, cpg)
     want = np.stack([o64.sum((0, 2)), (o64 ** 2).sum((0, 2))], 1)
@@ -139,6 +162,31 @@ def test_groupnorm_folded_from_sums_and_output_statistics(dev, lattice, C, F):
     # gn_stats kernel itself
     s64 = x.double().reshape(V, G, C // G)
     np.testing.assert_allclose(sums.cpu().numpy(), np.stack([s64.sum((0, 2)).numpy(), (s64 ** 2).sum((0, 2)).numpy()], 1), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 300.0])
+def test_fp16_operands_across_magnitudes_and_range_flag(dev, scale):
+    """fp16 hi/lo operands keep the fp32-class bound for small and large activations (power-of-two scaling, subnormal
+    lo parts), weights of any magnitude (per-tensor scale), and RAISE the flag -- instead of returning garbage
+    silently -- once an activation leaves the representable range (|x| * 2^5 >= 65504)."""
+    from temporal_latticenet_b200 import ops
+    g = torch.Generator().manual_seed(int(scale * 1000) % 9973)
+    V, C, F = 3000, 128, 64
+    x = torch.randn(V, C, generator=g) * scale
+    for wmag in (1e-4, 1.0, 5e3):
+        W = torch.randn(F, C, generator=g) * wmag
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        out = ops.conv_tc(x.to(dev), None, ops.k_major(W.to(dev), transposed=True), operands="f16", flag=flag).cpu().numpy()
+        _check(out, x.double().numpy(), W.double().numpy().T, np.zeros((V, F)), 2e-5)
+        assert int(flag.item()) == 0
+    xb = x.clone()
+    xb[1234, 77] = 2100.0      # 2100 * 32 > 65504
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.conv_tc(xb.to(dev), None, ops.k_major(W.to(dev), transposed=True), operands="f16", flag=flag)
+    assert int(flag.item()) == 1
+    # the tf32 operands take the same input without a flag
+    out = ops.conv_tc(xb.to(dev), None, ops.k_major(W.to(dev), transposed=True)).cpu().numpy()
+    _check(out, xb.double().numpy(), W.double().numpy().T, np.zeros((V, F)), 2e-5)
 
 
 def test_alternative_operand_paths_agree(dev, lattice):

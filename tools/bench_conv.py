@@ -38,9 +38,11 @@ for name, Vq, Vx, nb, C, F in cases:
     fl = 2.0 * Vq * S * C * F
     t3 = graph_time(lambda: ops.conv_tc(x, nb, wt, nr_rows=Vq, out=out))
     t1 = graph_time(lambda: ops.conv_tc(x, nb, wt, nr_rows=Vq, out=out, passes=1))
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    t16 = graph_time(lambda: ops.conv_tc(x, nb, wt, nr_rows=Vq, out=out, operands="f16", flag=flag)) if C % 64 == 0 else float("nan")
     rows = torch.empty(Vq, S * C, device=dev)
     if nb is not None:
         tb = graph_time(lambda: torch.mm(funcs.im2row_raw(x, nb), W, out=out))
     else:
         tb = graph_time(lambda: torch.mm(x, W, out=out))
-    print("%-26s 3pass %.1f us %6.1f TF/s | 1pass %.1f us %6.1f TF/s | im2row+cuBLAS fp32 %.1f us %6.1f TF/s" % (name, 1e3*t3, fl / t3 / 1e9, 1e3*t1, fl / t1 / 1e9, 1e3*tb, fl / tb / 1e9))
+    print("%-26s f16x3 %.1f us %6.1f TF/s | tf32x3 %.1f us %6.1f TF/s | tf32x1 %.1f us %6.1f TF/s | im2row+cuBLAS fp32 %.1f us %6.1f TF/s" % (name, 1e3*t16, fl / t16 / 1e9, 1e3*t3, fl / t3 / 1e9, 1e3*t1, fl / t1 / 1e9, 1e3*tb, fl / tb / 1e9))
