@@ -24,10 +24,10 @@
 //    from a dedicated warp, completing on the same mbarrier as the A producers.
 //    A multi-stage mbarrier ring decouples both from the single MMA-issuing thread; tcgen05.commit
 //    releases stages and finally hands the accumulator to the epilogue.
-//  * epilogue (8 warps): tcgen05.ld 32x32b (thread = row, 32 columns at a time) -> + bias, + residual ->
-//    128-byte row-segment stores; optionally the GroupNorm statistics of the OUTPUT (sum, sum of squares
-//    per group) are reduced here with a warp reduce-scatter, so the next layer's normalisation costs no
-//    extra pass over the data.
+//  * epilogue (8 warps): tcgen05.ld 32x32b (thread = row, 32 columns at a time) -> per-warp swizzled transpose in
+//    the idle operand ring -> quarter-warp per row: + bias, + residual, whole 128-byte lines stored; optionally
+//    the GroupNorm statistics of the OUTPUT (sum, sum of squares per group) are reduced here, so the next
+//    layer's normalisation costs no extra pass over the data.
 //  * sizes that only the device knows (vertex counts after hash insertion) are read from device
 //    memory (vq_dev / vx_dev), so the launch needs no host synchronisation.
 #include "ltn_common.cuh"
@@ -171,21 +171,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// warp reduce-scatter: lane L ends with sum over the 32 lanes of v[L]  (31 shuffles instead of 160)
-__device__ __forceinline__ float warp_column_sums(float* v, int lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int j = 0; j < off; ++j) {
-            float send = upper ? v[j] : v[j + off];
-            float keep = upper ? v[j + off] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    return v[0];
 }
 
 struct ConvParams {
@@ -531,41 +516,58 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         mbar_wait(bar_acc, 0);
         tc_fence_after();
         if (tid == 0) trace_stamp(p, 4);   // accumulator complete
+        // The accumulator leaves TMEM with thread = row (tcgen05.ld 32x32b), but a row-per-thread global store touches
+        // 32 different cache lines per instruction, 16 bytes each.  Every warp therefore turns its 32 x 32 block around
+        // in a private 4 KB of the (now idle) operand ring -- swizzled so that both directions are conflict-free -- and
+        // finishes quarter-warp per row: whole 128-byte lines for the output stores and the residual loads, the
+        // GroupNorm statistics of the output from 2 shuffle rounds per column quad.
         const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const int er = (warp & 3) * 32 + lane;     // accumulator row = TMEM lane
-        const int ev = row0 + er;
-        const bool erow_ok = ev < Vq;
+        float* stage = reinterpret_cast<float*>(smem + warp * 4096);
+        const int wrow = (warp & 3) * 32;
         const float out_mul = F16 ? p.out_mul : 1.0f;
         for (int cb = group * 32; cb < N; cb += 32 * kGroups) {
             float acc[32];
             tmem_ld32(t_lane + (uint32_t)cb, acc);   // warp-collective: executed by every lane
-            const int ncol = min(32, N - cb);
-            const float* rs = (p.res && erow_ok) ? p.res + (size_t)ev * p.F + n0 + cb : nullptr;
-            const float* bs = p.bias ? p.bias + n0 + cb : nullptr;
-            float* o = p.out + (size_t)ev * p.ldo + n0 + cb;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                if (j < ncol) {   // N is a multiple of 8, so whole float4 groups
-                    float4 t = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-                    if (F16) { t.x *= out_mul; t.y *= out_mul; t.z *= out_mul; t.w *= out_mul; }   // exact: power of two
-                    if (bs) { float4 b = __ldg(reinterpret_cast<const float4*>(bs + j)); t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w; }
-                    if (rs) { float4 q = __ldg(reinterpret_cast<const float4*>(rs + j)); t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
-                    if (erow_ok) *reinterpret_cast<float4*>(o + j) = t;
-                    acc[j] = t.x; acc[j + 1] = t.y; acc[j + 2] = t.z; acc[j + 3] = t.w;
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                    make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            __syncwarp();
+            const bool col_ok = 4 * chunk < N - cb;   // N is a multiple of 8, so whole float4 groups
+            const int col = n0 + cb + 4 * chunk;
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + sub;
+                const int v = row0 + wrow + r;
+                float4 t = *reinterpret_cast<const float4*>(stage + r * 32 + ((chunk ^ (r & 7)) << 2));
+                if (F16) { t.x *= out_mul; t.y *= out_mul; t.z *= out_mul; t.w *= out_mul; }   // exact: power of two
+                t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w;
+                if (v < Vq && col_ok) {
+                    if (p.res) {
+                        const float4 q = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)v * p.F + col));
+                        t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+                    }
+                    *reinterpret_cast<float4*>(p.out + (size_t)v * p.ldo + col) = t;
+                    cs.x += t.x; cs.y += t.y; cs.z += t.z; cs.w += t.w;
+                    cq.x = fmaf(t.x, t.x, cq.x); cq.y = fmaf(t.y, t.y, cq.y); cq.z = fmaf(t.z, t.z, cq.z); cq.w = fmaf(t.w, t.w, cq.w);
                 }
             }
+            __syncwarp();   // the block is consumed before the next chunk overwrites it
             if (p.out_sums) {
-                float sq[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (!erow_ok || j >= ncol) acc[j] = 0.f;
-                    sq[j] = acc[j] * acc[j];
+                for (int o = 8; o <= 16; o <<= 1) {   // the four row groups of a column quad
+                    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+                    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+                    cq.x += __shfl_xor_sync(0xffffffffu, cq.x, o); cq.y += __shfl_xor_sync(0xffffffffu, cq.y, o);
+                    cq.z += __shfl_xor_sync(0xffffffffu, cq.z, o); cq.w += __shfl_xor_sync(0xffffffffu, cq.w, o);
                 }
-                const float cs = warp_column_sums(acc, lane);
-                const float cq = warp_column_sums(sq, lane);
-                if (lane < ncol) {
-                    atomicAdd(&s_colsum[cb + lane], cs);
-                    atomicAdd(&s_colsum[256 + cb + lane], cq);
+                if (sub == 0 && col_ok) {
+                    float* sc = s_colsum + cb + 4 * chunk;
+                    atomicAdd(sc, cs.x); atomicAdd(sc + 1, cs.y); atomicAdd(sc + 2, cs.z); atomicAdd(sc + 3, cs.w);
+                    atomicAdd(sc + 256, cq.x); atomicAdd(sc + 257, cq.y); atomicAdd(sc + 258, cq.z); atomicAdd(sc + 259, cq.w);
                 }
             }
         }

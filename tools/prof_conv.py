@@ -13,8 +13,10 @@ C = F = 192
 x = torch.randn(V, C, device=dev)
 W = torch.randn(9 * C, F, device=dev) / (9 * C) ** 0.5
 wt = ops.k_major(W)
-passes = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+passes = 3
+mode = sys.argv[1] if len(sys.argv) > 1 else "f16"
+flag = torch.zeros(1, dtype=torch.int32, device=dev)
 for _ in range(4):
-    out = ops.conv_tc(x, nbr, wt, passes=passes)
+    out = ops.conv_tc(x, nbr, wt, passes=passes, operands=mode, flag=flag)
 torch.cuda.synchronize()
 print("ok", V, float(out.abs().mean()))
