@@ -40,7 +40,7 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 8;          // tf32: 32 bytes per MMA
-constexpr int kGroups = 2;         // producer warpgroups (round-robin k-blocks); 3 measured slower (67 vs 60 us at 192->192)
+constexpr int kGroups = 2;         // producer warpgroups (round-robin k-blocks); 3 measured equal (fp16, A in tensor memory) or slower (tf32: register spills)
 constexpr int kGroupThreads = 128;
 constexpr int kMmaWarp = 4 * kGroups, kTmaWarp = 4 * kGroups + 1;
 constexpr int kThreads = 32 * (4 * kGroups + 2);   // producer/epilogue warps + MMA warp + TMA warp
@@ -125,6 +125,19 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+template <bool F16>
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (F16) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        umma_tf32_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);
+    }
+}
 // 32 registers of this thread -> 32 consecutive TMEM columns of its lane (warp w%4 owns lanes 32(w%4)..+31)
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
@@ -135,6 +148,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
           "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
           "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
           "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+// 16 lanes x 32 columns: thread T supplies, per column group g, the columns 8g + 2(T%4) + {0,1} of lane T/4 (registers
+// 4g, 4g+1) and of lane T/4 + 8 (registers 4g+2, 4g+3)
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -218,7 +240,6 @@ unsigned long long* g_trace = nullptr;
 template <int PASSES, bool ATMEM, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, ConvParams p) {
-    static_assert(!(ATMEM && F16), "the tensor-memory A path exists for tf32 operands only");
     constexpr int KB = F16 ? 64 : kBlockK;          // K elements per k-block
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 1];
@@ -337,6 +358,100 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         // All ring / k-block bookkeeping is incremental: no integer division in the loop.
         const float4* x4 = reinterpret_cast<const float4*>(p.x);
         const uint32_t c4 = (uint32_t)p.C >> 2;
+        if constexpr (F16 && ATMEM) {
+            // ---- fp16 operands staged in TENSOR memory: no shared-memory A ring at all -------------------------------
+            // tcgen05.st.16x256b hands thread T the 32-bit columns 8g + 2(T%4) + {0,1} of lanes T/4 and T/4 + 8 -- four
+            // consecutive fp16 channels of two rows per column group g.  The gather is laid out the SAME way (thread T
+            // fetches the float4 at channel 16g + 4(T%4) of its rows; 4 lanes cover 64 contiguous bytes of a row), so the
+            // converted values go from registers straight to the operand's place: no transpose, no shuffle, no st.shared,
+            // and the tensor core no longer reads A through the shared-memory pipe (80 of the 120-200 KB per k-block).
+            // A unit is 16 tile rows x 64 channels (8 float4 per thread), two units per k-block and warp.
+            const int ra = lane >> 2, cq = lane & 3;
+            float4 buf[2][8];
+            uint32_t bmask[2];
+            uint32_t rowidx[4];    // float4 index of (source vertex of tile row wrow0 + ra + 8r, this lane's channel quad)
+            uint32_t rmask = 0;
+            float amax = 0.f;
+            int i_slot = group / kb_per_slot, i_c0 = (group - i_slot * kb_per_slot) * KB, i_cur = -1;   // issue position
+            int c_c0 = i_c0, c_stage = group % SA;                                                    // consume position
+            uint32_t c_par = ((group / SA) & 1) ^ 1;
+            auto issue = [&](float4* dst, uint32_t& dmask, const int half) {
+                if (i_slot != i_cur) {
+                    i_cur = i_slot;
+                    const int* tap = s_nbr + i_slot * kBlockM + wrow0 + ra;
+                    rmask = 0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int sv = tap[8 * r];
+                        rowidx[r] = (uint32_t)(sv >= 0 ? sv : 0) * c4 + (uint32_t)cq;   // row 0 stands in for an absent neighbour
+                        rmask |= (sv >= 0 ? 1u : 0u) << r;
+                    }
+                }
+                const uint32_t o = (uint32_t)i_c0 >> 2;
+                dmask = half ? (rmask >> 2) : rmask;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t ri = (half ? rowidx[2 + h] : rowidx[h]) + o;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) dst[4 * h + g] = __ldg(x4 + ri + 4 * g);
+                }
+                if (!half) return;
+                i_c0 += kGroups * KB;
+                while (i_c0 >= p.C) { i_c0 -= p.C; ++i_slot; }
+            };
+            auto consume = [&](const float4* cur, uint32_t cmask, const int half) {
+                if (half == 0) {
+                    if (lane == 0) mbar_wait(bar_empty + 8 * c_stage, c_par);   // one waiter per warp
+                    __syncwarp();
+                    tc_fence_after();
+                }
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float4 sc = make_float4(a_mul, a_mul, a_mul, a_mul), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (affine) {
+                        sc = *reinterpret_cast<const float4*>(s_affine + c_c0 + 16 * g + 4 * cq);
+                        sh = *reinterpret_cast<const float4*>(s_affine + 256 + c_c0 + 16 * g + 4 * cq);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float4 t = cur[4 * h + g];
+                        t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y);
+                        t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
+                        if (p.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+                        if (!((cmask >> h) & 1u)) t = make_float4(0.f, 0.f, 0.f, 0.f);   // absent neighbour / row beyond the tile
+                        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+                        const __half2 h01 = __floats2half2_rn(t.x, t.y), h23 = __floats2half2_rn(t.z, t.w);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        const __half2 l01 = __floats2half2_rn(t.x - f01.x, t.y - f01.y), l23 = __floats2half2_rn(t.z - f23.x, t.w - f23.y);
+                        hi[4 * g + 2 * h] = *reinterpret_cast<const uint32_t*>(&h01);
+                        hi[4 * g + 2 * h + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                        lo[4 * g + 2 * h] = *reinterpret_cast<const uint32_t*>(&l01);
+                        lo[4 * g + 2 * h + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+                    }
+                }
+                const uint32_t ta = tmem_base + ((uint32_t)(wrow0 + 16 * half) << 16) + a_col0 + (uint32_t)c_stage * 64u;
+                tmem_st_16x256b_x4(ta, hi);
+                if (PASSES == 3) tmem_st_16x256b_x4(ta + 32u, lo);
+                if (half == 0) return;
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + 8 * c_stage);   // one arrival per warp
+                c_c0 += kGroups * KB;
+                while (c_c0 >= p.C) c_c0 -= p.C;
+                c_stage += kGroups;
+                while (c_stage >= SA) { c_stage -= SA; c_par ^= 1u; }
+            };
+            if (group < num_kb) issue(buf[0], bmask[0], 0);
+            for (int kb = group; kb < num_kb; kb += kGroups) {
+                issue(buf[1], bmask[1], 1);
+                consume(buf[0], bmask[0], 0);
+                if (kb + kGroups < num_kb) issue(buf[0], bmask[0], 0);
+                consume(buf[1], bmask[1], 1);
+            }
+            if (p.flag && !(amax < 65504.f)) atomicOr(p.flag, 1);
+        } else {
         float4 buf[2][8];      // two register buffers, used with compile-time indices
         uint32_t bmask[2];     // bit j: tile row j of the warp's walk is a present neighbour
         uint32_t rowidx[8];    // float4 index of (row j's source vertex, this lane's chunk), refreshed per slot
@@ -511,6 +626,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
             }
         }
 
+        }
+
         // ===================== epilogue: TMEM -> registers -> global (8 warps, alternate 32-column chunks) ====
         if (tid == 0) trace_stamp(p, 3);   // producers done
         mbar_wait(bar_acc, 0);
@@ -595,11 +712,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {   // 4 MMAs of 32 bytes of K per 128-byte swizzle row (8 tf32 / 16 fp16 elements)
                     const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                    if (ATMEM) {
-                        umma_tf32_ts(tmem_base, ta + k * kUmmaK, b_hi + adv, idesc, (kb | k) != 0);
+                    if (ATMEM) {   // 8 tensor-memory columns per MMA: 8 tf32 or 16 fp16 elements of K
+                        umma_ts<F16>(tmem_base, ta + k * 8, b_hi + adv, idesc, (kb | k) != 0);
                         if (PASSES == 3) {
-                            umma_tf32_ts(tmem_base, ta + 32u + k * kUmmaK, b_hi + adv, idesc, 1);
-                            umma_tf32_ts(tmem_base, ta + k * kUmmaK, b_lo + adv, idesc, 1);
+                            umma_ts<F16>(tmem_base, ta + 32u + k * 8, b_hi + adv, idesc, 1);
+                            umma_ts<F16>(tmem_base, ta + k * 8, b_lo + adv, idesc, 1);
                         }
                     } else {
                         umma_ss<F16>(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
@@ -786,8 +903,10 @@ int conv_launch(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     // Measured (tools/bench_conv.py, 192->192 on 13.7k vertices): A staged in shared memory 60.6 us, A staged in tensor
     // memory 111.7 us (1-pass: 40.8 vs 79.1 us) -- correct, but the register transpose + tcgen05.st/wait::st chain in
     // the producers costs more than the tensor core's shared-memory reads it removes.  Off unless LTN_CONV_ATMEM=1.
-    static const int want_atmem = []() { const char* e = getenv("LTN_CONV_ATMEM"); return e ? atoi(e) : 0; }();
-    const bool atmem = want_atmem != 0 && !half;
+    // fp16 operands: A staged in tensor memory is the default (the gather is laid out like the tcgen05.st fragment,
+    // so nothing has to be transposed); LTN_CONV_ATMEM=0 keeps the shared-memory ring.
+    static const int want_atmem = []() { const char* e = getenv("LTN_CONV_ATMEM"); return e ? atoi(e) : -1; }();
+    const bool atmem = half ? (want_atmem != 0) : (want_atmem > 0);
     int sa, sb;
     size_t smem;
     if (atmem) {
@@ -800,7 +919,9 @@ int conv_launch(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
         sb = (int)(budget / b_stage);
         if (sb > kMaxStages) sb = kMaxStages;
         if (sb < 2) return -3;
-        smem = sb * b_stage + 1024;
+        smem = sb * b_stage;
+        if (smem < 12 * 4096) smem = 12 * 4096;   // the epilogue turns each warp's 32 x 32 block around in 4 KB of this region
+        smem += 1024;
     } else {
         sa = (int)((budget - 2 * b_stage) / a_stage);
         if (sa > kMaxStages) sa = kMaxStages;
@@ -827,7 +948,7 @@ int conv_launch(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     if (rc) return rc;
     rc = make_weight_map(&map_lo, passes == 3 ? wt_lo : wt_hi, F, p.S * C, n_tile / cl, half);
     if (rc) return rc;
-    const void* fn = half ? (const void*)k_conv_tc<3, false, true>
+    const void* fn = half ? (atmem ? (const void*)k_conv_tc<3, true, true> : (const void*)k_conv_tc<3, false, true>)
                    : passes == 3 ? (atmem ? (const void*)k_conv_tc<3, true, false> : (const void*)k_conv_tc<3, false, false>)
                                  : (atmem ? (const void*)k_conv_tc<1, true, false> : (const void*)k_conv_tc<1, false, false>);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -76,13 +76,14 @@ class GRUModule(torch.nn.Module, _HiddenState):
             self._store(lv)
             return lv, ls
         g = self.GRU
-        h = ops.linear(self.h_lv, self.hidden_linear.weight, self.hidden_linear.bias)
+        hrows = self._rows_dev()   # static mode: h covers the PREVIOUS frame's rows; the buffer beyond them is stale
+        h = ops.linear(self.h_lv, self.hidden_linear.weight, self.hidden_linear.bias, rows_dev=hrows)
         V, C, Vh = lv.shape[0], lv.shape[1], h.shape[0]
         if _fused_ok(lv, h, g.weight_ih):
             if Vh > V:
                 _pad_rows(h, V)
             gi = ops.linear(lv, g.weight_ih, g.bias_ih)
-            gh = ops.linear(h, g.weight_hh, g.bias_hh)
+            gh = ops.linear(h, g.weight_hh, g.bias_hh, rows_dev=hrows)
             new_lv = torch.empty_like(lv)
             p = _lib.ptr
             _lib.check(_lib.load().ltn_gru_pointwise(p(gi), p(gh), p(h.contiguous()), p(g.bias_hh), V, Vh, _lib.rows_dev(V),
@@ -111,13 +112,14 @@ class LSTMModule(torch.nn.Module, _HiddenState):
             self._store(lv)
             return lv, ls
         c = self.lstm
-        h = ops.linear(self.h_lv, self.hidden_linear.weight, self.hidden_linear.bias)
+        hrows = self._rows_dev()
+        h = ops.linear(self.h_lv, self.hidden_linear.weight, self.hidden_linear.bias, rows_dev=hrows)
         V, C, Vh = lv.shape[0], lv.shape[1], h.shape[0]
         if _fused_ok(lv, h, c.weight_ih):
             if Vh > V:
                 _pad_rows(h, V)
             gi = ops.linear(lv, c.weight_ih, c.bias_ih)
-            gh = ops.linear(h, c.weight_hh, c.bias_hh)
+            gh = ops.linear(h, c.weight_hh, c.bias_hh, rows_dev=hrows)
             new_lv = torch.empty_like(lv)
             p = _lib.ptr
             _lib.check(_lib.load().ltn_lstm_pointwise(p(gi), p(gh), p(c.bias_hh), V, Vh, _lib.rows_dev(V), self._rows_dev(), C,

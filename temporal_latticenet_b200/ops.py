@@ -19,12 +19,14 @@ def no_grad_path(*tensors):
     return not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors))
 
 
-def linear(x, weight, bias=None, relu_out=False):
+def linear(x, weight, bias=None, relu_out=False, rows_dev=None):
     """x @ weight.T + bias.  Without autograd and for tensor-core friendly shapes this is the S = 1 case
-    of the fused tcgen05 kernel (nn.Linear weights are K-major already); otherwise cuBLAS fp32."""
+    of the fused tcgen05 kernel (nn.Linear weights are K-major already); otherwise cuBLAS fp32.
+    rows_dev (static-capacity mode): device pointer of the live row count of x when it is NOT the count of its
+    capacity class -- a hidden state carries the previous frame's count; rows beyond it are never read."""
     if (x.dim() == 2 and x.is_cuda and no_grad_path(x, weight, bias) and conv_tc_supported(x.shape[1], weight.shape[0], False)
             and x.shape[0] > 0):
-        out = conv_tc(x, None, k_major(weight, transposed=True), bias=None if bias is None else bias.detach())
+        out = conv_tc(x, None, k_major(weight, transposed=True), bias=None if bias is None else bias.detach(), rows_dev=rows_dev)
         return torch.relu_(out) if relu_out else out
     out = torch.nn.functional.linear(x, weight, bias)
     return torch.relu(out) if relu_out else out
@@ -249,7 +251,7 @@ def gn_sums(x, groups):
 
 
 def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, gn=None, relu=False, bias=None, res=None, out=None,
-            out_sums=None, passes=None, operands=None, flag=None):
+            out_sums=None, passes=None, operands=None, flag=None, rows_dev=None):
     """out[v,:] = sum_s act(x[nbr[v,s],:]) @ W[s] (+bias) (+res); nbr None = plain row-wise GEMM.
     wt = k_major(weight).  gn = (sums [G,2], gamma, beta, eps): GroupNorm of x folded into the gather.
     out_sums [Gout,2] (zeroed): receives the GroupNorm statistics of the output.
@@ -270,20 +272,22 @@ def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, gn=None, relu=
         g_sums, g_gamma, g_beta, g_eps = gn
         g_groups = g_sums.shape[0]
     passes = TC_PASSES if passes is None else passes
+    vx_dev = _lib.rows_dev(x.shape[0]) if rows_dev is None else rows_dev
+    vq_dev = _lib.rows_dev(Vq) if rows_dev is None else rows_dev
     mode = _TC["mode"] if operands is None else operands
     flag = _TC["flag"] if flag is None else flag
     if mode == "f16" and passes == 3 and C % 64 == 0:
         if flag is None:
             raise RuntimeError("fp16 operands need a range flag")
         hi, lo, w_log2 = wt.f16()
-        rc = _lib.load().ltn_conv_tc_f16(p(x), x.shape[0], _lib.rows_dev(x.shape[0]), p(nbr), Vq, _lib.rows_dev(Vq), C, S, p(hi), p(lo),
+        rc = _lib.load().ltn_conv_tc_f16(p(x), x.shape[0], vx_dev, p(nbr), Vq, vq_dev, C, S, p(hi), p(lo),
                                          int(w_log2), int(A_LOG2), F, p(a_scale), p(a_shift), p(g_sums), p(g_gamma), p(g_beta),
                                          float(g_eps), int(g_groups), 1 if relu else 0, p(bias), p(res), p(out), out.stride(0),
                                          p(out_sums), 0 if out_sums is None else out_sums.shape[0], p(flag), _lib.stream())
         _lib.check(rc, "ltn_conv_tc_f16")
     else:
         hi, lo = wt.tf32()
-        rc = _lib.load().ltn_conv_tc(p(x), x.shape[0], _lib.rows_dev(x.shape[0]), p(nbr), Vq, _lib.rows_dev(Vq), C, S, p(hi), p(lo), F,
+        rc = _lib.load().ltn_conv_tc(p(x), x.shape[0], vx_dev, p(nbr), Vq, vq_dev, C, S, p(hi), p(lo), F,
                                      p(a_scale), p(a_shift),
                                      p(g_sums), p(g_gamma), p(g_beta), float(g_eps), int(g_groups), 1 if relu else 0, p(bias), p(res),
                                      p(out), out.stride(0), p(out_sums), 0 if out_sums is None else out_sums.shape[0],
