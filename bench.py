@@ -160,10 +160,10 @@ class Probe:
     def wrap(self, name, fn, work_fn):
         import torch
 
-        def wrapped(*a):
+        def wrapped(*a, **kw):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            r = fn(*a)
+            r = fn(*a, **kw)
             e1.record()
             self.records.setdefault(name, []).append((e0, e1, work_fn(*a) if work_fn else 0.0))
             return r
@@ -478,7 +478,7 @@ def main():
     mm_orig, lin_orig = ops.matmul, ops.linear
     ops.matmul = probe.wrap("torch.mm(cuBLAS sgemm)", mm_orig, lambda a, b: 2.0 * a.shape[0] * a.shape[1] * b.shape[1])
     ops.linear = probe.wrap("torch.linear(cuBLAS sgemm)", lin_orig,
-                            lambda x, w, b=None: 2.0 * x.shape[0] * x.shape[1] * w.shape[0])
+                            lambda x, w, b=None, *r: 2.0 * x.shape[0] * x.shape[1] * w.shape[0])
     for i in range(min(args.steps, 4)):
         flush.zero_()
         runner.infer_window_device(devw[i % len(devw)])

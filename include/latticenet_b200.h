@@ -157,6 +157,14 @@ int ltn_pointnet(const float* rows, int width, const int* idx, int R, const int*
                  const float* w2, const float* b2, const float* w3, const float* b3, int V, const int* v_dev,
                  unsigned long long* packed, const double* vert_acc, int min_rows, float* out, void* stream);
 
+/* The same with the 32 -> 64 layer on the tensor cores: fp16 hi/lo operands (three passes, fp32-class results as in
+ * ltn_conv_tc_f16), activations staged as relu(h2) * 2^a_log2 straight into tensor memory.  *flag (int32) is OR-ed
+ * with 1 when an activation leaves the fp16 range: the caller then redoes the work with ltn_pointnet. */
+int ltn_pointnet_tc(const float* rows, int width, const int* idx, int R, const int* r_dev, const float* w1, const float* b1,
+                    const float* w2, const float* b2, const float* w3, const float* b3, int V, const int* v_dev,
+                    unsigned long long* packed, const double* vert_acc, int min_rows, float* out, int a_log2, int* flag,
+                    void* stream);
+
 /* ---- temporal fusion (seq_lattice/lattice_modules.py:17-339) ------------------------------------ */
 
 /* GRUModule.forward pointwise stage (lattice_modules.py:58-63); rows >= Vh are the zero padding */

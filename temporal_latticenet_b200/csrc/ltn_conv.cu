@@ -31,6 +31,7 @@
 //  * sizes that only the device knows (vertex counts after hash insertion) are read from device
 //    memory (vq_dev / vx_dev), so the launch needs no host synchronisation.
 #include "ltn_common.cuh"
+#include "ltn_tc.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cstdlib>
@@ -45,32 +46,6 @@ constexpr int kGroupThreads = 128;
 constexpr int kMmaWarp = 4 * kGroups, kTmaWarp = 4 * kGroups + 1;
 constexpr int kThreads = 32 * (4 * kGroups + 2);   // producer/epilogue warps + MMA warp + TMA warp
 constexpr int kMaxStages = 4;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra LAB_WAIT;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // TMA: 2-D tile global -> swizzled shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -159,21 +134,10 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_
           "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 // arrive on the barrier at this offset in EVERY CTA of the mask once the MMAs issued so far have completed
 __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(cta_mask) : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in bits
-// [0,14), leading byte offset (unused for swizzled K-major, 1) [16,30), stride byte offset = 1024 B
-// between 8-row groups [32,46), descriptor version 1 [46,48), layout type SWIZZLE_128B = 2 [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
 }
 
 __device__ __forceinline__ float tf32_hi(float x) {

@@ -15,6 +15,8 @@
 // HBM-bound by construction: reads 4N x 24 B of rows + ids once, writes V x 512 B; the 4N x 64 atomics
 // resolve in L2 (V x 64 x 8 B = 7 MB at V = 14k).
 #include "ltn_common.cuh"
+#include "ltn_tc.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -168,8 +170,9 @@ k_pointnet_mlp_max(const float* __restrict__ rows, int width, const int* __restr
                 const int sl = e >> 4, c = e & 15;
                 const unsigned long long key = ((unsigned long long)t_val[c * kPitch + sl] << 32) |
                                                (unsigned long long)(0xFFFFFFFFu - t_row[c * kPitch + sl]);
-                unsigned long long* dst = packed + (size_t)slot_id[sl] * D3 + q * 16 + c;
-                if (__ldcg(dst) < key) atomicMax(dst, key);
+                // fire-and-forget reduction: no read-back, so nothing waits for an L2 round trip (a `__ldcg` pre-check
+                // here made every thread sit through ~3 dependent L2 latencies per quarter: 157 us -> see profiles/)
+                atomicMax(packed + (size_t)slot_id[sl] * D3 + q * 16 + c, key);
             }
             if (lslot >= kSlots) {   // more distinct vertices than the shared tables hold: this row goes to L2 directly
                 unsigned long long* dst = packed + (size_t)id * D3 + q * 16;
@@ -182,6 +185,245 @@ k_pointnet_mlp_max(const float* __restrict__ rows, int width, const int* __restr
             }
             __syncthreads();
         }
+    }
+}
+
+// The same front end with the LAST MLP layer (32 -> 64: 2048 of the 2624 multiply-adds per row, and most of the
+// shared-memory weight reads that bound the kernel above) on the tensor cores.
+//   * a block owns 256 consecutive rows = two M = 128 accumulator tiles; thread t computes layers 1-2 for ITS row in
+//     registers, splits relu(h2) * 2^a_log2 into fp16 hi + lo (the 11 + 11 significant bits of the fp32-parity
+//     convolution, csrc/ltn_conv.cu) and writes both straight into tensor memory with tcgen05.st.32x32b -- thread =
+//     row = TMEM lane is exactly the A-operand layout of a TS-mode MMA, so the activations never touch shared memory;
+//   * W3 is split the same way by every block into a 128-byte-swizzled K-major tile (K padded to one 128-byte row),
+//     scaled by a power of two taken from max|W3|;
+//   * 2 k-steps x 3 passes (hi*hi + lo*hi + hi*lo) per tile by one thread, fp32 accumulation in TMEM;
+//   * each thread reads its row of the accumulator back 16 columns at a time and feeds the same block-local
+//     segmented max as above.
+// *flag is OR-ed with 1 when a staged activation leaves the fp16 range (the caller then uses k_pointnet_mlp_max).
+__global__ void __launch_bounds__(kThreads, 2)
+k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__ idx, int R, const int* __restrict__ r_dev,
+              MlpWeights w, int V, const int* __restrict__ v_dev, unsigned long long* packed, float a_mul, int* flag) {
+    __shared__ __align__(1024) uint8_t s_w3[2 * 64 * 128];   // [hi | lo] 64 output rows x 128 bytes, SWIZZLE_128B
+    __shared__ __align__(16) float s1[D0 * D1], s2[D1 * D2], sb1[D1], sb2[D2], sb3[D3];
+    __shared__ int h_key[kHash], h_slot[kHash], slot_id[kThreads], nslots;
+    extern __shared__ uint32_t t_dyn[];   // all 64 channels at once: 7 block barriers per 256 rows instead of 20
+    uint32_t* const t_val = t_dyn;
+    uint32_t* const t_row = t_dyn + D3 * kPitch;
+    __shared__ __align__(8) uint64_t bar_mma;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_wmax[kThreads / 32];
+    __shared__ float s_wmul;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < D0 * D1; i += kThreads) s1[(i % D0) * D1 + i / D0] = __ldg(w.w1 + i);
+    for (int i = tid; i < D1 * D2; i += kThreads) s2[(i % D1) * D2 + i / D1] = __ldg(w.w2 + i);
+    for (int i = tid; i < D1; i += kThreads) sb1[i] = __ldg(w.b1 + i);
+    for (int i = tid; i < D2; i += kThreads) sb2[i] = __ldg(w.b2 + i);
+    for (int i = tid; i < D3; i += kThreads) sb3[i] = __ldg(w.b3 + i);
+    // ---- W3 [64, 32] -> fp16 hi / lo, K-major, 128-byte swizzle; thread t: output row t / 4, 8 inputs (one 16-byte chunk)
+    float wv[8];
+    {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w.w3) + tid * 2), b = __ldg(reinterpret_cast<const float4*>(w.w3) + tid * 2 + 1);
+        wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w; wv[4] = b.x; wv[5] = b.y; wv[6] = b.z; wv[7] = b.w;
+        float m = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(wv[i]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) s_wmax[warp] = m;
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(&bar_mma), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float m = 0.f;
+        for (int i = 0; i < kThreads / 32; ++i) m = fmaxf(m, s_wmax[i]);
+        // largest |w| -> [2^13, 2^14): exact power-of-two scale, undone in the epilogue
+        int e = 0;
+        if (m > 0.f && m < 3.0e38f) e = 13 - (int)((__float_as_uint(m) >> 23) & 0xFFu) + 127;
+        e = max(-60, min(60, e));
+        s_wmul = __uint_as_float((uint32_t)(127 + e) << 23);
+    }
+    __syncthreads();
+    const float w_mul = s_wmul;
+    {
+        const int n = tid >> 2, chunk = tid & 3;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float x0 = wv[2 * i] * w_mul, x1 = wv[2 * i + 1] * w_mul;
+            const __half2 h = __floats2half2_rn(x0, x1);
+            const float2 f = __half22float2(h);
+            const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+            hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        uint8_t* dst = s_w3 + n * 128 + ((chunk ^ (n & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + 64 * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        // the upper half of every 128-byte row (K = 32..63) is never read: the MMAs stop after two 32-byte k-steps
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t acc_col = (uint32_t)(warp >> 2) * 64u;          // accumulator of this thread's tile
+    const uint32_t a_col = 128u + (uint32_t)(warp >> 2) * 32u;     // its A operand: 16 columns hi, 16 columns lo
+    const float out_mul = 1.0f / (a_mul * w_mul);                  // both powers of two: exact
+    if (r_dev) R = min(R, *r_dev);
+    if (v_dev) V = min(V, *v_dev);
+    float amax = 0.f;
+    uint32_t phase = 0;
+    for (int base = blockIdx.x * kThreads; base < R; base += gridDim.x * kThreads) {   // block-uniform trip count
+        const int row = base + tid;
+        int id = -1;
+        if (row < R) {
+            id = __ldg(idx + row);
+            id = id < 0 ? 0 : id;                   // lattice_modules.py:479-480
+            if (id >= V) id = -1;
+        }
+        for (int i = tid; i < kHash; i += kThreads) h_key[i] = -1;
+        if (tid == 0) nslots = 0;
+        // ---- MLP 4 -> 16 -> 32 in registers, relu, fp16 hi / lo straight into tensor memory ---------------------
+        {
+            float x[D0] = {0.f, 0.f, 0.f, 0.f};
+            if (id >= 0) {
+                const float* in = rows + (size_t)row * width;
+#pragma unroll
+                for (int i = 0; i < D0; ++i) x[i] = __ldg(in + i);
+            }
+            float h1[D1], h2[D2];
+#pragma unroll
+            for (int o = 0; o < D1; ++o) h1[o] = sb1[o];
+#pragma unroll
+            for (int i = 0; i < D0; ++i)
+#pragma unroll
+                for (int o = 0; o < D1; ++o) h1[o] = fmaf(x[i], s1[i * D1 + o], h1[o]);
+#pragma unroll
+            for (int o = 0; o < D2; ++o) h2[o] = sb2[o];
+#pragma unroll
+            for (int i = 0; i < D1; ++i) {
+                const float a = fmaxf(h1[i], 0.f);
+#pragma unroll
+                for (int o = 0; o < D2; o += 4) {
+                    const float4 ww = *reinterpret_cast<const float4*>(s2 + i * D2 + o);
+                    h2[o] = fmaf(a, ww.x, h2[o]); h2[o + 1] = fmaf(a, ww.y, h2[o + 1]);
+                    h2[o + 2] = fmaf(a, ww.z, h2[o + 2]); h2[o + 3] = fmaf(a, ww.w, h2[o + 3]);
+                }
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float x0 = fmaxf(h2[2 * i], 0.f) * a_mul, x1 = fmaxf(h2[2 * i + 1], 0.f) * a_mul;
+                amax = fmaxf(amax, fmaxf(x0, x1));
+                const __half2 h = __floats2half2_rn(x0, x1);
+                const float2 f = __half22float2(h);
+                const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+                hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+                lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            tmem_st16(t_lane + a_col, hi);
+            tmem_st16(t_lane + a_col + 16u, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            // D = F32, A = B = F16, K-major, N = 64, M = 128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t b_hi = make_desc(smem_u32(s_w3)), b_lo = make_desc(smem_u32(s_w3 + 64 * 128));
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const uint32_t d = tmem_base + (uint32_t)m * 64u, a = tmem_base + 128u + (uint32_t)m * 32u;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {   // 16 fp16 of K = 8 columns of A = 32 bytes of the B row
+                    const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                    umma_f16_ts(d, a + k * 8, b_hi + adv, idesc, k);
+                    umma_f16_ts(d, a + 16u + k * 8, b_hi + adv, idesc, 1);
+                    umma_f16_ts(d, a + k * 8, b_lo + adv, idesc, 1);
+                }
+            }
+            umma_commit(smem_u32(&bar_mma));
+        }
+        // ---- block-local numbering of the distinct vertices (overlaps the MMAs) -------------------------------
+        int hpos = 0;
+        if (id >= 0) {
+            hpos = (int)(((uint32_t)id * 2654435761u) >> 23) & (kHash - 1);
+            while (true) {
+                const int old = atomicCAS(&h_key[hpos], -1, id);
+                if (old == -1 || old == id) break;
+                hpos = (hpos + 1) & (kHash - 1);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < kHash; i += kThreads)
+            if (h_key[i] >= 0) {
+                const int sl = atomicAdd(&nslots, 1);
+                h_slot[i] = sl;
+                slot_id[sl] = h_key[i];
+            }
+        __syncthreads();
+        const int lslot = id >= 0 ? h_slot[hpos] : -1;
+        const int ns = min(nslots, kSlots);
+        const bool local = lslot >= 0 && lslot < kSlots;
+        for (int e = tid; e < ns * D3; e += kThreads) {
+            const int at = (e & (D3 - 1)) * kPitch + (e >> 6);
+            t_val[at] = 0u;
+            t_row[at] = 0xFFFFFFFFu;
+        }
+        mbar_wait(smem_u32(&bar_mma), phase);
+        phase ^= 1u;
+        tc_fence_after();
+        uint32_t enc[D3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float y[16];
+            tmem_ld16(t_lane + acc_col + (uint32_t)(q * 16), y);   // warp-collective
+#pragma unroll
+            for (int o = 0; o < 16; ++o) enc[q * 16 + o] = ord_enc(fmaf(y[o], out_mul, sb3[q * 16 + o]));
+        }
+        __syncthreads();
+        if (local) {
+#pragma unroll
+            for (int o = 0; o < D3; ++o) atomicMax(&t_val[o * kPitch + lslot], enc[o]);
+        }
+        __syncthreads();
+        if (local) {
+#pragma unroll
+            for (int o = 0; o < D3; ++o)
+                if (t_val[o * kPitch + lslot] == enc[o]) atomicMin(&t_row[o * kPitch + lslot], (uint32_t)row);   // smallest row wins ties
+        }
+        __syncthreads();
+        // one fire-and-forget 64-bit reduction per (distinct vertex, channel): value in the high word, ~row in the low word;
+        // 64 consecutive channels of a vertex = 512 contiguous bytes per two warps
+        for (int e = tid; e < ns * D3; e += kThreads) {
+            const int sl = e >> 6, c = e & (D3 - 1);
+            const unsigned long long key = ((unsigned long long)t_val[c * kPitch + sl] << 32) |
+                                           (unsigned long long)(0xFFFFFFFFu - t_row[c * kPitch + sl]);
+            atomicMax(packed + (size_t)slot_id[sl] * D3 + c, key);
+        }
+        if (lslot >= kSlots) {   // more distinct vertices than the shared tables hold: this row goes to L2 directly
+            unsigned long long* dst = packed + (size_t)id * D3;
+            const unsigned long long low = (unsigned long long)(0xFFFFFFFFu - (uint32_t)row);
+#pragma unroll
+            for (int o = 0; o < D3; ++o) atomicMax(dst + o, ((unsigned long long)enc[o] << 32) | low);
+        }
+        __syncthreads();
+        tc_fence_before();   // the next tile's tcgen05.st / MMAs follow this tile's tcgen05.ld across the block barrier above
+    }
+    if (flag && !(amax < 65504.f)) atomicOr(flag, 1);
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
     }
 }
 
@@ -231,6 +473,36 @@ int ltn_pointnet(const float* rows, int width, const int* idx, int R, const int*
         int blocks = (R + kThreads - 1) / kThreads;
         if (blocks > 148 * 8) blocks = 148 * 8;
         k_pointnet_mlp_max<<<blocks, kThreads, 0, st>>>(rows, width, idx, R, r_dev, w, V, v_dev, packed);
+        LTN_CHECK_LAUNCH();
+    }
+    long long total = (long long)V * D3;
+    int blocks = (int)((total + kThreads - 1) / kThreads);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_pointnet_decode<<<blocks, kThreads, 0, st>>>(packed, V, v_dev, R, r_dev, rows, width, vert_acc, min_rows, out);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+// ltn_pointnet with the 32 -> 64 layer on the tensor cores (fp16 hi/lo operands, fp32-parity three passes; activations
+// staged as relu(h2) * 2^a_log2).  *flag (int32) is OR-ed with 1 when an activation leaves the fp16 range: the result is
+// then unusable and the caller redoes the frame with ltn_pointnet.
+int ltn_pointnet_tc(const float* rows, int width, const int* idx, int R, const int* r_dev, const float* w1, const float* b1,
+                    const float* w2, const float* b2, const float* w3, const float* b3, int V, const int* v_dev,
+                    unsigned long long* packed, const double* vert_acc, int min_rows, float* out, int a_log2, int* flag,
+                    void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (V <= 0) return 0;
+    if (width != D0 + 1 || !flag) return -2;
+    cudaError_t e = cudaMemsetAsync(packed, 0, sizeof(unsigned long long) * (size_t)V * D3, st);
+    if (e != cudaSuccess) return (int)e;
+    if (R > 0) {
+        MlpWeights w{w1, b1, w2, b2, w3, b3};
+        int blocks = (R + kThreads - 1) / kThreads;
+        if (blocks > 148 * 2) blocks = 148 * 2;   // persistent: two blocks per SM (256 tensor-memory columns each)
+        const size_t dyn = sizeof(uint32_t) * 2 * D3 * kPitch;
+        e = cudaFuncSetAttribute(k_pointnet_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return (int)e;
+        k_pointnet_tc<<<blocks, kThreads, dyn, st>>>(rows, width, idx, R, r_dev, w, V, v_dev, packed, ldexpf(1.0f, a_log2), flag);
         LTN_CHECK_LAUNCH();
     }
     long long total = (long long)V * D3;

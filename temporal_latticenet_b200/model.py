@@ -91,6 +91,14 @@ class PointNetSeq(torch.nn.Module):
         red = torch.empty(V, 128, dtype=torch.float32, device=dev)
         p = _lib.ptr
         l1, l2, l3 = self.layers
+        from . import ops
+        if ops._TC["mode"] == "f16" and ops._TC["flag"] is not None:   # last layer on the tensor cores (range-flagged)
+            _lib.check(_lib.load().ltn_pointnet_tc(p(distributed), 5, p(indices), R, _lib.rows_dev(R), p(l1.weight.detach()),
+                                                   p(l1.bias.detach()), p(l2.weight.detach()), p(l2.bias.detach()), p(l3.weight.detach()),
+                                                   p(l3.bias.detach()), V, _lib.rows_dev(V), p(packed), p(ls._vert_acc),
+                                                   0 if self.fusion_kind == "maxpool" else _MIN_POINTS_PER_VERTEX, p(red),
+                                                   int(ops.A_LOG2), p(ops._TC["flag"]), _lib.stream()), "ltn_pointnet_tc")
+            return red
         _lib.check(_lib.load().ltn_pointnet(p(distributed), 5, p(indices), R, _lib.rows_dev(R), p(l1.weight.detach()), p(l1.bias.detach()),
                                             p(l2.weight.detach()), p(l2.bias.detach()), p(l3.weight.detach()), p(l3.bias.detach()),
                                             V, _lib.rows_dev(V), p(packed), p(ls._vert_acc), 0 if self.fusion_kind == "maxpool" else

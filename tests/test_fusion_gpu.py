@@ -156,3 +156,64 @@ def test_scatter_max_add_mean_semantics(dev):
     hits = torch.zeros(R, C)
     hits.scatter_add_(0, a.clamp(max=R - 1), (~empty).float())
     assert torch.equal(s.grad.cpu(), hits)
+
+
+@pytest.mark.parametrize("kernel", ["cuda_cores", "tensor_cores"])
+def test_pointnet_front_end_matches_float64(dev, kernel):
+    """PointNetSeqModule front end (lattice_modules.py:448-530): MLP 4 -> 16 -> 32 -> 64 per distributed row, segmented
+    max per vertex with arg-max (smallest row on ties), barycentric weight of the winning row (quirk Q3), min-4-rows mask.
+    Both kernels -- the whole MLP on the CUDA cores, and the 32 -> 64 layer on the tensor cores with fp16 hi/lo operands --
+    against a float64 evaluation: maxima within 1e-5 (relative to the layer's |a||w| sum), and where the float64 runner-up
+    is not within that tolerance of the maximum the arg-max row, hence the gathered barycentric weight, must be the same."""
+    from temporal_latticenet_b200 import _lib
+    from temporal_latticenet_b200.lattice import Lattice
+    p_np, v_np = small_window(seed=5, frames=1, radius=12.0, max_points=20000)[0]
+    ls = Lattice(60000, 0.6, device=dev)
+    rows, idx, w = ls.distribute(torch.from_numpy(p_np).to(dev), torch.from_numpy(v_np).to(dev), True)
+    V, R = ls.nr_lattice_vertices(), rows.shape[0]
+    g = torch.Generator().manual_seed(3)
+    w1, b1 = torch.randn(16, 4, generator=g) * 0.7, torch.randn(16, generator=g) * 0.3
+    w2, b2 = torch.randn(32, 16, generator=g) * 0.35, torch.randn(32, generator=g) * 0.3
+    w3, b3 = torch.randn(64, 32, generator=g) * 0.25, torch.randn(64, generator=g) * 0.3
+    P, lib = _lib.ptr, _lib.load()
+    d = [t.to(dev).contiguous() for t in (w1, b1, w2, b2, w3, b3)]
+    packed = torch.empty(V, 64, dtype=torch.int64, device=dev)
+    out = torch.empty(V, 128, device=dev)
+    if kernel == "cuda_cores":
+        rc = lib.ltn_pointnet(P(rows), 5, P(idx), R, None, *[P(t) for t in d], V, None, P(packed), P(ls._vert_acc), 4, P(out), _lib.stream())
+    else:
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        rc = lib.ltn_pointnet_tc(P(rows), 5, P(idx), R, None, *[P(t) for t in d], V, None, P(packed), P(ls._vert_acc), 4, P(out), 5, P(flag),
+                                 _lib.stream())
+        assert int(flag.item()) == 0
+    assert rc == 0
+    got = out.cpu().double().numpy()
+    # float64 reference
+    x = rows.cpu().double()
+    ids = idx.cpu().long().clamp(min=0)
+    h = torch.relu(x[:, :4] @ w1.double().t() + b1.double())
+    h = torch.relu(h @ w2.double().t() + b2.double())
+    y = h @ w3.double().t() + b3.double()
+    bound = (h.abs() @ w3.double().abs().t() + b3.double().abs()).numpy()
+    y, ids = y.numpy(), ids.numpy()
+    bary = x[:, 4].numpy()
+    cnt = np.bincount(ids, minlength=V)
+    order = np.argsort(ids, kind="stable")
+    starts = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    checked = 0
+    for v in range(V):
+        if cnt[v] < 4:
+            assert not got[v].any()
+            continue
+        rws = order[starts[v]:starts[v] + cnt[v]]
+        yy = y[rws]
+        best = yy.max(0)
+        tol = 1e-5 * bound[rws].max(0)
+        assert np.all(np.abs(got[v, :64] - best) <= tol + 1e-7), (v, np.abs(got[v, :64] - best).max())
+        arg = rws[yy.argmax(0)]
+        arg = np.where(arg > V, 0, arg)                      # quirk Q3, literally
+        srt = np.sort(yy, 0)
+        clear = (srt[-1] - srt[-2] > 4 * tol) if cnt[v] > 1 else np.ones(64, bool)
+        assert np.array_equal(got[v, 64:][clear], bary[arg][clear].astype(np.float32).astype(np.float64)), v
+        checked += int(clear.sum())
+    assert checked > 32 * (cnt >= 4).sum()
