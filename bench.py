@@ -44,13 +44,39 @@ def peaks():
 # clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
 # ------------------------------------------------------------------------------------------------
 class Clocks:
+    """SM clock / throttle-reason samples DURING the timed regions.  In-process NVML (the library nvidia-smi itself
+    queries) from a background thread every 50 ms: a `nvidia-smi -lms` child process was measured to stall the
+    launching thread for tens of milliseconds per query -- a third of a 75 ms timed region.  Falls back to the
+    nvidia-smi child when the NVML binding is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.samples, self.nvml = index, None, [], [], None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_CLOCKS_MS", "200")], stdout=subprocess.PIPE,
@@ -60,11 +86,34 @@ class Clocks:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = (("hw_slowdown", getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                mask = int(reasons_fn(self.h))
+                self.samples.append((sm, [name for name, bit in bits if mask & bit]))
+            except Exception:
+                pass
+            self._stop.wait(float(os.environ.get("BENCH_CLOCKS_MS", "50")) / 1e3)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            sm = sorted(s for s, _ in self.samples)
+            reasons = sorted({r for _, rs in self.samples for r in rs})
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(sm),
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -88,7 +137,7 @@ class Clocks:
                     reasons.add(n)
         sm.sort()
         med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -306,7 +355,7 @@ def run_train(args, rank, world, dev, devw, windows_np, lib, seeded_state):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--windows", type=int, default=2, help="distinct synthetic windows cycled through")
@@ -546,6 +595,8 @@ def main():
                        if graph_mode else "eager op-by-op launches"},
             "e2e": {"value": total_scans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "hbm_kernels": hbm, "cpu_baseline": cpu}
+    if graph_mode:   # windows that left the graph path: static capacities exceeded / fp16 operand range flag raised
+        line["fallbacks"] = {"eager_reruns": sum(l.fallbacks for l in multi.lanes), "fp16_range": sum(l.range_fallbacks for l in multi.lanes)}
     if args.breakdown:
         line["breakdown_ms_per_step"] = {k: v["ms_total"] / min(args.steps, 4) for k, v in
                                          sorted(summ.items(), key=lambda kv: -kv[1]["ms_total"])}
