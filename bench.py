@@ -540,7 +540,7 @@ def main():
     summ = probe.summary()
     pk = peaks()
     traffic, traffic_note = None, None
-    tpath = os.path.join(REPO, "profiles", "r1_conv_tc_ncu_full.json")
+    tpath = os.path.join(REPO, "profiles", "r1_conv_tc_f16_192_ncu_full.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
