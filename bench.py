@@ -390,7 +390,7 @@ def main():
     lib = _lib.load()
 
     # inputs: every rank owns its windows (sharded by window); pinned host + device copies
-    windows_np = make_windows(args.windows, 1000 + 100 * rank)
+    windows_np = make_windows(args.windows, 1000)   # the same synthetic windows on every rank: per-GPU work is identical (weak scaling)
     host = [[(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in w] for w in windows_np]
     devw = [[(p.to(dev), v.to(dev)) for p, v in w] for w in host]
     pts = [int(p.shape[0]) for p, _ in windows_np[0]]
@@ -589,7 +589,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "points_per_scan": pts, "frames": FRAMES, "vertices_per_level_after_4_frames": v_counts,
                        "l2": "256 MB flush between steps; per-step working set (im2row buffers) also exceeds L2",
-                       "parallelism": "windows sharded over %d rank(s), no data-path collective" % world,
+                       "parallelism": "windows sharded over %d rank(s) (every rank runs its own copy of the same synthetic windows), no data-path collective" % world,
                        "execution": ("CUDA-graph replay per frame kind, %d window(s) in flight per GPU (one stream each), "
                                      "static capacities %s, capacities respected: %s" % (lanes, runner.caps, capacity_ok))
                        if graph_mode else "eager op-by-op launches"},

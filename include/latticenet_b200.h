@@ -179,6 +179,14 @@ int ltn_aflow(const float* lv, const float* h, int V, int Vh, const int* v_dev, 
               const float* alpha, const float* beta, const float* bias, float pad_value, int use_center, float* out,
               float* weights_out, void* stream);
 
+/* ---- window assembly (dataloader/kitti_dataloader.py:129-171) ------------------------------------- */
+
+/* One SemanticKITTI scan from its wire format to the model's inputs on the device: raw [N,4] float32 = the .bin payload
+ * (x, y, z, reflectance); mats = HOST pointer to nr_mats (1..3) row-major 4x4 float64 matrices applied in order to
+ * [x,y,z,1] in float64 (velo -> world, world -> first scan of the window, -90 degrees about x), then divided by w and
+ * rounded to float32 (kitti_dataloader.py:160-171, DataTransformer.py:88-91); pos [N,3], val [N,1] = reflectance. */
+int ltn_assemble_scan(const float* raw, int N, const double* mats, int nr_mats, float* pos, float* val, void* stream);
+
 /* library version / build info */
 int ltn_version(void);
 /* dst[0] = a, dst[1] = b on the stream (per-frame point counts of the graph engine; values travel in the launch) */

@@ -1,0 +1,154 @@
+"""SemanticKITTI wire formats and device-side window assembly.
+
+Mirrors what the reference's loader and drivers do around the hot path, with the per-point arithmetic on the GPU:
+  * dataloader/kitti_dataloader.py:100-114  window indices; :205-256 calib / poses; :129-132 .bin; :281-291 .label
+  * :122,160-171  velo -> world -> first scan of the window -> -90 degrees about x  (csrc/ltn_io.cu, float64 on the device)
+  * test_ln.py:219-231  prediction files (decimal text, one uint32 label per line)
+  * train_ln.py:248-254 checkpoint names; test_ln.py:169-185 checkpoint loading protocol
+At several hundred windows per second and GPU the numpy loader (4 matmuls over 120k points per scan on one core) is
+the bottleneck; here a scan costs one pinned host read of the file bytes, one H2D copy and one kernel.
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def parse_calibration(filename):
+    """calib.txt -> {key: 4x4 float64} (kitti_dataloader.py:205-230)"""
+    calib = {}
+    with open(filename) as f:
+        for line in f:
+            if ":" not in line:
+                continue
+            key, content = line.strip().split(":")
+            v = [float(x) for x in content.strip().split()]
+            m = np.zeros((4, 4))
+            m[0, :], m[1, :], m[2, :], m[3, 3] = v[0:4], v[4:8], v[8:12], 1.0
+            calib[key] = m
+    return calib
+
+
+def parse_poses(filename, calibration):
+    """poses.txt -> list of velo-to-world 4x4 float64, Tr^-1 . P . Tr (kitti_dataloader.py:232-256)"""
+    Tr = calibration["Tr"]
+    Tr_inv = np.linalg.inv(Tr)
+    poses = []
+    with open(filename) as f:
+        for line in f:
+            v = [float(x) for x in line.strip().split()]
+            if len(v) < 12:
+                continue
+            m = np.zeros((4, 4))
+            m[0, :], m[1, :], m[2, :], m[3, 3] = v[0:4], v[4:8], v[8:12], 1.0
+            poses.append(np.matmul(Tr_inv, np.matmul(m, Tr)))
+    return poses
+
+
+def rotation_x(angle_deg):
+    """DataTransformer.py:19-31 rotation_matrix(angle, "x")"""
+    a = math.radians(angle_deg)
+    c, s = math.cos(a), math.sin(a)
+    T = np.identity(4)
+    T[1, 1], T[1, 2], T[2, 1], T[2, 2] = c, -s, s, c
+    return T
+
+
+def window_indices(index, frames, scope):
+    """scan numbers of the window ending at `index` (kitti_dataloader.py:100-114): clamped at the sequence start"""
+    return np.maximum((np.arange(frames) - (frames - 1)) * scope + index, 0)
+
+
+def remap_lut(learning_map):
+    """learning_map {raw label: class} -> lookup table (kitti_dataloader.py:42-47, including its +100 slack)"""
+    lut = np.zeros((max(learning_map.keys()) + 100), dtype=np.int32)
+    lut[list(learning_map.keys())] = list(learning_map.values())
+    return lut
+
+
+def load_labels(path, lut):
+    """.label: uint32 per point, lower 16 bits = label, upper 16 = instance id (kitti_dataloader.py:281-291)"""
+    raw = np.fromfile(path, dtype=np.uint32)
+    return lut[(raw & 0xFFFF).astype(np.int64)]
+
+
+def write_prediction(path, labels):
+    """what test_ln.py:219-231 leaves on disk: one decimal uint32 label per line (remap_semantic_labels.py reads it with
+    np.fromfile(..., dtype=np.uint32, sep="\\n"))"""
+    arr = torch.as_tensor(labels).reshape(-1).to("cpu").numpy().astype(np.uint32)
+    with open(path, "w") as f:
+        f.write("".join("%d\n" % int(x) for x in arr))
+
+
+def read_prediction(path):
+    return np.fromfile(path, dtype=np.uint32, sep="\n")
+
+
+def checkpoint_name(date_time, include_moving_classes, dataset_name, values_mode, sigma_0, rnn_modules, accumulate_clouds,
+                    frames_per_seq, cloud_scope, epoch):
+    """train_ln.py:248-249"""
+    return "{}_{}_{}_{}_sigma{}_type{}_frames{}_scope{}_epoch{}".format(
+        date_time, "multi" if include_moving_classes is True else "single", "Kitti" if dataset_name == "semantickitti" else "Paris",
+        "Ref" if values_mode == "reflectance" else "xyz", str(sigma_0)[0:3],
+        "-".join(rnn_modules) if not accumulate_clouds else "ACCUM", frames_per_seq, cloud_scope, epoch)
+
+
+class KittiSequence:
+    """One sequence directory (sequences/XX with velodyne/, labels/, calib.txt, poses.txt) as a source of windows."""
+
+    def __init__(self, data_dir, seq, frames=4, scope=3, learning_map=None, device=None):
+        self.dir = os.path.join(data_dir, "sequences", "%02d" % int(seq))
+        self.frames, self.scope = frames, scope
+        self.poses = parse_poses(os.path.join(self.dir, "poses.txt"), parse_calibration(os.path.join(self.dir, "calib.txt")))
+        self.lut = remap_lut(learning_map) if learning_map is not None else None
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self._rx = rotation_x(-90.0)
+
+    def scan_path(self, idx):
+        return os.path.join(self.dir, "velodyne", "%06d.bin" % int(idx))
+
+    def matrices(self, idx, first_idx):
+        """the three float64 matrices of kitti_dataloader.py:160-167, in application order"""
+        return np.ascontiguousarray(np.stack([self.poses[int(idx)], np.linalg.inv(self.poses[int(first_idx)]), self._rx]))
+
+    def read_raw(self, idx):
+        """the .bin payload as a pinned host tensor [N,4] float32 (no per-point work on the host)"""
+        raw = np.fromfile(self.scan_path(idx), dtype=np.float32).reshape(-1, 4)
+        return torch.from_numpy(raw).pin_memory()
+
+    def labels(self, idx):
+        if self.lut is None:
+            return None
+        return torch.from_numpy(load_labels(os.path.join(self.dir, "labels", "%06d.label" % int(idx)), self.lut).astype(np.int64))
+
+    def window(self, index, with_labels=False):
+        """-> [(positions [N,3], values [N,1])] on the device (+ labels of the last frame): the model's inputs for the window
+        ending at scan `index`, every frame expressed in the first frame's coordinates (kitti_dataloader.py:119-171)"""
+        _lib.require_cuda()
+        idxs = window_indices(index, self.frames, self.scope)
+        out = []
+        for idx in idxs:
+            raw = self.read_raw(idx).to(self.device, non_blocking=True)
+            out.append(assemble_scan(raw, self.matrices(idx, idxs[0])))
+        if with_labels:
+            return out, self.labels(idxs[-1])
+        return out
+
+
+def assemble_scan(raw_dev, mats):
+    """raw_dev [N,4] float32 on the device, mats [k,4,4] float64 (host) applied in order -> (positions [N,3], values [N,1])"""
+    if not raw_dev.is_cuda:
+        raise RuntimeError("assemble_scan runs on the GPU; there is no CPU fallback")
+    raw_dev = raw_dev.contiguous()
+    n = raw_dev.shape[0]
+    pos = torch.empty(n, 3, dtype=torch.float32, device=raw_dev.device)
+    val = torch.empty(n, 1, dtype=torch.float32, device=raw_dev.device)
+    m = np.ascontiguousarray(np.asarray(mats, dtype=np.float64).reshape(-1, 16))
+    rc = _lib.load().ltn_assemble_scan(_lib.ptr(raw_dev), n, m.ctypes.data_as(ctypes.c_void_p), int(m.shape[0]), _lib.ptr(pos),
+                                       _lib.ptr(val), _lib.stream())
+    _lib.check(rc, "ltn_assemble_scan")
+    return pos, val
