@@ -362,7 +362,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="add a per-entry-point time breakdown (extra untimed pass)")
     ap.add_argument("--eager", action="store_true", help="eager per-op launches instead of CUDA-graph replay")
-    ap.add_argument("--lanes", type=int, default=3, help="independent windows in flight per GPU (one CUDA stream each)")
+    ap.add_argument("--lanes", type=int, default=4, help="independent windows in flight per GPU (one CUDA stream each)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer = BASELINE config 3 (headline); train = config 4 (BPTT + AdamW + NCCL gradient all-reduce)")
     args = ap.parse_args()
