@@ -45,7 +45,8 @@ constexpr int kGroups = 2;         // producer warpgroups (round-robin k-blocks)
 constexpr int kGroupThreads = 128;
 constexpr int kMmaWarp = 4 * kGroups, kTmaWarp = 4 * kGroups + 1;
 constexpr int kThreads = 32 * (4 * kGroups + 2);   // producer/epilogue warps + MMA warp + TMA warp
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 4;    // A ring (tensor-memory columns / shared memory)
+constexpr int kMaxStagesB = 8;   // weight ring: with A in tensor memory the shared memory is all its own
 
 // TMA: 2-D tile global -> swizzled shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -206,16 +207,29 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, ConvParams p) {
     constexpr int KB = F16 ? 64 : kBlockK;          // K elements per k-block
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 1];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2 * kMaxStagesB + 1];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_affine[2 * 256];
     __shared__ float s_colsum[2 * 256];
     __shared__ int s_nbr[LTN_FEXT * kBlockM];   // [slot][tile row]: source vertex of every tap of the tile, -1 = absent
 
     if (threadIdx.x == 0) trace_stamp(p, 0);   // entry
+    const int row0 = blockIdx.x * kBlockM;
+    // The tile's slice of the neighbour table ([128, S] ints, contiguous in global memory) is fetched ONCE, coalesced, and
+    // kept slot-major in shared memory: a slot change in the gather loop then costs a shared-memory read instead of a
+    // dependent global load + warp shuffles in front of every row fetch.  The loads are issued FIRST, bounded by the host
+    // capacity only, so their latency overlaps the device-side row counts read next (the masks are applied at the store).
+    constexpr int kNbrPerThread = (LTN_FEXT * kBlockM + kThreads - 1) / kThreads;
+    int nbr_pref[kNbrPerThread];
+#pragma unroll
+    for (int q = 0; q < kNbrPerThread; ++q) {
+        const int i = (int)threadIdx.x + q * kThreads;
+        const int r = i / p.S;
+        nbr_pref[q] = -1;
+        if (i < kBlockM * p.S && row0 + r < p.Vq) nbr_pref[q] = p.nbr ? __ldg(p.nbr + (size_t)row0 * p.S + i) : row0 + r;
+    }
     const int Vq = p.vq_dev ? min(p.Vq, __ldg(p.vq_dev)) : p.Vq;
     const int Vx = p.vx_dev ? min(p.Vx, __ldg(p.vx_dev)) : p.Vx;
-    const int row0 = blockIdx.x * kBlockM;
     const int CL = p.cluster;
     // uniform per CLUSTER, before any barrier / TMEM allocation: a CTA without rows still takes part in its
     // cluster's weight multicast when a sibling has rows
@@ -241,8 +255,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
     uint8_t* smem_b = smem + (ATMEM ? 0 : (size_t)SA * a_stage);   // ATMEM: the A ring lives in tensor memory
 
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]);
-    const uint32_t bar_fullb = smem_u32(&bars[2 * kMaxStages]), bar_emptyb = smem_u32(&bars[3 * kMaxStages]);
-    const uint32_t bar_acc = smem_u32(&bars[4 * kMaxStages]);
+    const uint32_t bar_fullb = smem_u32(&bars[2 * kMaxStages]), bar_emptyb = smem_u32(&bars[2 * kMaxStages + kMaxStagesB]);
+    const uint32_t bar_acc = smem_u32(&bars[2 * kMaxStages + 2 * kMaxStagesB]);
     // tensor memory: accumulator columns [0, Nmma); ATMEM: A ring behind it, 64 columns per stage (hi | lo)
     const uint32_t a_col0 = ((uint32_t)Nmma + 31u) & ~31u;
     uint32_t tmem_cols = 32;
@@ -253,12 +267,29 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
             mbar_init(bar_full + 8 * s, kGroupThreads / 32);   // one arrive per gather warp of the group that owns the k-block
             mbar_init(bar_empty + 8 * s, 1);
         }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // The TMA lane owns the weight ring's barriers: it initialises them and, when no cluster sibling has to be waited
+    // for, streams the first SB weight stages right away -- the TMA round trip (~1 us) then runs under the rest of the
+    // set-up instead of after the block barrier.
+    int tma_kb0 = 0;
+    if (warp == kTmaWarp && lane == 0) {
         for (int s = 0; s < SB; ++s) {
             mbar_init(bar_fullb + 8 * s, 1);                   // the TMA thread's expect_tx arrive (+ the bytes of all CL slices)
             mbar_init(bar_emptyb + 8 * s, CL);                 // every CTA of the cluster has finished reading the stage
         }
-        mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (CL == 1) {
+            const uint32_t tx = (PASSES == 3 ? 2u : 1u) * b_bytes;
+            tma_kb0 = min(SB, num_kb);
+            for (int kb = 0; kb < tma_kb0; ++kb) {
+                const uint32_t bb = smem_u32(smem_b + (size_t)kb * b_stage);
+                mbar_arrive_expect_tx(bar_fullb + 8 * kb, tx);
+                tma_load_2d(bb, &map_hi, bar_fullb + 8 * kb, kb * KB, n0);
+                if (PASSES == 3) tma_load_2d(bb + b_bytes, &map_lo, bar_fullb + 8 * kb, kb * KB, n0);
+            }
+        }
     }
     if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols));
@@ -288,18 +319,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
     }
     if (p.out_sums)
         for (int c = tid; c < 2 * 256; c += kThreads) s_colsum[c] = 0.f;
-    // The tile's slice of the neighbour table ([128, S] ints, contiguous in global memory) is fetched ONCE, coalesced,
-    // and kept slot-major in shared memory: a slot change in the gather loop then costs a shared-memory read instead
-    // of a dependent global load + warp shuffles in front of every row fetch.
-    for (int i = tid; i < kBlockM * p.S; i += kThreads) {
-        const int r = i / p.S, sl = i - r * p.S;
-        const int v = row0 + r;
-        int sv = -1;
-        if (v < Vq) {
-            sv = p.nbr ? __ldg(p.nbr + (size_t)row0 * p.S + i) : v;
-            if (sv >= Vx) sv = -1;
+#pragma unroll
+    for (int q = 0; q < kNbrPerThread; ++q) {
+        const int i = tid + q * kThreads;
+        if (i < kBlockM * p.S) {
+            const int r = i / p.S, sl = i - r * p.S;
+            int sv = nbr_pref[q];
+            if (row0 + r >= Vq || sv >= Vx) sv = -1;
+            s_nbr[sl * kBlockM + r] = sv;
         }
-        s_nbr[sl * kBlockM + r] = sv;
     }
     tc_fence_before();
     __syncthreads();
@@ -703,9 +731,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         // ===================== TMA warp: stream the pre-split weight tiles =====================
         if (lane == 0) {
             const uint32_t tx = (PASSES == 3 ? 2u : 1u) * b_bytes;
-            int sb = 0;
-            uint32_t pb = 1;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            // stages [0, tma_kb0) were issued during the set-up (first lap of the ring: nothing to wait for)
+            int sb = tma_kb0 == SB ? 0 : tma_kb0;
+            uint32_t pb = tma_kb0 == SB ? 0u : 1u;
+            for (int kb = tma_kb0; kb < num_kb; ++kb) {
                 mbar_wait(bar_emptyb + 8 * sb, pb);
                 const uint32_t bb = smem_u32(smem_b + (size_t)sb * b_stage);
                 mbar_arrive_expect_tx(bar_fullb + 8 * sb, tx);   // the whole stage: own slice + the siblings' multicasts
@@ -880,8 +909,10 @@ int conv_launch(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
         sa = (512 - acc_cols) / 64;
         if (sa > kMaxStages) sa = kMaxStages;
         if (sa < 2) return -3;
+        static const int sb_cap = []() { const char* e = getenv("LTN_CONV_SB"); return e && atoi(e) >= 2 ? atoi(e) : 4; }();
         sb = (int)(budget / b_stage);
-        if (sb > kMaxStages) sb = kMaxStages;
+        if (sb > kMaxStagesB) sb = kMaxStagesB;
+        if (sb > sb_cap) sb = sb_cap;   // measured: 2 / 3 / 4 / 8 stages -> see DESIGN.md (a shallower ring leaves more L1 to the gather)
         if (sb < 2) return -3;
         smem = sb * b_stage;
         if (smem < 12 * 4096) smem = 12 * 4096;   // the epilogue turns each warp's 32 x 32 block around in 4 KB of this region
