@@ -158,12 +158,13 @@ int ltn_pointnet(const float* rows, int width, const int* idx, int R, const int*
                  unsigned long long* packed, const double* vert_acc, int min_rows, float* out, void* stream);
 
 /* The same with the 32 -> 64 layer on the tensor cores: fp16 hi/lo operands (three passes, fp32-class results as in
- * ltn_conv_tc_f16), activations staged as relu(h2) * 2^a_log2 straight into tensor memory.  *flag (int32) is OR-ed
- * with 1 when an activation leaves the fp16 range: the caller then redoes the work with ltn_pointnet. */
-int ltn_pointnet_tc(const float* rows, int width, const int* idx, int R, const int* r_dev, const float* w1, const float* b1,
-                    const float* w2, const float* b2, const float* w3, const float* b3, int V, const int* v_dev,
-                    unsigned long long* packed, const double* vert_acc, int min_rows, float* out, int a_log2, int* flag,
-                    void* stream);
+ * ltn_conv_tc_f16), activations staged as relu(h2) * 2^a_log2 straight into tensor memory.  w12_host: HOST pointer to
+ * layers 1-2 in nn.Linear layout, concatenated (w1 [16,4], b1 [16], w2 [32,16], b2 [32] = 624 floats): they travel as
+ * kernel parameters and are read as constant-bank operands.  *flag (int32) is OR-ed with 1 when an activation leaves
+ * the fp16 range: the caller then redoes the work with ltn_pointnet. */
+int ltn_pointnet_tc(const float* rows, int width, const int* idx, int R, const int* r_dev, const float* w12_host,
+                    const float* w3, const float* b3, int V, const int* v_dev, unsigned long long* packed,
+                    const double* vert_acc, int min_rows, float* out, int a_log2, int* flag, void* stream);
 
 /* ---- temporal fusion (seq_lattice/lattice_modules.py:17-339) ------------------------------------ */
 

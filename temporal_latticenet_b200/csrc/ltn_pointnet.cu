@@ -35,6 +35,13 @@ struct MlpWeights {
     const float *w1, *b1, *w2, *b2, *w3, *b3;  // nn.Linear layout [out, in]
 };
 
+// Layers 1-2 BY VALUE (2.5 KB of kernel parameters = constant bank): every FFMA of the fully unrolled loops takes its
+// weight as a constant-bank operand, so the 576 multiply-adds per row cost no shared-memory reads at all (they were a
+// third of the shared-memory wavefronts that bound k_pointnet_tc).  [in][out] order, as the inner loops walk it.
+struct Mlp12 {
+    float w1[D0 * D1], b1[D1], w2[D1 * D2], b2[D2];
+};
+
 constexpr int kHash = 512;   // block-local vertex table (256 rows -> at most 256 distinct vertices)
 constexpr int kSlots = 128;  // distinct vertices per block resolved in shared memory (typical: 30-60); the rest go straight to L2
 constexpr int kPitch = kSlots + 1;
@@ -202,9 +209,10 @@ k_pointnet_mlp_max(const float* __restrict__ rows, int width, const int* __restr
 // *flag is OR-ed with 1 when a staged activation leaves the fp16 range (the caller then uses k_pointnet_mlp_max).
 __global__ void __launch_bounds__(kThreads, 2)
 k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__ idx, int R, const int* __restrict__ r_dev,
-              MlpWeights w, int V, const int* __restrict__ v_dev, unsigned long long* packed, float a_mul, int* flag) {
+              MlpWeights w, const __grid_constant__ Mlp12 M, int V, const int* __restrict__ v_dev, unsigned long long* packed,
+              float a_mul, int* flag) {
     __shared__ __align__(1024) uint8_t s_w3[2 * 64 * 128];   // [hi | lo] 64 output rows x 128 bytes, SWIZZLE_128B
-    __shared__ __align__(16) float s1[D0 * D1], s2[D1 * D2], sb1[D1], sb2[D2], sb3[D3];
+    __shared__ __align__(16) float sb3[D3];
     __shared__ int h_key[kHash], h_slot[kHash], slot_id[kThreads], nslots;
     extern __shared__ uint32_t t_dyn[];   // all 64 channels at once: 7 block barriers per 256 rows instead of 20
     uint32_t* const t_val = t_dyn;
@@ -214,10 +222,6 @@ k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__
     __shared__ float s_wmax[kThreads / 32];
     __shared__ float s_wmul;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < D0 * D1; i += kThreads) s1[(i % D0) * D1 + i / D0] = __ldg(w.w1 + i);
-    for (int i = tid; i < D1 * D2; i += kThreads) s2[(i % D1) * D2 + i / D1] = __ldg(w.w2 + i);
-    for (int i = tid; i < D1; i += kThreads) sb1[i] = __ldg(w.b1 + i);
-    for (int i = tid; i < D2; i += kThreads) sb2[i] = __ldg(w.b2 + i);
     for (int i = tid; i < D3; i += kThreads) sb3[i] = __ldg(w.b3 + i);
     // ---- W3 [64, 32] -> fp16 hi / lo, K-major, 128-byte swizzle; thread t: output row t / 4, 8 inputs (one 16-byte chunk)
     float wv[8];
@@ -301,22 +305,18 @@ k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__
             }
             float h1[D1], h2[D2];
 #pragma unroll
-            for (int o = 0; o < D1; ++o) h1[o] = sb1[o];
+            for (int o = 0; o < D1; ++o) h1[o] = M.b1[o];
 #pragma unroll
             for (int i = 0; i < D0; ++i)
 #pragma unroll
-                for (int o = 0; o < D1; ++o) h1[o] = fmaf(x[i], s1[i * D1 + o], h1[o]);
+                for (int o = 0; o < D1; ++o) h1[o] = fmaf(x[i], M.w1[i * D1 + o], h1[o]);
 #pragma unroll
-            for (int o = 0; o < D2; ++o) h2[o] = sb2[o];
+            for (int o = 0; o < D2; ++o) h2[o] = M.b2[o];
 #pragma unroll
             for (int i = 0; i < D1; ++i) {
                 const float a = fmaxf(h1[i], 0.f);
 #pragma unroll
-                for (int o = 0; o < D2; o += 4) {
-                    const float4 ww = *reinterpret_cast<const float4*>(s2 + i * D2 + o);
-                    h2[o] = fmaf(a, ww.x, h2[o]); h2[o + 1] = fmaf(a, ww.y, h2[o + 1]);
-                    h2[o + 2] = fmaf(a, ww.z, h2[o + 2]); h2[o + 3] = fmaf(a, ww.w, h2[o + 3]);
-                }
+                for (int o = 0; o < D2; ++o) h2[o] = fmaf(a, M.w2[i * D2 + o], h2[o]);   // constant-bank operand: no LDS
             }
             uint32_t hi[16], lo[16];
 #pragma unroll
@@ -486,23 +486,30 @@ int ltn_pointnet(const float* rows, int width, const int* idx, int R, const int*
 // ltn_pointnet with the 32 -> 64 layer on the tensor cores (fp16 hi/lo operands, fp32-parity three passes; activations
 // staged as relu(h2) * 2^a_log2).  *flag (int32) is OR-ed with 1 when an activation leaves the fp16 range: the result is
 // then unusable and the caller redoes the frame with ltn_pointnet.
-int ltn_pointnet_tc(const float* rows, int width, const int* idx, int R, const int* r_dev, const float* w1, const float* b1,
-                    const float* w2, const float* b2, const float* w3, const float* b3, int V, const int* v_dev,
-                    unsigned long long* packed, const double* vert_acc, int min_rows, float* out, int a_log2, int* flag,
-                    void* stream) {
+int ltn_pointnet_tc(const float* rows, int width, const int* idx, int R, const int* r_dev, const float* w12_host,
+                    const float* w3, const float* b3, int V, const int* v_dev, unsigned long long* packed,
+                    const double* vert_acc, int min_rows, float* out, int a_log2, int* flag, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (V <= 0) return 0;
-    if (width != D0 + 1 || !flag) return -2;
+    if (width != D0 + 1 || !flag || !w12_host) return -2;
+    Mlp12 M;
+    // host copy of layers 1-2 in nn.Linear layout: w1 [16,4], b1 [16], w2 [32,16], b2 [32] -> [in][out]
+    for (int o = 0; o < D1; ++o)
+        for (int i = 0; i < D0; ++i) M.w1[i * D1 + o] = w12_host[o * D0 + i];
+    for (int o = 0; o < D1; ++o) M.b1[o] = w12_host[D0 * D1 + o];
+    for (int o = 0; o < D2; ++o)
+        for (int i = 0; i < D1; ++i) M.w2[i * D2 + o] = w12_host[D0 * D1 + D1 + o * D1 + i];
+    for (int o = 0; o < D2; ++o) M.b2[o] = w12_host[D0 * D1 + D1 + D1 * D2 + o];
     cudaError_t e = cudaMemsetAsync(packed, 0, sizeof(unsigned long long) * (size_t)V * D3, st);
     if (e != cudaSuccess) return (int)e;
     if (R > 0) {
-        MlpWeights w{w1, b1, w2, b2, w3, b3};
+        MlpWeights w{nullptr, nullptr, nullptr, nullptr, w3, b3};
         int blocks = (R + kThreads - 1) / kThreads;
         if (blocks > 148 * 2) blocks = 148 * 2;   // persistent: two blocks per SM (256 tensor-memory columns each)
         const size_t dyn = sizeof(uint32_t) * 2 * D3 * kPitch;
         e = cudaFuncSetAttribute(k_pointnet_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return (int)e;
-        k_pointnet_tc<<<blocks, kThreads, dyn, st>>>(rows, width, idx, R, r_dev, w, V, v_dev, packed, ldexpf(1.0f, a_log2), flag);
+        k_pointnet_tc<<<blocks, kThreads, dyn, st>>>(rows, width, idx, R, r_dev, w, M, V, v_dev, packed, ldexpf(1.0f, a_log2), flag);
         LTN_CHECK_LAUNCH();
     }
     long long total = (long long)V * D3;

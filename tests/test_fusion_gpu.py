@@ -183,7 +183,9 @@ def test_pointnet_front_end_matches_float64(dev, kernel):
         rc = lib.ltn_pointnet(P(rows), 5, P(idx), R, None, *[P(t) for t in d], V, None, P(packed), P(ls._vert_acc), 4, P(out), _lib.stream())
     else:
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        rc = lib.ltn_pointnet_tc(P(rows), 5, P(idx), R, None, *[P(t) for t in d], V, None, P(packed), P(ls._vert_acc), 4, P(out), 5, P(flag),
+        w12 = np.ascontiguousarray(np.concatenate([t.numpy().reshape(-1) for t in (w1, b1, w2, b2)]).astype(np.float32))
+        import ctypes
+        rc = lib.ltn_pointnet_tc(P(rows), 5, P(idx), R, None, w12.ctypes.data_as(ctypes.c_void_p), P(d[4]), P(d[5]), V, None, P(packed), P(ls._vert_acc), 4, P(out), 5, P(flag),
                                  _lib.stream())
         assert int(flag.item()) == 0
     assert rc == 0

@@ -19,8 +19,10 @@ def _ulp_check(got, want):
     assert got.shape == want.shape and got.dtype == np.float32
     same = got == want
     assert same.mean() >= 0.999, same.mean()
-    ulp = np.spacing(np.abs(want).astype(np.float32))
-    assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= ulp.astype(np.float64))
+    # one float32 ulp, with an absolute floor for coordinates that cancel to ~0 (float64 rounding of the 4-term dot
+    # products, ~1e-14, is then larger than the ulp of the tiny result)
+    ulp = np.maximum(np.spacing(np.abs(want).astype(np.float32)).astype(np.float64), 1e-9)
+    assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= ulp)
 
 
 def test_window_from_wire_format_matches_reference_loader():
@@ -54,3 +56,65 @@ def test_full_size_scan_transform_and_round_trip():
     # empty scan
     p0, v0 = P.assemble_scan(torch.zeros(0, 4, device="cuda"), mats)
     assert p0.shape == (0, 3) and v0.shape == (0, 1)
+
+
+def _write_sequence(root, frames_yup):
+    """a SemanticKITTI-style sequence 08 on disk whose scans, once assembled, reproduce the given y-up frames (up to the
+    float32 rounding of the .bin payload): moving sensor, real calibration matrix"""
+    from temporal_latticenet_b200 import kitti_io as P
+    sdir = os.path.join(root, "sequences", "08")
+    os.makedirs(os.path.join(sdir, "velodyne"))
+    Tr = np.array([[4.276802385584e-04, -9.999672484946e-01, -8.084491683471e-03, -1.198459927713e-02],
+                   [-7.210626507497e-03, 8.081198471645e-03, -9.999413164504e-01, -5.403984729748e-02],
+                   [9.999738645903e-01, 4.859485810390e-04, -7.206933692422e-03, -2.921968648686e-01]])
+    with open(os.path.join(sdir, "calib.txt"), "w") as f:
+        f.write("Tr: %s\n" % " ".join("%.12e" % x for x in Tr.reshape(-1)))
+    cams = []
+    for i in range(len(frames_yup)):
+        yaw = 0.01 * i
+        cams.append(np.array([[np.cos(yaw), 0, np.sin(yaw), 0.02 * i], [0, 1, 0, 0.0], [-np.sin(yaw), 0, np.cos(yaw), 0.9 * i]]))
+    with open(os.path.join(sdir, "poses.txt"), "w") as f:
+        for c in cams:
+            f.write(" ".join("%.12e" % x for x in c.reshape(-1)) + "\n")
+    poses = P.parse_poses(os.path.join(sdir, "poses.txt"), P.parse_calibration(os.path.join(sdir, "calib.txt")))
+    for i, (pos, val) in enumerate(frames_yup):
+        M = P.rotation_x(-90) @ np.linalg.inv(poses[0]) @ poses[i]
+        hom = np.ones((4, pos.shape[0])); hom[:3] = pos.T.astype(np.float64)
+        raw = (np.linalg.inv(M) @ hom)[:3].T
+        np.concatenate([raw, val.astype(np.float64)], 1).astype(np.float32).tofile(os.path.join(sdir, "velodyne", "%06d.bin" % i))
+
+
+def test_sequence_files_to_prediction_files_end_to_end(tmp_path):
+    """SURVEY 8(f) ranks 1-3 together: .bin / poses / calib on disk -> device-side window assembly -> the window runner
+    (test_ln.py:149-231 loop shape) -> prediction file in the reference's on-disk format, against the CPU oracle fed with the
+    oracle-assembled window (same seeded weights)."""
+    from oracle import kitti_oracle as K
+    from oracle import window_oracle as WO
+    from temporal_latticenet_b200 import kitti_io as P
+    from temporal_latticenet_b200.runner import WindowRunner
+    from tests.helpers import CFG, seeded_state, small_window
+    dev = torch.device("cuda:0")
+    root = str(tmp_path)
+    _write_sequence(root, small_window(seed=21, frames=4, radius=8.0, max_points=4000))
+    seq = P.KittiSequence(root, 8, frames=4, scope=1, device=dev)
+    frames = seq.window(3)
+    runner = WindowRunner(CFG, 26, dev).materialise_parameters(frames, seeded_state)
+    logp = runner.infer_window_device(frames)
+    labels = logp.argmax(1)
+    out = os.path.join(root, "000003.label")
+    P.write_prediction(out, labels)
+    assert np.array_equal(P.read_prediction(out), labels.cpu().numpy().astype(np.uint32))
+    # oracle side: numpy-assembled window through the CPU window oracle
+    oframes = [(p, v) for p, v, _ in K.assemble_window(root, 8, 3, frames=4, scope=1)]
+    for (gp, gv), (op, ov) in zip(frames, oframes):
+        _ulp_check(gp.cpu().numpy(), op)
+        assert np.array_equal(gv.cpu().numpy(), ov)
+    orc = WO.OracleWindowRunner(CFG, 26).materialise_parameters(oframes)
+    want = orc.infer_window(oframes)
+    want = want.detach().cpu().numpy() if hasattr(want, "detach") else np.asarray(want)
+    got = logp.cpu().numpy()
+    assert got.shape == want.shape
+    finite = np.isfinite(want)
+    assert np.array_equal(finite, np.isfinite(got))
+    assert float(np.abs(got[finite] - want[finite]).max()) <= 2e-3 * max(1.0, float(np.abs(want[finite]).max()))
+    assert (got.argmax(1) == want.argmax(1)).mean() > 0.98

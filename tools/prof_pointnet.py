@@ -28,13 +28,16 @@ for _ in range(10):
                      P(packed), P(ls._vert_acc), 4, P(out), _lib.stream())
 e1.record(); torch.cuda.synchronize()
 print("ltn_pointnet (memset + mlp_max + decode): %.1f us per call" % (1e3 * e0.elapsed_time(e1) / 10))
+import ctypes, numpy as np
+w12 = np.ascontiguousarray(np.concatenate([t.cpu().numpy().reshape(-1) for t in (w1, b1, w2, b2)]).astype(np.float32))
+W12 = w12.ctypes.data_as(ctypes.c_void_p)
 flag = torch.zeros(1, dtype=torch.int32, device=dev)
 for _ in range(3):
-    lib.ltn_pointnet_tc(P(rows), rows.shape[1], P(idx), rows.shape[0], None, P(w1), P(b1), P(w2), P(b2), P(w3), P(b3), V, None,
+    lib.ltn_pointnet_tc(P(rows), rows.shape[1], P(idx), rows.shape[0], None, W12, P(w3), P(b3), V, None,
                         P(packed), P(ls._vert_acc), 4, P(out), 5, P(flag), _lib.stream())
 e0.record()
 for _ in range(10):
-    lib.ltn_pointnet_tc(P(rows), rows.shape[1], P(idx), rows.shape[0], None, P(w1), P(b1), P(w2), P(b2), P(w3), P(b3), V, None,
+    lib.ltn_pointnet_tc(P(rows), rows.shape[1], P(idx), rows.shape[0], None, W12, P(w3), P(b3), V, None,
                         P(packed), P(ls._vert_acc), 4, P(out), 5, P(flag), _lib.stream())
 e1.record(); torch.cuda.synchronize()
 print("ltn_pointnet_tc (memset + tc + decode): %.1f us per call, flag %d" % (1e3 * e0.elapsed_time(e1) / 10, int(flag.item())))
