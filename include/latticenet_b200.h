@@ -166,6 +166,10 @@ int ltn_pointnet_tc(const float* rows, int width, const int* idx, int R, const i
                     const float* w3, const float* b3, int V, const int* v_dev, unsigned long long* packed,
                     const double* vert_acc, int min_rows, float* out, int a_log2, int* flag, void* stream);
 
+/* phase tracing of ltn_pointnet_tc (NULL switches it off): 8 clock64 stamps of one tile of block 0 (loop top, operands in
+ * tensor memory, vertices numbered, accumulator read, block max done, arg-max done, flushed, next tile) + distinct vertices */
+int ltn_pointnet_trace(long long* buf);
+
 /* ---- temporal fusion (seq_lattice/lattice_modules.py:17-339) ------------------------------------ */
 
 /* GRUModule.forward pointwise stage (lattice_modules.py:58-63); rows >= Vh are the zero padding */

@@ -17,6 +17,7 @@
 #include "ltn_common.cuh"
 #include "ltn_tc.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace {
 
@@ -42,6 +43,8 @@ struct Mlp12 {
     float w1[D0 * D1], b1[D1], w2[D1 * D2], b2[D2];
 };
 
+long long* g_pn_trace = nullptr;
+constexpr int kPointnetTcThreads = 128;   // rows per block of k_pointnet_tc (measured); LTN_PN_THREADS=256 for the other form
 constexpr int kHash = 512;   // block-local vertex table (256 rows -> at most 256 distinct vertices)
 constexpr int kSlots = 128;  // distinct vertices per block resolved in shared memory (typical: 30-60); the rest go straight to L2
 constexpr int kPitch = kSlots + 1;
@@ -167,9 +170,12 @@ k_pointnet_mlp_max(const float* __restrict__ rows, int width, const int* __restr
             }
             __syncthreads();
             if (local) {
+                unsigned win = 0u;   // loads first, then atomics for the winners only (see k_pointnet_tc)
+#pragma unroll
+                for (int o = 0; o < 16; ++o) win |= (unsigned)(t_val[o * kPitch + lslot] == enc[o]) << o;
 #pragma unroll
                 for (int o = 0; o < 16; ++o)
-                    if (t_val[o * kPitch + lslot] == enc[o]) atomicMin(&t_row[o * kPitch + lslot], (uint32_t)row);   // smallest row wins ties
+                    if ((win >> o) & 1u) atomicMin(&t_row[o * kPitch + lslot], (uint32_t)row);   // smallest row wins ties
             }
             __syncthreads();
             // one 64-bit atomic per (distinct vertex, channel): value in the high word, ~row in the low word
@@ -207,14 +213,17 @@ k_pointnet_mlp_max(const float* __restrict__ rows, int width, const int* __restr
 //   * each thread reads its row of the accumulator back 16 columns at a time and feeds the same block-local
 //     segmented max as above.
 // *flag is OR-ed with 1 when a staged activation leaves the fp16 range (the caller then uses k_pointnet_mlp_max).
-__global__ void __launch_bounds__(kThreads, 2)
+template <int NT>   // threads = rows per block: 256 (two M = 128 tiles, 2 blocks / SM) or 128 (one tile, 4 blocks / SM)
+__global__ void __launch_bounds__(NT, NT == 128 ? 4 : 2)
 k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__ idx, int R, const int* __restrict__ r_dev,
               MlpWeights w, const __grid_constant__ Mlp12 M, int V, const int* __restrict__ v_dev, unsigned long long* packed,
-              float a_mul, int* flag) {
+              float a_mul, int* flag, long long* trace) {
     __shared__ __align__(1024) uint8_t s_w3[2 * 64 * 128];   // [hi | lo] 64 output rows x 128 bytes, SWIZZLE_128B
     __shared__ __align__(16) float sb3[D3];
+    constexpr int kThreads = NT, kTiles = NT / 128, kHash = 2 * NT, kSlots = NT / 2, kPitch = kSlots + 1;
+    constexpr int kTmemCols = NT;          // kTiles x (64 accumulator + 32 operand columns) rounded up to a power of two
     __shared__ int h_key[kHash], h_slot[kHash], slot_id[kThreads], nslots;
-    extern __shared__ uint32_t t_dyn[];   // all 64 channels at once: 7 block barriers per 256 rows instead of 20
+    extern __shared__ uint32_t t_dyn[];   // all 64 channels at once: 7 block barriers per tile instead of 20
     uint32_t* const t_val = t_dyn;
     uint32_t* const t_row = t_dyn + D3 * kPitch;
     __shared__ __align__(8) uint64_t bar_mma;
@@ -223,14 +232,14 @@ k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__
     __shared__ float s_wmul;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < D3; i += kThreads) sb3[i] = __ldg(w.b3 + i);
-    // ---- W3 [64, 32] -> fp16 hi / lo, K-major, 128-byte swizzle; thread t: output row t / 4, 8 inputs (one 16-byte chunk)
-    float wv[8];
+    // ---- W3 [64, 32] -> fp16 hi / lo, K-major, 128-byte swizzle; item t: output row t / 4, 8 inputs (one 16-byte chunk)
     {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(w.w3) + tid * 2), b = __ldg(reinterpret_cast<const float4*>(w.w3) + tid * 2 + 1);
-        wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w; wv[4] = b.x; wv[5] = b.y; wv[6] = b.z; wv[7] = b.w;
         float m = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(wv[i]));
+        for (int t = tid; t < 256; t += kThreads) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(w.w3) + t * 2), b = __ldg(reinterpret_cast<const float4*>(w.w3) + t * 2 + 1);
+            m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                               fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if (lane == 0) s_wmax[warp] = m;
@@ -240,7 +249,7 @@ k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     __syncthreads();
@@ -255,8 +264,10 @@ k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__
     }
     __syncthreads();
     const float w_mul = s_wmul;
-    {
-        const int n = tid >> 2, chunk = tid & 3;
+    for (int t = tid; t < 256; t += kThreads) {
+        const int n = t >> 2, chunk = t & 3;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w.w3) + t * 2), b = __ldg(reinterpret_cast<const float4*>(w.w3) + t * 2 + 1);
+        const float wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -278,14 +289,16 @@ k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t acc_col = (uint32_t)(warp >> 2) * 64u;          // accumulator of this thread's tile
-    const uint32_t a_col = 128u + (uint32_t)(warp >> 2) * 32u;     // its A operand: 16 columns hi, 16 columns lo
+    const uint32_t acc_col = (uint32_t)(warp >> 2) * 64u;                     // accumulator of this thread's tile
+    const uint32_t a_col = (uint32_t)kTiles * 64u + (uint32_t)(warp >> 2) * 32u;   // its A operand: 16 columns hi, 16 columns lo
     const float out_mul = 1.0f / (a_mul * w_mul);                  // both powers of two: exact
     if (r_dev) R = min(R, *r_dev);
     if (v_dev) V = min(V, *v_dev);
     float amax = 0.f;
     uint32_t phase = 0;
     for (int base = blockIdx.x * kThreads; base < R; base += gridDim.x * kThreads) {   // block-uniform trip count
+        long long tk[8];
+        tk[0] = clock64();
         const int row = base + tid;
         int id = -1;
         if (row < R) {
@@ -333,6 +346,7 @@ k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__
             tmem_st16(t_lane + a_col + 16u, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
+        tk[1] = clock64();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
@@ -341,8 +355,8 @@ k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__
             const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint64_t b_hi = make_desc(smem_u32(s_w3)), b_lo = make_desc(smem_u32(s_w3 + 64 * 128));
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                const uint32_t d = tmem_base + (uint32_t)m * 64u, a = tmem_base + 128u + (uint32_t)m * 32u;
+            for (int m = 0; m < kTiles; ++m) {
+                const uint32_t d = tmem_base + (uint32_t)m * 64u, a = tmem_base + (uint32_t)kTiles * 64u + (uint32_t)m * 32u;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {   // 16 fp16 of K = 8 columns of A = 32 bytes of the B row
                     const uint64_t adv = (uint64_t)((k * 32) >> 4);
@@ -356,7 +370,7 @@ k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__
         // ---- block-local numbering of the distinct vertices (overlaps the MMAs) -------------------------------
         int hpos = 0;
         if (id >= 0) {
-            hpos = (int)(((uint32_t)id * 2654435761u) >> 23) & (kHash - 1);
+            hpos = (int)(((uint32_t)id * 2654435761u) >> 22) & (kHash - 1);
             while (true) {
                 const int old = atomicCAS(&h_key[hpos], -1, id);
                 if (old == -1 || old == id) break;
@@ -374,6 +388,7 @@ k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__
         const int lslot = id >= 0 ? h_slot[hpos] : -1;
         const int ns = min(nslots, kSlots);
         const bool local = lslot >= 0 && lslot < kSlots;
+        tk[2] = clock64();
         for (int e = tid; e < ns * D3; e += kThreads) {
             const int at = (e & (D3 - 1)) * kPitch + (e >> 6);
             t_val[at] = 0u;
@@ -390,17 +405,32 @@ k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__
 #pragma unroll
             for (int o = 0; o < 16; ++o) enc[q * 16 + o] = ord_enc(fmaf(y[o], out_mul, sb3[q * 16 + o]));
         }
+        tk[3] = clock64();
         __syncthreads();
         if (local) {
 #pragma unroll
             for (int o = 0; o < D3; ++o) atomicMax(&t_val[o * kPitch + lslot], enc[o]);
         }
+        tk[4] = clock64();
         __syncthreads();
         if (local) {
+            // which channels did this row win?  Pure loads first (they pipeline; interleaved with the atomics every load
+            // waited for the previous atomic: 9.8k of the 18k cycles of a tile), then predicated atomics for the few winners
+            unsigned long long win = 0ull;
 #pragma unroll
-            for (int o = 0; o < D3; ++o)
-                if (t_val[o * kPitch + lslot] == enc[o]) atomicMin(&t_row[o * kPitch + lslot], (uint32_t)row);   // smallest row wins ties
+            for (int o = 0; o < D3; ++o) win |= (unsigned long long)(t_val[o * kPitch + lslot] == enc[o]) << o;
+            uint32_t my_row = (uint32_t)row;
+            asm volatile("" : "+r"(my_row));   // keep it in a register: rematerialising it from %tid.x costs an S2R per channel
+            const uint32_t tr = smem_u32(t_row + lslot);
+            const uint32_t w_lo = (uint32_t)win, w_hi = (uint32_t)(win >> 32);
+#pragma unroll
+            for (int o = 0; o < D3; ++o) {   // predicated reductions, no branch per channel; smallest row wins ties
+                const uint32_t bit = ((o < 32 ? w_lo : w_hi) >> (o & 31)) & 1u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.min.u32 [%0], %1;\n\t}"
+                             ::"r"(tr + (uint32_t)(o * kPitch * 4)), "r"(my_row), "r"(bit) : "memory");
+            }
         }
+        tk[5] = clock64();
         __syncthreads();
         // one fire-and-forget 64-bit reduction per (distinct vertex, channel): value in the high word, ~row in the low word;
         // 64 consecutive channels of a vertex = 512 contiguous bytes per two warps
@@ -416,14 +446,20 @@ k_pointnet_tc(const float* __restrict__ rows, int width, const int* __restrict__
 #pragma unroll
             for (int o = 0; o < D3; ++o) atomicMax(dst + o, ((unsigned long long)enc[o] << 32) | low);
         }
+        tk[6] = clock64();
         __syncthreads();
+        tk[7] = clock64();
+        if (trace && blockIdx.x == 0 && tid == 0 && base == (int)(gridDim.x * kThreads)) {   // second tile of block 0
+            for (int i = 0; i < 8; ++i) trace[i] = tk[i];
+            trace[8] = ns;
+        }
         tc_fence_before();   // the next tile's tcgen05.st / MMAs follow this tile's tcgen05.ld across the block barrier above
     }
     if (flag && !(amax < 65504.f)) atomicOr(flag, 1);
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
     }
 }
 
@@ -483,6 +519,12 @@ int ltn_pointnet(const float* rows, int width, const int* idx, int R, const int*
     return 0;
 }
 
+// debugging aid: clock64 stamps of the phases of one tile of k_pointnet_tc (block 0, second tile) -> buf[0..7], buf[8] = distinct vertices
+int ltn_pointnet_trace(long long* buf) {
+    g_pn_trace = buf;
+    return 0;
+}
+
 // ltn_pointnet with the 32 -> 64 layer on the tensor cores (fp16 hi/lo operands, fp32-parity three passes; activations
 // staged as relu(h2) * 2^a_log2).  *flag (int32) is OR-ed with 1 when an activation leaves the fp16 range: the result is
 // then unusable and the caller redoes the frame with ltn_pointnet.
@@ -506,10 +548,16 @@ int ltn_pointnet_tc(const float* rows, int width, const int* idx, int R, const i
         MlpWeights w{nullptr, nullptr, nullptr, nullptr, w3, b3};
         int blocks = (R + kThreads - 1) / kThreads;
         if (blocks > 148 * 2) blocks = 148 * 2;   // persistent: two blocks per SM (256 tensor-memory columns each)
-        const size_t dyn = sizeof(uint32_t) * 2 * D3 * kPitch;
-        e = cudaFuncSetAttribute(k_pointnet_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        static const int nt = []() { const char* e = getenv("LTN_PN_THREADS"); return e && atoi(e) == 256 ? 256 : kPointnetTcThreads; }();
+        blocks = (R + nt - 1) / nt;
+        const int per_sm = nt == 128 ? 4 : 2;
+        if (blocks > 148 * per_sm) blocks = 148 * per_sm;   // persistent
+        const size_t dyn = sizeof(uint32_t) * 2 * D3 * (nt / 2 + 1);
+        const void* fn = nt == 128 ? (const void*)k_pointnet_tc<128> : (const void*)k_pointnet_tc<256>;
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return (int)e;
-        k_pointnet_tc<<<blocks, kThreads, dyn, st>>>(rows, width, idx, R, r_dev, w, M, V, v_dev, packed, ldexpf(1.0f, a_log2), flag);
+        if (nt == 128) k_pointnet_tc<128><<<blocks, 128, dyn, st>>>(rows, width, idx, R, r_dev, w, M, V, v_dev, packed, ldexpf(1.0f, a_log2), flag, g_pn_trace);
+        else k_pointnet_tc<256><<<blocks, 256, dyn, st>>>(rows, width, idx, R, r_dev, w, M, V, v_dev, packed, ldexpf(1.0f, a_log2), flag, g_pn_trace);
         LTN_CHECK_LAUNCH();
     }
     long long total = (long long)V * D3;

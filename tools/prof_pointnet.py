@@ -41,3 +41,11 @@ for _ in range(10):
                         P(packed), P(ls._vert_acc), 4, P(out), 5, P(flag), _lib.stream())
 e1.record(); torch.cuda.synchronize()
 print("ltn_pointnet_tc (memset + tc + decode): %.1f us per call, flag %d" % (1e3 * e0.elapsed_time(e1) / 10, int(flag.item())))
+tr = torch.zeros(16, dtype=torch.int64, device=dev)
+lib.ltn_pointnet_trace(P(tr))
+lib.ltn_pointnet_tc(P(rows), rows.shape[1], P(idx), rows.shape[0], None, W12, P(w3), P(b3), V, None,
+                    P(packed), P(ls._vert_acc), 4, P(out), 5, P(flag), _lib.stream())
+lib.ltn_pointnet_trace(None)
+t = tr.cpu().numpy()
+names = ["load+MLP+tmem st", "sync, hash insert, compaction", "table init, MMA wait, tmem ld", "sync + atomicMax", "sync + atomicMin", "sync + flush", "sync"]
+print("one tile of k_pointnet_tc (cycles):", ", ".join("%s %d" % (n, t[i + 1] - t[i]) for i, n in enumerate(names)), "| total", t[7] - t[0], "| distinct vertices", t[8])
