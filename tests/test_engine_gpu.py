@@ -211,3 +211,51 @@ def test_graph_runner_single_accumulated_frame(tmp_path):
         got = graph.infer_window_device(fd).cpu().numpy()
         assert graph.counts_ok() and got.shape == want.shape == (w[0][0].shape[0], 26)
         assert float(np.abs(got - want).max()) / float(np.abs(want).max()) < 1e-4
+
+
+def test_fp16_range_flag_reruns_the_window_with_tf32_operands():
+    """The fp16 hi/lo operand form is only a fast path: when an activation leaves the fp16 range the kernels raise the
+    device-side flag, and every runner redoes the window with the tf32 operands.  Reflectance values of 1e7 push the
+    PointNet activations far beyond 65504 / 2^5; the results must equal those of a runner that uses tf32 from the start,
+    on the eager path, on the graph path and through submit / collect."""
+    from temporal_latticenet_b200.engine import GraphWindowRunner, MultiWindowRunner
+    from temporal_latticenet_b200.runner import WindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    dev = torch.device("cuda:0")
+    normal = _window(31, n=4000)
+    huge = [(p, (v * 1e7).astype(np.float32)) for p, v in _window(32, n=4000)]
+    to_dev = lambda w: [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]  # noqa: E731
+    safe = WindowRunner(CFG, 26, dev, operands="tf32").materialise_parameters(to_dev(normal), seeded_state)
+    fast = WindowRunner(CFG, 26, dev).materialise_parameters(to_dev(normal), seeded_state)
+    assert fast.operands == "f16"
+    # a normal window: no re-run, fp16 and tf32 operands agree to fp32 accuracy
+    a, b = fast.infer_window_device(to_dev(normal)).cpu().numpy(), safe.infer_window_device(to_dev(normal)).cpu().numpy()
+    assert fast.range_fallbacks == 0
+    assert float(np.abs(a - b).max()) <= 1e-4 * float(np.abs(b).max())
+    # the out-of-range window: flagged, re-run, same answer as tf32 from the start (same kernels -> tight tolerance)
+    want = safe.infer_window_device(to_dev(huge)).cpu().numpy()
+    got = fast.infer_window_device(to_dev(huge)).cpu().numpy()
+    assert fast.range_fallbacks == 1 and int(fast.range_flag.item()) == 0
+    fin = np.isfinite(want)
+    assert np.array_equal(fin, np.isfinite(got))
+    assert float(np.abs(got[fin] - want[fin]).max()) <= 1e-4 * max(1.0, float(np.abs(want[fin]).max()))
+    # graph path: counts_ok() reports the raised flag, infer_window() re-runs eagerly
+    graph = GraphWindowRunner(CFG, 26, dev).materialise_parameters(to_dev(normal), seeded_state)
+    graph.plan(to_dev(normal))
+    graph.capture(to_dev(normal))
+    graph.infer_window_device(to_dev(huge))
+    assert not graph.counts_ok() and graph.range_fallbacks == 1
+    host = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in huge]
+    labels = graph.infer_window(host).clone()
+    assert (labels.numpy() == want.argmax(1)).mean() > 0.999
+    # and a normal window afterwards runs on the graphs again without a re-run
+    before = graph.fallbacks
+    graph.infer_window([(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in normal])
+    assert graph.fallbacks == before
+    # several windows in flight: only the lane with the out-of-range window re-runs
+    multi = MultiWindowRunner(CFG, 26, dev, lanes=2).prepare(to_dev(normal), seeded_state)
+    hn = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in normal]
+    out = multi.collect(multi.submit([hn, host]))
+    assert (out[1].numpy() == want.argmax(1)).mean() > 0.999
+    assert (out[0].numpy() == b.argmax(1)).mean() > 0.999
+    assert [l.fallbacks for l in multi.lanes] == [0, 1]
