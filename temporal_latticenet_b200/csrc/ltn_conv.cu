@@ -10,20 +10,26 @@
 // models.py:353,398), GnRelu1x1 / Conv1x1 / nn.Linear and the GRU/LSTM gate GEMMs (S = 1, nbr = NULL).
 //
 // Blackwell mapping
-//  * tcgen05.mma.cta_group::1.kind::tf32, M = 128 vertices per CTA, N = up to 256 output channels so the
-//    A rows are gathered exactly once; fp32 accumulator lives in TMEM (N columns x 128 lanes).
-//  * fp32 parity: every fp32 operand is split x = hi + lo (hi = round-to-tf32, lo = x - hi exactly) and
-//    the product is issued as hi*hi + lo*hi + hi*lo -- three tensor-core passes, ~2^-21 relative error per
-//    product, i.e. fp32-class results (the reference ran these GEMMs in fp32 / TF32 cuBLAS).
-//    PASSES = 1 is the single-pass TF32 variant (reported separately, never the default).
-//  * operands are staged K-major in 128-byte-swizzled shared memory (the UMMA canonical layout).
-//    A (gathered, data dependent): two producer warpgroups take alternate k-blocks; one thread per tile
-//    row loads 128 contiguous bytes of one vertex row (a whole cache line, L2-resident), applies the
-//    folded GroupNorm+ReLU, splits hi/lo and writes 16-byte chunks at chunk ^ (row & 7).
-//    B (weights, dense): pre-split hi/lo copies streamed by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B)
-//    from a dedicated warp, completing on the same mbarrier as the A producers.
-//    A multi-stage mbarrier ring decouples both from the single MMA-issuing thread; tcgen05.commit
-//    releases stages and finally hands the accumulator to the epilogue.
+//  * tcgen05.mma.cta_group::1, M = 128 vertices per CTA, N = up to 256 output channels so the A rows are gathered
+//    exactly once; fp32 accumulator lives in TMEM (N columns x 128 lanes).
+//  * fp32 parity: every fp32 operand is split x = hi + lo and the product is issued as hi*hi + lo*hi + hi*lo -- three
+//    tensor-core passes, ~2^-21 relative error per product, i.e. fp32-class results (the reference ran these GEMMs
+//    in fp32 / TF32 cuBLAS).  Two operand types carry the split:
+//      - fp16 (ltn_conv_tc_f16, what the window runners use): 11 + 11 significant bits in 2 bytes per element, kind::f16
+//        at twice the tf32 rate; exact power-of-two scaling of activations and weights plus a device-side range flag
+//        cover fp16's narrow exponent (the caller redoes flagged work with tf32).  The A operand never touches shared
+//        memory: the gather registers are converted and written straight into TENSOR memory with tcgen05.st.16x256b
+//        (the gather is laid out like that fragment) and the MMA reads A from there (TS mode).
+//      - tf32 (ltn_conv_tc; hi = round-to-tf32, lo = x - hi exactly): A staged K-major in 128-byte-swizzled shared
+//        memory by the producers (16-byte chunks at chunk ^ (row & 7), fence.proxy.async), kind::tf32.  PASSES = 1 is
+//        the single-pass TF32 variant (reported separately, never the default).
+//  * A (gathered, data dependent): two producer warpgroups take alternate k-blocks; the tile's slice of the neighbour
+//    table sits in shared memory, row segments are fetched with 128-bit loads one unit ahead, the folded
+//    GroupNorm+ReLU and the hi/lo split happen in registers.
+//  * B (weights, dense): pre-split hi/lo K-major copies streamed by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B)
+//    from a dedicated lane that owns the ring's barriers and starts streaming before the block-wide set-up barrier.
+//    mbarrier rings decouple both from the single MMA-issuing thread; tcgen05.commit releases stages and finally
+//    hands the accumulator to the epilogue.
 //  * epilogue (8 warps): tcgen05.ld 32x32b (thread = row, 32 columns at a time) -> per-warp swizzled transpose in
 //    the idle operand ring -> quarter-warp per row: + bias, + residual, whole 128-byte lines stored; optionally
 //    the GroupNorm statistics of the OUTPUT (sum, sum of squares per group) are reduced here, so the next
@@ -40,7 +46,6 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int kUmmaK = 8;          // tf32: 32 bytes per MMA
 constexpr int kGroups = 2;         // producer warpgroups (round-robin k-blocks); 3 measured equal (fp16, A in tensor memory) or slower (tf32: register spills)
 constexpr int kGroupThreads = 128;
 constexpr int kMmaWarp = 4 * kGroups, kTmaWarp = 4 * kGroups + 1;
