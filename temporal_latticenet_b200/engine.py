@@ -213,7 +213,7 @@ class MultiWindowRunner:
     strictly sequential chain.  Interleaving the frame graphs of two windows lets one window's small kernels
     run on the SMs the other leaves idle -- the intra-GPU form of the sharding-by-window of SURVEY.md 8(e)."""
 
-    def __init__(self, cfg_path, nr_classes=26, device=None, lanes=2, operands="f16"):
+    def __init__(self, cfg_path, nr_classes=26, device=None, lanes=4, operands="f16"):
         self.lanes = [GraphWindowRunner(cfg_path, nr_classes, device, operands=operands) for _ in range(lanes)]
         self.device = self.lanes[0].device
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(lanes)]

@@ -209,12 +209,17 @@ def test_alternative_operand_paths_agree(dev, lattice):
         "V = ls.nr_lattice_vertices(); g = torch.Generator().manual_seed(5)\n"
         "for C, F in ((64, 64), (192, 192), (128, 48)):\n"
         "    x = torch.randn(V, C, generator=g); W = torch.randn(9 * C, F, generator=g) / (9 * C) ** 0.5\n"
-        "    out = ops.conv_tc(x.to(dev), ls.neighbours(), ops.k_major(W.to(dev))).cpu().double()\n"
         "    nbr = ls.neighbours().cpu().long(); pad = torch.cat([x, torch.zeros(1, C)], 0).double()\n"
         "    rows = pad[torch.where(nbr < 0, torch.full_like(nbr, V), nbr).reshape(-1)].reshape(V, 9 * C)\n"
         "    want = rows @ W.double(); bound = rows.abs() @ W.double().abs() + 1e-30\n"
-        "    assert float(((out - want).abs() / bound).max()) < 2e-5\n"
+        "    flag = torch.zeros(1, dtype=torch.int32, device=dev)\n"
+        "    for mode in ('tf32', 'f16'):\n"
+        "        out = ops.conv_tc(x.to(dev), ls.neighbours(), ops.k_major(W.to(dev)), operands=mode, flag=flag).cpu().double()\n"
+        "        assert float(((out - want).abs() / bound).max()) < 2e-5, (C, F, mode)\n"
+        "    assert int(flag.item()) == 0\n"
         "print('ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for env in ({"LTN_CONV_ATMEM": "1"}, {"LTN_CONV_CLUSTER": "4"}, {"LTN_CONV_CLUSTER": "2"}):
+    # tf32: A in tensor memory (register transpose); fp16: A through the shared-memory ring instead of tensor memory;
+    # weight tiles multicast across clusters of 4 / 2 (both operand types)
+    for env in ({"LTN_CONV_ATMEM": "1"}, {"LTN_CONV_ATMEM": "0"}, {"LTN_CONV_CLUSTER": "4"}, {"LTN_CONV_CLUSTER": "2"}):
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
