@@ -158,8 +158,9 @@ def test_scatter_max_add_mean_semantics(dev):
     assert torch.equal(s.grad.cpu(), hits)
 
 
+@pytest.mark.parametrize("order", ["scan", "shuffled"])
 @pytest.mark.parametrize("kernel", ["cuda_cores", "tensor_cores"])
-def test_pointnet_front_end_matches_float64(dev, kernel):
+def test_pointnet_front_end_matches_float64(dev, kernel, order):
     """PointNetSeqModule front end (lattice_modules.py:448-530): MLP 4 -> 16 -> 32 -> 64 per distributed row, segmented
     max per vertex with arg-max (smallest row on ties), barycentric weight of the winning row (quirk Q3), min-4-rows mask.
     Both kernels -- the whole MLP on the CUDA cores, and the 32 -> 64 layer on the tensor cores with fp16 hi/lo operands --
@@ -168,6 +169,9 @@ def test_pointnet_front_end_matches_float64(dev, kernel):
     from temporal_latticenet_b200 import _lib
     from temporal_latticenet_b200.lattice import Lattice
     p_np, v_np = small_window(seed=5, frames=1, radius=12.0, max_points=20000)[0]
+    if order == "shuffled":   # the reference shuffles the points of a training scan (kitti_dataloader.py:174-180): a block of
+        perm = np.random.default_rng(1).permutation(p_np.shape[0])   # rows then touches many distinct vertices, which takes
+        p_np, v_np = np.ascontiguousarray(p_np[perm]), np.ascontiguousarray(v_np[perm])   # the kernels' table-overflow path
     ls = Lattice(60000, 0.6, device=dev)
     rows, idx, w = ls.distribute(torch.from_numpy(p_np).to(dev), torch.from_numpy(v_np).to(dev), True)
     V, R = ls.nr_lattice_vertices(), rows.shape[0]
