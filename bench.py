@@ -588,6 +588,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "points_per_scan": pts, "frames": FRAMES, "vertices_per_level_after_4_frames": v_counts,
+                       "precision": "fp32 results: every tensor-core product is the 3-pass hi/lo split (fp16 operands, exact power-of-two "
+                                    "scaling, fp32 accumulation; range-flagged with a tf32 hi/lo re-run), 2e-5 * sum|a||w| of float64 in the tests",
                        "l2": "256 MB flush between steps; per-step working set (im2row buffers) also exceeds L2",
                        "parallelism": "windows sharded over %d rank(s) (every rank runs its own copy of the same synthetic windows), no data-path collective" % world,
                        "execution": ("CUDA-graph replay per frame kind, %d window(s) in flight per GPU (one stream each), "
