@@ -143,15 +143,6 @@ int ltn_conv_tc_f16(const float* x, int Vx, const int* vx_dev, const int* nbr, i
                     int gn_groups, int relu, const float* bias, const float* res, float* out, int ldo, double* out_sums,
                     int out_groups, int* flag, void* stream);
 int ltn_split_f16(const float* w, int K, int F, int transposed_in, int w_log2, void* wt_hi, void* wt_lo, void* stream);
-/* GRUModule.forward (lattice_modules.py:53-63) in two launches instead of four: gh = h' W_hh^T + b_hh comes from
- * ltn_conv_tc_f16 as before; this call computes gi = x W_ih^T + b_ih on the tensor cores (fp16 hi/lo operands) and applies
- * the gates r = s(gi_r+gh_r), z = s(gi_z+gh_z), n = tanh(gi_n + r gh_n), h_new = (1-z) n + z h' in its epilogue, writing
- * out [V,C] directly: no gi tensor, no pointwise kernel.  wt_hi / wt_lo / bias_perm: W_ih / b_ih with their 3C rows
- * permuted to [32-channel block][r | z | n][32]; gh [Vh,3C], h [Vh,C] = h', b_hh [3C] in the standard order; rows v >= Vh
- * are the zero padding (gh = b_hh, h' = 0).  C % 64 == 0. */
-int ltn_conv_tc_f16_gru(const float* x, int V, const int* v_dev, int C, const void* wt_hi, const void* wt_lo, int w_log2, int a_log2,
-                        const float* bias_perm, const float* gh, const float* h, const float* b_hh, int Vh, const int* vh_dev,
-                        float* out, int* flag, void* stream);
 /* phase tracing of the following ltn_conv_tc* launches (NULL switches it off): buf receives 8 globaltimer stamps (ns)
  * per CTA in launch-grid order -- entry, set-up done, first operands staged, producers done, accumulator complete,
  * epilogue stores issued, teardown, (unused) */

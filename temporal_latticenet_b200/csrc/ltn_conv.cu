@@ -188,17 +188,7 @@ struct ConvParams {
     float a_mul, out_mul;   // fp16 operands: power-of-two scale applied to A, and its (and the weights') inverse for the output
     int* flag;              // fp16 operands: set to 1 when a staged magnitude leaves the half range (nullable)
     unsigned long long* trace;  // nullable: [CTA][8] globaltimer stamps of the phases (ltn_conv_trace)
-    // GRU epilogue (nullable gru_gh = off): this GEMM is gi = x W_ih^T with the weight rows permuted to
-    // [32-channel block][r | z | n][32], so the r, z and n pre-activations of a channel sit in the same CTA; the epilogue
-    // reads gh / h' / b_hh and writes h_new [Vq, gru_C] directly -- no gi tensor, no pointwise kernel
-    const float* gru_gh;    // [Vh, 3 gru_C]  h' W_hh^T + b_hh  (standard r,z,n column order)
-    const float* gru_h;     // [Vh, gru_C]    h' (the linearly transformed hidden state)
-    const float* gru_bhh;   // [3 gru_C]      gh of the zero-padded rows v >= Vh
-    const int* gru_vh_dev;
-    int gru_Vh, gru_C;
 };
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ void trace_stamp(const ConvParams& p, int phase) {
     if (p.trace) {
@@ -649,66 +639,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CU
         float* stage = reinterpret_cast<float*>(smem + warp * 4096);
         const int wrow = (warp & 3) * 32;
         const float out_mul = F16 ? p.out_mul : 1.0f;
-        if (F16 && p.gru_gh) {
-            // ---- GRU epilogue: warp group g owns the 32-channel block 2 blockIdx.y + g: accumulator columns 96 g + {0,32,64}
-            // hold its r, z, n pre-activations (lattice_modules.py:58-62, PyTorch gate order).  The three 32 x 32 chunks are
-            // turned around like the plain epilogue's one; then a quarter-warp per row reads gh / h' (whole 128-byte lines),
-            // applies the gates and stores 128 bytes of h_new.
-            const int Vh = p.gru_vh_dev ? min(p.gru_Vh, __ldg(p.gru_vh_dev)) : p.gru_Vh;
-            const int GC = p.gru_C;
-            float* stage3 = reinterpret_cast<float*>(smem + warp * 3 * 4096);
-            for (int g3 = group; g3 * 96 < N; g3 += kGroups) {
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    float acc[32];
-                    tmem_ld32(t_lane + (uint32_t)(g3 * 96 + q * 32), acc);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(stage3 + q * 1024 + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                            make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-                }
-                __syncwarp();
-                const int c = (n0 / 96 + g3) * 32 + 4 * chunk;        // output channel of this lane's float4
-                const int bcol = n0 + g3 * 96 + 4 * chunk;            // its r column in the permuted layout (z: +32, n: +64)
-                float4 bi[3], bh[3];
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    bi[q] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + bcol + 32 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    bh[q] = __ldg(reinterpret_cast<const float4*>(p.gru_bhh + q * GC + c));
-                }
-#pragma unroll 2
-                for (int it = 0; it < 8; ++it) {
-                    const int r = it * 4 + sub;
-                    const int v = row0 + wrow + r;
-                    if (v >= Vq) continue;
-                    float4 gi[3], gh[3], hp = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const float4 a = *reinterpret_cast<const float4*>(stage3 + q * 1024 + r * 32 + ((chunk ^ (r & 7)) << 2));
-                        gi[q] = make_float4(fmaf(a.x, out_mul, bi[q].x), fmaf(a.y, out_mul, bi[q].y), fmaf(a.z, out_mul, bi[q].z), fmaf(a.w, out_mul, bi[q].w));
-                        gh[q] = bh[q];
-                    }
-                    if (v < Vh) {
-                        const float* ghv = p.gru_gh + (size_t)v * 3 * GC + c;
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) gh[q] = __ldg(reinterpret_cast<const float4*>(ghv + q * GC));
-                        hp = __ldg(reinterpret_cast<const float4*>(p.gru_h + (size_t)v * GC + c));
-                    }
-                    float4 o;
-#define LTN_GRU_LANE(f)                                               \
-                    {                                                 \
-                        const float rr = sigmoidf_(gi[0].f + gh[0].f); \
-                        const float zz = sigmoidf_(gi[1].f + gh[1].f); \
-                        const float nn = tanhf(gi[2].f + rr * gh[2].f); \
-                        o.f = (1.0f - zz) * nn + zz * hp.f;            \
-                    }
-                    LTN_GRU_LANE(x) LTN_GRU_LANE(y) LTN_GRU_LANE(z) LTN_GRU_LANE(w)
-#undef LTN_GRU_LANE
-                    *reinterpret_cast<float4*>(p.out + (size_t)v * p.ldo + c) = o;
-                }
-                __syncwarp();
-            }
-        } else
         for (int cb = group * 32; cb < N; cb += 32 * kGroups) {
             float acc[32];
             tmem_ld32(t_lane + (uint32_t)cb, acc);   // warp-collective: executed by every lane
@@ -928,17 +858,11 @@ int make_weight_map(CUtensorMap* map, const void* w, int F, int K, int n_tile, b
 }
 
 // common launcher.  half: fp16 operands (wt_* are __half copies scaled by 2^w_log2, activations are scaled by 2^a_log2).
-struct GruEpilogue {
-    const float *gh, *h, *bhh;
-    const int* vh_dev;
-    int Vh, C;
-};
-
 int conv_launch(const float* x, int Vx, const int* vx_dev, const int* nbr, int Vq, const int* vq_dev, int C, int S,
                 const void* wt_hi, const void* wt_lo, int F, const float* a_scale, const float* a_shift, const double* gn_sums,
                 const float* gn_gamma, const float* gn_beta, float gn_eps, int gn_groups, int relu, const float* bias,
                 const float* res, float* out, int ldo, double* out_sums, int out_groups, int passes, bool half, int a_log2,
-                int w_log2, int* flag, void* stream, const GruEpilogue* gru = nullptr) {
+                int w_log2, int* flag, void* stream) {
     if (Vq <= 0) return 0;
     if (Vx <= 0) return -2;   // row 0 of x must be readable (stand-in address of absent neighbours)
     const bool affine = a_scale || gn_sums;
@@ -958,12 +882,6 @@ int conv_launch(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     p.out_mul = half ? ldexpf(1.0f, -(a_log2 + w_log2)) : 1.0f;
     p.flag = half ? flag : nullptr;
     p.trace = g_trace;
-    p.gru_gh = nullptr; p.gru_h = nullptr; p.gru_bhh = nullptr; p.gru_vh_dev = nullptr; p.gru_Vh = 0; p.gru_C = 0;
-    if (gru) {
-        // F = 3 C_gru permuted gate columns; tiles of 192 = two 32-channel blocks x (r | z | n)
-        if (!half || nbr || res || out_sums || gru->C % 64 || F != 3 * gru->C || !gru->gh || !gru->h || !gru->bhh) return -2;
-        p.gru_gh = gru->gh; p.gru_h = gru->h; p.gru_bhh = gru->bhh; p.gru_vh_dev = gru->vh_dev; p.gru_Vh = gru->Vh; p.gru_C = gru->C;
-    }
     // Output channels per CTA.  All of them when they fit one accumulator (A rows gathered once); when that
     // leaves SMs idle (few row tiles) the channels are split further, but never beyond ONE wave of 148 CTAs
     // (one CTA per SM: a second, partly filled wave would cost a whole extra tile time).
@@ -973,7 +891,6 @@ int conv_launch(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     while (row_tiles * (ny + 1) <= 148 && (F / (ny + 1)) >= 32) ++ny;
     int n_tile = ((F + ny - 1) / ny + unit - 1) / unit * unit;
     if (n_tile > 256) n_tile = 256 / unit * unit;
-    if (gru) n_tile = 192;
     if (n_tile <= 0) return -2;
     ny = (F + n_tile - 1) / n_tile;
     p.n_tile = n_tile;
@@ -987,7 +904,7 @@ int conv_launch(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
     // fp16 operands: A staged in tensor memory is the default (the gather is laid out like the tcgen05.st fragment,
     // so nothing has to be transposed); LTN_CONV_ATMEM=0 keeps the shared-memory ring.
     static const int want_atmem = []() { const char* e = getenv("LTN_CONV_ATMEM"); return e ? atoi(e) : -1; }();
-    const bool atmem = half ? (want_atmem != 0 || gru != nullptr) : (want_atmem > 0);
+    const bool atmem = half ? (want_atmem != 0) : (want_atmem > 0);
     int sa, sb;
     size_t smem;
     if (atmem) {
@@ -1004,7 +921,6 @@ int conv_launch(const float* x, int Vx, const int* vx_dev, const int* nbr, int V
         if (sb < 2) return -3;
         smem = sb * b_stage;
         if (smem < 12 * 4096) smem = 12 * 4096;   // the epilogue turns each warp's 32 x 32 block around in 4 KB of this region
-        if (gru && smem < (size_t)(4 * kGroups) * 3 * 4096) smem = (size_t)(4 * kGroups) * 3 * 4096;
         smem += 1024;
     } else {
         sa = (int)((budget - 2 * b_stage) / a_stage);
@@ -1104,19 +1020,6 @@ int ltn_conv_tc_f16(const float* x, int Vx, const int* vx_dev, const int* nbr, i
                     int out_groups, int* flag, void* stream) {
     return conv_launch(x, Vx, vx_dev, nbr, Vq, vq_dev, C, S, wt_hi, wt_lo, F, a_scale, a_shift, gn_sums, gn_gamma, gn_beta, gn_eps,
                        gn_groups, relu, bias, res, out, ldo, out_sums, out_groups, 3, true, a_log2, w_log2, flag, stream);
-}
-
-// GRUModule in two launches instead of four (lattice_modules.py:53-63): gh = h' W_hh^T + b_hh comes from ltn_conv_tc_f16 as
-// before; THIS call computes gi = x W_ih^T + b_ih on the tensor cores and applies the GRU gates in its epilogue, writing
-// h_new [V, C] directly.  wt_hi / wt_lo / bias_perm: W_ih / b_ih with their 3C rows permuted to
-// [32-channel block][r | z | n][32] (ops.gru_permutation); gh [Vh,3C], h [Vh,C] = h', b_hh [3C] in the standard order; rows
-// v >= Vh are the zero padding (gh = b_hh, h' = 0).  C % 64 == 0.  The flag has the meaning of ltn_conv_tc_f16.
-int ltn_conv_tc_f16_gru(const float* x, int V, const int* v_dev, int C, const void* wt_hi, const void* wt_lo, int w_log2, int a_log2,
-                        const float* bias_perm, const float* gh, const float* h, const float* b_hh, int Vh, const int* vh_dev,
-                        float* out, int* flag, void* stream) {
-    GruEpilogue g{gh, h, b_hh, vh_dev, Vh, C};
-    return conv_launch(x, V, v_dev, nullptr, V, v_dev, C, 1, wt_hi, wt_lo, 3 * C, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0, 0,
-                       bias_perm, nullptr, out, C, nullptr, 0, 3, true, a_log2, w_log2, flag, stream, &g);
 }
 
 }  // extern "C"

@@ -82,16 +82,12 @@ class GRUModule(torch.nn.Module, _HiddenState):
         if _fused_ok(lv, h, g.weight_ih):
             if Vh > V:
                 _pad_rows(h, V)
+            gi = ops.linear(lv, g.weight_ih, g.bias_ih)
             gh = ops.linear(h, g.weight_hh, g.bias_hh, rows_dev=hrows)
-            if ops.gru_fused_ok(C) and V > 0 and Vh > 0:
-                # the gates run in the epilogue of the gi GEMM: no gi tensor, no pointwise kernel
-                new_lv = ops.conv_tc_gru(lv, g.weight_ih, g.bias_ih, gh, h, g.bias_hh, vh_dev=hrows)
-            else:
-                gi = ops.linear(lv, g.weight_ih, g.bias_ih)
-                new_lv = torch.empty_like(lv)
-                p = _lib.ptr
-                _lib.check(_lib.load().ltn_gru_pointwise(p(gi), p(gh), p(h.contiguous()), p(g.bias_hh), V, Vh, _lib.rows_dev(V),
-                                                         self._rows_dev(), C, p(new_lv), _lib.stream()), "ltn_gru_pointwise")
+            new_lv = torch.empty_like(lv)
+            p = _lib.ptr
+            _lib.check(_lib.load().ltn_gru_pointwise(p(gi), p(gh), p(h.contiguous()), p(g.bias_hh), V, Vh, _lib.rows_dev(V),
+                                                     self._rows_dev(), C, p(new_lv), _lib.stream()), "ltn_gru_pointwise")
         else:
             new_lv = g(lv, _pad_rows(h, V))
         self._store(new_lv)

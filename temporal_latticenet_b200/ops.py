@@ -241,50 +241,6 @@ def k_major_padded(weight, rows):
     return _cached_split(weight, (id(weight), "pad", int(rows)), make)
 
 
-def gru_permutation(C, device=None):
-    """row order of W_ih / b_ih for the fused GRU epilogue: [32-channel block][r | z | n][32] <- PyTorch's [r | z | n][C]"""
-    b = torch.arange(C // 32, device=device).view(-1, 1, 1)
-    g = torch.arange(3, device=device).view(1, -1, 1)
-    j = torch.arange(32, device=device).view(1, 1, -1)
-    return (g * C + b * 32 + j).reshape(-1)
-
-
-def k_major_gru(weight_ih, bias_ih):
-    """(SplitWeight of the gate-interleaved W_ih, permuted b_ih), cached per parameter version"""
-    def make():
-        perm = gru_permutation(weight_ih.shape[1], weight_ih.device)
-        return (SplitWeight(weight_ih.detach()[perm].contiguous().float(), True), bias_ih.detach()[perm].contiguous().float(), bias_ih._version)
-    sw, bp, bver = _cached_split(weight_ih, (id(weight_ih), "gru"), make)
-    if bver != bias_ih._version:      # the bias changed without the weight: rebuild
-        _WT_CACHE.pop((id(weight_ih), "gru"), None)
-        sw, bp, bver = _cached_split(weight_ih, (id(weight_ih), "gru"), make)
-    return sw, bp
-
-
-def conv_tc_gru(x, weight_ih, bias_ih, gh, h, b_hh, vh_dev=None, out=None):
-    """GRU gates in the epilogue of the gi GEMM (csrc/ltn_conv.cu, ltn_conv_tc_f16_gru): h_new [V,C] from x [V,C],
-    gh [Vh,3C] = h' W_hh^T + b_hh, h [Vh,C] = h'.  fp16 operands only (needs the range flag of ops.tc_operands)."""
-    flag = _TC["flag"]
-    if _TC["mode"] != "f16" or flag is None:
-        raise RuntimeError("the fused GRU epilogue runs with fp16 operands (ops.tc_operands)")
-    x = x.contiguous()
-    V, C = x.shape
-    sw, bias_perm = k_major_gru(weight_ih, bias_ih)
-    hi, lo, w_log2 = sw.f16()
-    if out is None:
-        out = torch.empty(V, C, dtype=torch.float32, device=x.device)
-    p = _lib.ptr
-    rc = _lib.load().ltn_conv_tc_f16_gru(p(x), V, _lib.rows_dev(V), C, p(hi), p(lo), int(w_log2), int(A_LOG2), p(bias_perm),
-                                         p(gh.contiguous()), p(h.contiguous()), p(b_hh.detach().contiguous()), int(h.shape[0]), vh_dev,
-                                         p(out), p(flag), _lib.stream())
-    _lib.check(rc, "ltn_conv_tc_f16_gru")
-    return out
-
-
-def gru_fused_ok(C):
-    return _TC["mode"] == "f16" and _TC["flag"] is not None and C % 64 == 0
-
-
 def gn_sums(x, groups):
     """[G,2] double: per-group sum and sum of squares of x [V,C] (GroupNorm over [1,C,V])"""
     x = x.contiguous()
