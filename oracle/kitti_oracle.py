@@ -59,8 +59,9 @@ def load_label(path, remap_lut):
     return np.squeeze(remap_lut[labels], axis=1)
 
 
-def assemble_window(data_dir, seq, index, frames, scope, remap_lut=None):
-    """-> [(positions [N,3] float32, reflectance [N,1] float32, labels [N] or None)] for the window ending at scan `index`"""
+def assemble_window(data_dir, seq, index, frames, scope, remap_lut=None, cap_distance=-1, min_distance=-1):
+    """-> [(positions [N,3] float32, reflectance [N,1] float32, labels [N] or None)] for the window ending at scan `index`;
+    cap_distance / min_distance: the training-time range crop of kitti_dataloader.py:142-154"""
     sdir = os.path.join(data_dir, "sequences", "%02d" % seq)
     poses = parse_poses(os.path.join(sdir, "poses.txt"), parse_calibration(os.path.join(sdir, "calib.txt")))
     idxs = window_indices(index, frames, scope)
@@ -69,15 +70,23 @@ def assemble_window(data_dir, seq, index, frames, scope, remap_lut=None):
     for idx in idxs:
         raw = np.fromfile(os.path.join(sdir, "velodyne", "%06d.bin" % idx), dtype=np.float32).reshape(-1, 4).transpose()
         refl, xyz = raw[3, :], raw[0:3, :]
+        lab = None
+        if remap_lut is not None:
+            lab = load_label(os.path.join(sdir, "labels", "%06d.label" % idx), remap_lut)
+        if cap_distance >= 0:
+            mask = np.linalg.norm(xyz, axis=0) < cap_distance
+            xyz, refl = xyz[:, mask], refl[mask]
+            lab = lab[mask] if lab is not None else None
+        if min_distance >= 0:
+            mask = np.linalg.norm(xyz, axis=0) > min_distance
+            xyz, refl = xyz[:, mask], refl[mask]
+            lab = lab[mask] if lab is not None else None
         hom = np.ones((4, xyz.shape[1]))
         hom[0:3, :] = xyz
         world = np.matmul(poses[idx], hom)
         world = np.matmul(np.linalg.inv(first), world)
         ros = np.matmul(rotation_matrix_x(-90), world)
         scan = (ros[0:3, :] / ros[3, :]).transpose()
-        lab = None
-        if remap_lut is not None:
-            lab = load_label(os.path.join(sdir, "labels", "%06d.label" % idx), remap_lut)
         out.append((scan.astype(np.float32), np.expand_dims(refl, 1).astype(np.float32), lab))
     return out
 

@@ -125,18 +125,50 @@ class KittiSequence:
             return None
         return torch.from_numpy(load_labels(os.path.join(self.dir, "labels", "%06d.label" % int(idx)), self.lut).astype(np.int64))
 
-    def window(self, index, with_labels=False):
+    def window(self, index, with_labels=False, cap_distance=-1.0, min_distance=-1.0, shuffle=False, generator=None):
         """-> [(positions [N,3], values [N,1])] on the device (+ labels of the last frame): the model's inputs for the window
-        ending at scan `index`, every frame expressed in the first frame's coordinates (kitti_dataloader.py:119-171)"""
+        ending at scan `index`, every frame expressed in the first frame's coordinates (kitti_dataloader.py:119-171).
+        Training-time options of the reference loader: cap_distance / min_distance >= 0 drop the points outside that range
+        of the SENSOR (:142-154, before the pose transform, order preserved), shuffle permutes the points of every frame
+        (:173-180; the same permutation for positions, values and labels)."""
         _lib.require_cuda()
         idxs = window_indices(index, self.frames, self.scope)
-        out = []
-        for idx in idxs:
+        out, last_labels = [], None
+        for k, idx in enumerate(idxs):
             raw = self.read_raw(idx).to(self.device, non_blocking=True)
+            lab = self.labels(idx) if (with_labels and k == len(idxs) - 1) else None
+            keep = range_mask(raw, cap_distance, min_distance)
+            if keep is not None:
+                raw = raw[keep]
+                if lab is not None:
+                    lab = lab[keep.cpu()]
+            if shuffle:
+                perm = torch.randperm(raw.shape[0], device=raw.device, generator=generator)
+                raw = raw[perm]
+                if lab is not None:
+                    lab = lab[perm.cpu()]
             out.append(assemble_scan(raw, self.matrices(idx, idxs[0])))
+            if lab is not None:
+                last_labels = lab
         if with_labels:
-            return out, self.labels(idxs[-1])
+            return out, last_labels
         return out
+
+
+def range_mask(raw, cap_distance=-1.0, min_distance=-1.0):
+    """boolean keep-mask of kitti_dataloader.py:142-154 (None when both limits are off): distance of the raw sensor-frame
+    point from the origin, in float32 exactly as np.linalg.norm forms it ((x*x + y*y) + z*z, each step rounded, then sqrt),
+    strictly below cap_distance and strictly above min_distance.  Works on whatever device `raw` [N,4] lives on."""
+    if cap_distance < 0 and min_distance < 0:
+        return None
+    x, y, z = raw[:, 0], raw[:, 1], raw[:, 2]
+    length = torch.sqrt((x * x + y * y) + z * z)
+    keep = torch.ones_like(length, dtype=torch.bool)
+    if cap_distance >= 0:
+        keep &= length < cap_distance
+    if min_distance >= 0:
+        keep &= length > min_distance
+    return keep
 
 
 def assemble_scan(raw_dev, mats):

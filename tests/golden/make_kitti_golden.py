@@ -69,6 +69,31 @@ def main():
         out["label_%d" % i] = l.numpy()
         out["path_%d" % i] = np.asarray(os.path.relpath(path_seq[i], TINY))
     np.savez_compressed(os.path.join(HERE, "kitti_window.npz"), **out)
+    # training split of the same loader: range crop on (cap 30 m, min 8 m), point shuffle and every augmentation off, so the
+    # output is deterministic.  The train split starts with sequence 00: a copy of the tiny sequence under /tmp.
+    import shutil
+    tmp_root = "/tmp/kitti_tiny_train"
+    shutil.rmtree(tmp_root, ignore_errors=True)
+    shutil.copytree(os.path.join(TINY, "sequences", "08"), os.path.join(tmp_root, "sequences", "00"))
+    lk["dataset_path"] = tmp_root
+    lk["cap_distance"], lk["min_distance"], lk["shuffle_points"] = 30, 8, False
+    tr = lk["transformer"]
+    for k in ("random_translation_xyz_magnitude", "random_translation_xz_magnitude", "rotation_y_max_angle", "random_stretch_xyz_magnitude",
+              "random_subsample_percentage", "chance_of_xyz_noise"):
+        tr[k] = 0.0
+    for k in ("random_mirror_x", "random_mirror_z", "random_rotation_90_degrees_y"):
+        tr[k] = False
+    with open(tmp_cfg, "w") as f:
+        f.write(hjson.dumps(cfg))
+    ds_train = SemanticKittiDataset("train", cfgParser(tmp_cfg), sequence_learning=True)
+    scan_seq, feature_seq, label_seq, path_seq, len_seq = ds_train[7]
+    for i, (s_, f_, l) in enumerate(zip(scan_seq, feature_seq, label_seq)):
+        out["crop_scan_%d" % i] = s_.numpy()
+        out["crop_feature_%d" % i] = f_.numpy()
+        out["crop_label_%d" % i] = l.numpy()
+    out["crop_len_seq"] = np.asarray(len_seq)
+    np.savez_compressed(os.path.join(HERE, "kitti_window.npz"), **out)
+    print("train split, cap 30 / min 8:", len_seq)
     # the dataset's label maps (facts of SemanticKITTI, read from the reference's yaml) for the product's configs/
     import yaml
     with open(lk["yaml_config_all"]) as f:
@@ -76,7 +101,7 @@ def main():
     with open(os.path.join(REPO, "configs", "semantic_kitti_label_maps.yaml"), "w") as f:
         f.write("# SemanticKITTI label maps with the moving classes (26 training classes), extracted by tests/golden/make_kitti_golden.py\n")
         yaml.safe_dump({"learning_map": data["learning_map"], "learning_map_inv": data["learning_map_inv"]}, f, sort_keys=True)
-    print("frames", len(scan_seq), "points", len_seq, [os.path.basename(p) for p in path_seq], scan_seq[0].dtype)
+    print("valid split:", int(out["nr_frames"]), "frames,", out["len_seq"].tolist(), "points")
 
 
 if __name__ == "__main__":

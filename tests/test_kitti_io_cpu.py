@@ -64,3 +64,32 @@ def test_prediction_files_and_checkpoint_names(tmp_path):
     assert P.checkpoint_name(*args) == K.checkpoint_name(*args) == "18102026_1200_multi_Kitti_Ref_sigma0.6_typegru-gru-aflow-gru_frames4_scope3_epoch7"
     args = ("01012027_0000", False, "parislille", "none", "0.9 3", ["none"] * 4, True, 1, 1, 0)
     assert P.checkpoint_name(*args) == K.checkpoint_name(*args) == "01012027_0000_single_Paris_xyz_sigma0.9_typeACCUM_frames1_scope1_epoch0"
+
+
+def test_training_range_crop_matches_reference_loader():
+    """kitti_dataloader.py:142-154 (cap_distance / min_distance, training split only): the oracle against the reference
+    loader's train split run with every random augmentation off, and the product's keep-mask (float32 norm formed exactly
+    like np.linalg.norm forms it) against the oracle's, bit for bit."""
+    import torch
+    from oracle import kitti_oracle as K
+    from temporal_latticenet_b200 import kitti_io as P
+    g = _golden()
+    frames = K.assemble_window(TINY, 8, 7, frames=4, scope=3, remap_lut=g["remap_lut"], cap_distance=30, min_distance=8)
+    assert [f[0].shape[0] for f in frames] == g["crop_len_seq"].tolist()
+    for i, (pos, refl, lab) in enumerate(frames):
+        assert np.array_equal(pos, g["crop_scan_%d" % i])
+        assert np.array_equal(refl, g["crop_feature_%d" % i])
+        assert np.array_equal(lab, g["crop_label_%d" % i])
+    sdir = os.path.join(TINY, "sequences", "08")
+    for k in (0, 1, 4, 7):
+        raw = np.fromfile(os.path.join(sdir, "velodyne", "%06d.bin" % k), dtype=np.float32).reshape(-1, 4)
+        length = np.linalg.norm(raw[:, :3].T, axis=0)
+        for cap, mn in ((30, 8), (30, -1), (-1, 8), (12.5, 12.4)):
+            want = np.ones(raw.shape[0], bool)
+            if cap >= 0:
+                want &= length < cap
+            if mn >= 0:
+                want &= length > mn
+            got = P.range_mask(torch.from_numpy(raw), cap, mn)
+            assert np.array_equal(got.numpy(), want)
+    assert P.range_mask(torch.zeros(5, 4), -1, -1) is None

@@ -36,6 +36,36 @@ def test_window_from_wire_format_matches_reference_loader():
         assert np.array_equal(val.cpu().numpy(), g["feature_%d" % i])
 
 
+def test_training_crop_and_shuffle_on_the_device():
+    """range crop (kitti_dataloader.py:142-154) against the reference loader's train split; shuffle (:173-180): every frame is
+    a permutation of the unshuffled frame, labels permuted alike"""
+    from temporal_latticenet_b200.kitti_io import KittiSequence
+    import yaml
+    from tests.helpers import REPO
+    g = np.load(os.path.join(GOLDEN, "kitti_window.npz"))
+    with open(os.path.join(REPO, "configs", "semantic_kitti_label_maps.yaml")) as f:
+        lm = yaml.safe_load(f)["learning_map"]
+    seq = KittiSequence(TINY, 8, frames=4, scope=3, learning_map=lm, device="cuda:0")
+    frames, labels = seq.window(7, with_labels=True, cap_distance=30, min_distance=8)
+    for i, (pos, val) in enumerate(frames):
+        assert pos.shape[0] == int(g["crop_len_seq"][i])
+        _ulp_check(pos.cpu().numpy(), g["crop_scan_%d" % i])
+        assert np.array_equal(val.cpu().numpy(), g["crop_feature_%d" % i])
+    assert np.array_equal(labels.numpy(), g["crop_label_3"])
+    gen = torch.Generator(device="cuda:0").manual_seed(5)
+    sframes, slabels = seq.window(7, with_labels=True, cap_distance=30, min_distance=8, shuffle=True, generator=gen)
+    for (p0, v0), (p1, v1) in zip(frames, sframes):
+        a = torch.cat([p0, v0], 1).cpu().numpy()
+        b = torch.cat([p1, v1], 1).cpu().numpy()
+        assert a.shape == b.shape and not np.array_equal(a, b)
+        assert np.array_equal(a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])])
+    # the labels follow their points: match rows of the last frame by value
+    a = torch.cat(list(frames[-1]), 1).cpu().numpy()
+    b = torch.cat(list(sframes[-1]), 1).cpu().numpy()
+    ia, ib = np.lexsort(a.T[::-1]), np.lexsort(b.T[::-1])
+    assert np.array_equal(labels.numpy()[ia], slabels.numpy()[ib])
+
+
 def test_full_size_scan_transform_and_round_trip():
     from temporal_latticenet_b200 import kitti_io as P
     rng = np.random.default_rng(4)
