@@ -192,6 +192,12 @@ int ltn_aflow(const float* lv, const float* h, int V, int Vh, const int* v_dev, 
  * rounded to float32 (kitti_dataloader.py:160-171, DataTransformer.py:88-91); pos [N,3], val [N,1] = reflectance. */
 int ltn_assemble_scan(const float* raw, int N, const double* mats, int nr_mats, float* pos, float* val, void* stream);
 
+/* Scores.accumulate_scores (callbacks/scores.py:13-30; train_ln.py:219 via StateCallback): arg-max of scores [N,K],
+ * K x K confusion counts of one cloud folded into per-class intersection / union (classes present in gt only,
+ * `unlabeled` skipped).  conf [K,K] u64 scratch (zeroed by the caller once), inter / uni [K] int64 accumulators. */
+int ltn_scores_accumulate(const float* scores, const long long* gt, int N, const int* n_dev, int K, int unlabeled,
+                          unsigned long long* conf, long long* inter, long long* uni, void* stream);
+
 /* library version / build info */
 int ltn_version(void);
 /* dst[0] = a, dst[1] = b on the stream (per-frame point counts of the graph engine; values travel in the launch) */

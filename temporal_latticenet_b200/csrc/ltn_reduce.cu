@@ -136,6 +136,49 @@ inline int grid_for(long long work_items, int threads) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// IoU accumulation of callbacks/scores.py:13-30 on the device.  One thread per point: arg-max of its K class scores
+// (first maximum wins, like torch.argmax), then the (gt, pred) pair is counted in a block-local K x K histogram that
+// is flushed with one 64-bit atomic per non-empty cell.
+__global__ void __launch_bounds__(kThreads)
+k_confusion(const float* __restrict__ scores, const long long* __restrict__ gt, int N, const int* __restrict__ n_dev, int K,
+            unsigned long long* conf) {
+    extern __shared__ unsigned int s_hist[];
+    if (n_dev) N = min(N, __ldg(n_dev));
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+        const float* row = scores + (size_t)p * K;
+        int best = 0;
+        float bv = __ldg(row);
+        for (int k = 1; k < K; ++k) {
+            const float v = __ldg(row + k);
+            if (v > bv || (v != v && bv == bv)) { bv = v; best = k; }   // NaN counts as the maximum (torch.argmax)
+        }
+        const long long g = __ldg(gt + p);
+        if (g >= 0 && g < K) atomicAdd(&s_hist[(int)g * K + best], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(conf + i, (unsigned long long)s_hist[i]);
+}
+
+// folds one cloud's confusion matrix into the running per-class intersection / union (scores.py:24-30: only classes
+// PRESENT in this cloud's ground truth, the unlabeled class skipped) and clears the matrix for the next cloud
+__global__ void k_scores_fold(unsigned long long* conf, int K, int unlabeled, long long* inter, long long* uni) {
+    const int l = threadIdx.x;
+    unsigned long long g = 0, pr = 0, d = 0;
+    if (l < K) {
+        for (int j = 0; j < K; ++j) { g += conf[l * K + j]; pr += conf[j * K + l]; }
+        d = conf[l * K + l];
+    }
+    __syncthreads();
+    if (l < K && g > 0 && l != unlabeled) {
+        inter[l] += (long long)d;
+        uni[l] += (long long)(g + pr - d);
+    }
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) conf[i] = 0ull;
+}
+
 }  // namespace
 
 extern "C" {
@@ -186,6 +229,23 @@ int ltn_gn_apply(const float* x, int V, const int* v_dev, int C, int G, const do
     if (G <= 0 || C % G) return -2;
     k_gn_apply<<<grid_for((long long)V * C, kThreads), kThreads, sizeof(float) * 2 * C, (cudaStream_t)stream>>>(
         x, V, v_dev, C, C / G, sums, gamma, beta, eps, relu, y);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+// scores [N,K] (any monotone transform of the class probabilities), gt [N] int64; conf [K,K] u64 scratch (zero on first
+// use, left zero), inter / uni [K] int64 accumulators.  K <= 64.
+int ltn_scores_accumulate(const float* scores, const long long* gt, int N, const int* n_dev, int K, int unlabeled,
+                          unsigned long long* conf, long long* inter, long long* uni, void* stream) {
+    if (K <= 0 || K > 64) return -2;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 0) {
+        int blocks = (N + kThreads - 1) / kThreads;
+        if (blocks > 4 * 148) blocks = 4 * 148;
+        k_confusion<<<blocks, kThreads, sizeof(unsigned int) * K * K, st>>>(scores, gt, N, n_dev, K, conf);
+        LTN_CHECK_LAUNCH();
+    }
+    k_scores_fold<<<1, 64, 0, st>>>(conf, K, unlabeled, inter, uni);
     LTN_CHECK_LAUNCH();
     return 0;
 }

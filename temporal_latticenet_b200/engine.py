@@ -35,13 +35,19 @@ class GraphWindowRunner(WindowRunner):
         self.graphs = {}
         self.kernels = {}      # frame kind -> kernels of this library inside its graph (bench.py: gpu_launches)
         self.caps = None
-        self.supported = all(k in _STATIC_FUSION for k in self.model.rnn_modules) and self.model.sequence_learning
+        # static capacities need every per-row kernel to take its live count from the device: that holds for the FUSED
+        # PointNet front end only (widths [16,32,64], one value column); other cfgs take the eager path, where the
+        # unfused scatter_max / scatter_add see exactly-sized tensors
+        self.supported = (all(k in _STATIC_FUSION for k in self.model.rnn_modules) and self.model.sequence_learning
+                          and self.model.point_net_seq.layer_widths == [16, 32, 64])
         self.fallbacks = 0
         self._force_eager = False
 
     # ---- capacities from an eager probe window ---------------------------------------------------------
     def plan(self, frames_dev):
         """runs one eager window to learn the sizes, then fixes the capacities (with headroom)"""
+        if any(v.shape[1] != 1 for _, v in frames_dev):
+            self.supported = False     # the fused PointNet front end takes [x, y, z, value] rows only
         out = super().infer_window_device(frames_dev)
         counts, lvl = [], self.lattice
         while lvl is not None:
@@ -51,11 +57,15 @@ class GraphWindowRunner(WindowRunner):
         caps = {"n": _round_up(n_max * 1.02 + 1024, 4096)}
         vcaps = [_round_up(c * self.headroom + 512, 1024) for c in counts]
         vcaps = [min(v, self.lattice.capacity) for v in vcaps]
-        # row classes must be told apart by their capacity alone
+        # row classes must be told apart by their capacity alone; collisions are resolved DOWNWARDS so that a vertex
+        # capacity never exceeds the hash table's (the table clamps its counter there, and the overflow check
+        # `count < cap` must be able to fail)
         used = {caps["n"], 4 * caps["n"]}
         for i, v in enumerate(vcaps):
-            while v in used:
-                v += 1024
+            while v in used and v > 1024:
+                v -= 1024
+            if v in used or v > self.lattice.capacity or v < counts[i]:
+                self.supported = False   # no distinct capacity left below the table's: this window runs eagerly
             used.add(v)
             vcaps[i] = v
         caps["v"] = vcaps
@@ -74,7 +84,7 @@ class GraphWindowRunner(WindowRunner):
         lvl = self.static_lattice
         for _ in range(len(self.caps["v"]) - 1):
             lvl = lvl.coarse_level()
-        self._counts_host = torch.zeros(len(self.caps["v"]) + 1, dtype=torch.int32).pin_memory()   # + the fp16 range flag
+        self._counts_host = torch.zeros(4 * len(self.caps["v"]) + 1, dtype=torch.int32).pin_memory()   # + the fp16 range flag
         self.graphs = {}
         self.pool = None
 
@@ -142,6 +152,9 @@ class GraphWindowRunner(WindowRunner):
         return self
 
     def infer_window_device(self, frames_dev):
+        """NOTE on lifetime: in graph mode the result is a view of the captured graph's static output tensor -- valid
+        until the next window runs on this runner; clone it to keep it (infer_window's labels likewise live in a reused
+        pinned buffer)."""
         if not self.supported or self.caps is None or self._force_eager:
             return super().infer_window_device(frames_dev)
         if any(p.shape[0] > self.caps["n"] for p, _ in frames_dev):   # more points than the static buffers hold
@@ -161,20 +174,27 @@ class GraphWindowRunner(WindowRunner):
         return sum(self.kernels.get((t == 0, t == nr_frames - 1), 0) for t in range(nr_frames))
 
     def _copy_checks(self, host):
-        """queues the device->host copies of the window's safety checks: vertex counts of every level + the fp16 range flag"""
+        """queues the device->host copies of the window's safety checks: the four counters of every level (vertices,
+        previous, overflowed, keys out of the packable range) + the fp16 range flag"""
         lvl, i, nv = self.static_lattice, 0, len(self.caps["v"])
         while lvl is not None and i < nv:
-            host[i:i + 1].copy_(lvl.hash_table.count_tensor(), non_blocking=True)
+            host[4 * i:4 * i + 4].copy_(lvl.hash_table.counters[0:4], non_blocking=True)
             lvl, i = lvl._coarse, i + 1
-        host[nv:nv + 1].copy_(self.range_flag, non_blocking=True)
+        host[4 * nv:4 * nv + 1].copy_(self.range_flag, non_blocking=True)
 
     def _checks_ok(self, host):
         vals, nv = host.tolist(), len(self.caps["v"])
-        if vals[nv]:   # an activation left the fp16 range: clear the flag, the caller re-runs the window
+        if vals[4 * nv]:   # an activation left the fp16 range: clear the flag, the caller re-runs the window
             self.range_flag.zero_()
             self.range_fallbacks += 1
             return False
-        return all(int(c) < cap for c, cap in zip(vals[:nv], self.caps["v"]))
+        for i, cap in enumerate(self.caps["v"]):
+            count, _, overflowed, out_of_range = vals[4 * i:4 * i + 4]
+            if out_of_range:   # the eager re-run raises the RuntimeError of HashTable._sync_counters for it
+                return False
+            if overflowed or not int(count) < cap:
+                return False
+        return True
 
     def counts_ok(self):
         """one small device->host read: did every level stay within its capacity, and every staged activation
@@ -230,12 +250,14 @@ class MultiWindowRunner:
                 lane.capture(frames_dev)
             torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self.supported = all(l.supported for l in self.lanes)
         return self
 
     def infer_windows_device(self, windows_dev):
         """windows_dev: up to `lanes` windows (lists of (positions, values) CUDA tensors).  Frame t of every
         window is issued before frame t+1 of any, so the streams interleave.  Returns the log-softmax of each
-        window's last frame; the caller's stream waits for all lanes."""
+        window's last frame; the caller's stream waits for all lanes.  The returned tensors are views of each lane's static
+        graph output: valid until that lane runs its next window (clone to keep)."""
         cur = torch.cuda.current_stream()
         outs = [None] * len(windows_dev)
         T = max(len(w) for w in windows_dev)
@@ -267,6 +289,11 @@ class MultiWindowRunner:
             self._host_out = {}
         wins, ticket = [], {"host": windows_host, "labels": [], "counts": [], "events": []}
         oversize = [any(p.shape[0] > self.lanes[i].caps["n"] for p, _ in w) for i, w in enumerate(windows_host)]
+        for i, w in enumerate(windows_host):   # a frame kind this lane has not captured yet (e.g. a 1-frame window)
+            kinds = {(t == 0, t == len(w) - 1) for t in range(len(w))}
+            if not oversize[i] and any(k not in self.lanes[i].graphs for k in kinds):
+                with torch.cuda.stream(self.streams[i]):
+                    self.lanes[i].capture([(p.to(dev), v.to(dev)) for p, v in w])
         for i, w in enumerate(windows_host):
             self.streams[i].wait_stream(cur)
             with torch.cuda.stream(self.streams[i]):
@@ -291,7 +318,7 @@ class MultiWindowRunner:
                 buf = self._host_out.get(key)
                 if buf is None or buf[0].shape[0] < n:
                     buf = (torch.empty(max(n, lane.caps["n"]), dtype=torch.int64).pin_memory(),
-                           torch.zeros(len(lane.caps["v"]) + 1, dtype=torch.int32).pin_memory())
+                           torch.zeros(4 * len(lane.caps["v"]) + 1, dtype=torch.int32).pin_memory())
                     self._host_out[key] = buf
                 buf[0][:n].copy_(lab, non_blocking=True)
                 lane._copy_checks(buf[1])

@@ -223,3 +223,61 @@ def test_alternative_operand_paths_agree(dev, lattice):
     for env in ({"LTN_CONV_ATMEM": "1"}, {"LTN_CONV_ATMEM": "0"}, {"LTN_CONV_CLUSTER": "4"}, {"LTN_CONV_CLUSTER": "2"}):
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Bit reproducibility: k_conv_tc writes `out` without atomics (one CTA owns each output tile, fixed k order), so the
+# same inputs must give the SAME BITS on every launch -- alone and with four streams hammering the kernel at once.
+# Every convolution shape of the KITTI model, both operand types, with and without the folded GroupNorm.  (The
+# epilogue's GroupNorm statistics ARE accumulated with atomics and are compared with a tolerance instead.)
+# ---------------------------------------------------------------------------------------------------------------
+MODEL_SHAPES = [  # (C, F, S): SURVEY.md B.10 -- convs, coarsen / finefy, 1x1 layers, GRU / AFlow dense layers
+    (128, 64, 9), (64, 64, 9), (64, 128, 9), (128, 128, 9), (128, 256, 9), (256, 128, 9), (192, 192, 9),
+    (256, 64, 1), (64, 256, 1), (192, 192, 1), (192, 96, 1), (128, 384, 1), (64, 192, 1), (192, 576, 1), (512, 256, 1)]
+
+
+@pytest.mark.parametrize("operands", ["f16", "tf32"])
+def test_conv_tc_is_bit_reproducible(dev, lattice, operands):
+    from temporal_latticenet_b200 import ops
+    ls, tab = lattice
+    V = tab.size()
+    nbr = ls.neighbours()
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    reps = 40
+    streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+    for C, F, S in MODEL_SHAPES:
+        if operands == "f16" and C % 64:
+            continue
+        g = torch.Generator().manual_seed(C * 7 + F * 3 + S)
+        x = torch.randn(V, C, generator=g).to(dev)
+        W = (torch.randn(S * C, F, generator=g) / (S * C) ** 0.5).to(dev)
+        wt = ops.k_major(W)
+        gamma, beta = torch.rand(C, generator=g).to(dev) + 0.5, torch.randn(C, generator=g).to(dev)
+        for folded in ((False, True) if C <= 256 else (False,)):
+            gn = (ops.gn_sums(x, ops.gn_groups(C)), gamma, beta, 1e-5) if folded else None
+            kw = dict(gn=gn, relu=folded, operands=operands, flag=flag)
+            first = ops.conv_tc(x, nbr if S == 9 else None, wt, **kw)
+            torch.cuda.synchronize()
+            for _ in range(reps):
+                again = ops.conv_tc(x, nbr if S == 9 else None, wt, **kw)
+                assert torch.equal(first, again), (C, F, S, folded, "sequential")
+            # four streams at once, each with its own output (and statistics) buffer
+            outs, sums = [], []
+            cur = torch.cuda.current_stream()
+            for s in streams:
+                s.wait_stream(cur)
+            for r in range(reps // 4):
+                for s in streams:
+                    with torch.cuda.stream(s):
+                        sm = torch.zeros(ops.gn_groups(F), 2, dtype=torch.float64, device=dev)
+                        outs.append(ops.conv_tc(x, nbr if S == 9 else None, wt, out_sums=sm, **kw))
+                        sums.append(sm)
+            for s in streams:
+                cur.wait_stream(s)
+            torch.cuda.synchronize()
+            want_sums = torch.stack([first.double().view(V, ops.gn_groups(F), -1).sum((0, 2)),
+                                     (first.double() ** 2).view(V, ops.gn_groups(F), -1).sum((0, 2))], 1)
+            for o, sm in zip(outs, sums):
+                assert torch.equal(first, o), (C, F, S, folded, "concurrent")
+                assert torch.allclose(sm, want_sums, rtol=1e-5, atol=1e-3), (C, F, S, folded, "statistics")
+    assert int(flag.item()) == 0

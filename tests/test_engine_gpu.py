@@ -259,3 +259,51 @@ def test_fp16_range_flag_reruns_the_window_with_tf32_operands():
     assert (out[1].numpy() == want.argmax(1)).mean() > 0.999
     assert (out[0].numpy() == b.argmax(1)).mean() > 0.999
     assert [l.fallbacks for l in multi.lanes] == [0, 1]
+
+
+def test_non_default_pointnet_widths_leave_the_graph_path(tmp_path):
+    """the static-capacity graphs rely on the FUSED PointNet front end (device-side row counts); a cfg with other widths
+    must run eagerly -- and correctly -- instead of reducing uninitialised padding rows (round-1 advisor finding)"""
+    import hjson
+    import os
+    from temporal_latticenet_b200.engine import GraphWindowRunner
+    from temporal_latticenet_b200.runner import WindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    with open(CFG) as f:
+        cfg = hjson.loads(f.read())
+    cfg["model"]["pointnet_layers"] = [16, 32, 32]
+    path = os.path.join(str(tmp_path), "cfg_widths.cfg")
+    with open(path, "w") as f:
+        f.write(hjson.dumps(cfg))
+    dev = torch.device("cuda:0")
+    w = _window(14, frames=3, n=3000)
+    fd = [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]
+    g = GraphWindowRunner(path, 26, dev).materialise_parameters(fd, seeded_state)
+    assert not g.supported
+    g.capture(fd)
+    eager = WindowRunner(path, 26, dev).materialise_parameters(fd, seeded_state)
+    want = eager.infer_window_device(fd)
+    for rep in range(2):
+        got = g.infer_window_device(fd)
+        assert len(g.graphs) == 0
+        assert float((got - want).abs().max()) < 1e-4 * float(want.abs().max())
+
+
+def test_submit_captures_a_frame_kind_it_has_not_seen():
+    """a 1-frame window (kind first-and-last) submitted to lanes prepared on 4-frame windows (round-1 advisor finding)"""
+    from temporal_latticenet_b200.engine import MultiWindowRunner
+    from temporal_latticenet_b200.runner import WindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    dev = torch.device("cuda:0")
+    w4 = _window(23, n=4000)
+    to_dev = lambda w: [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]  # noqa: E731
+    eager = WindowRunner(CFG, 26, dev).materialise_parameters(to_dev(w4), seeded_state)
+    multi = MultiWindowRunner(CFG, 26, dev, lanes=2).prepare(to_dev(w4), seeded_state)
+    w1 = w4[:1]
+    host = [[(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in w] for w in (w1, w4)]
+    labels = [l.clone() for l in multi.infer_windows(host)]
+    assert (True, True) in multi.lanes[0].graphs
+    for l, w in zip(labels, (w1, w4)):
+        want = eager.infer_window_device(to_dev(w)).argmax(1).cpu()
+        assert (l == want).float().mean() > 0.999
+    assert sum(l.fallbacks for l in multi.lanes) == 0

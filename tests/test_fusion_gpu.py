@@ -223,3 +223,37 @@ def test_pointnet_front_end_matches_float64(dev, kernel, order):
         assert np.array_equal(got[v, 64:][clear], bary[arg][clear].astype(np.float32).astype(np.float64)), v
         checked += int(clear.sum())
     assert checked > 32 * (cnt >= 4).sum()
+
+
+def test_scores_iou_matches_oracle():
+    """device-side IoU accumulation (callbacks/scores.py:13-47) against the pinned numpy oracle, on the golden clouds
+    and on one full-size cloud; the result also goes through the reference-named accessors"""
+    import os
+    from oracle.scores_oracle import ScoresOracle
+    from temporal_latticenet_b200.scores import Scores
+    from tests.helpers import GOLDEN
+    dev = torch.device("cuda:0")
+    z = np.load(os.path.join(GOLDEN, "scores.npz"))
+    for case in range(3):
+        nr_clouds, K, unl = [int(x) for x in z["c%d_meta" % case]]
+        s = Scores()
+        for i in range(nr_clouds):
+            s.accumulate_scores(torch.from_numpy(z["c%d_logits%d" % (case, i)]).to(dev), torch.from_numpy(z["c%d_gt%d" % (case, i)]).to(dev), unl)
+        assert s.intersection_per_class == z["c%d_inter" % case].tolist()
+        assert s.union_per_class == z["c%d_union" % case].tolist()
+        assert s.avg_class_iou() == float(z["c%d_avg" % case])
+        per = s.iou_per_class()
+        assert [per.get(i, -1.0) for i in range(K)] == z["c%d_per" % case].tolist()
+        s.update_best()
+        assert s.best_iou == float(z["c%d_avg" % case])
+    rng = np.random.default_rng(5)
+    n, K = 125000, 26
+    logits = rng.standard_normal((n, K)).astype(np.float32)
+    gt = rng.integers(0, K, n)
+    logits[np.arange(n), gt] += 1.0
+    s, o = Scores(), ScoresOracle()
+    for rep in range(2):
+        s.accumulate_scores(torch.from_numpy(logits).to(dev), torch.from_numpy(gt).to(dev), 0)
+        o.accumulate_scores(logits, gt, 0)
+    assert s.intersection_per_class == o.inter and s.union_per_class == o.union
+    assert s.compute_stats() == o.compute_stats()

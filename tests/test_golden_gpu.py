@@ -7,8 +7,9 @@ equal the reference's), reset_sequence(), fresh Lattice, the window is re-run.
 
 Bar: vertex counts and keys bit-exact (numbering is deterministic, so no canonicalisation is even
 needed; the sorted-key comparison is kept as the contract the north star states); features after
-~40 stacked fp32 GEMM layers within 2e-3 of the tensor's absolute maximum (fp32 accumulation order
-differs between cuBLAS / our kernels and the CPU BLAS that produced the goldens).
+~40 stacked fp32 GEMM layers within FEATURE_TOL of the tensor's absolute maximum (fp32 accumulation
+order differs between our kernels and the CPU BLAS that produced the goldens; the observed errors are
+printed, the tolerance is ~4x the largest one observed on the B200).
 """
 import json
 import os
@@ -22,7 +23,9 @@ from tests.helpers import CFG, GOLDEN, canonical_order, seeded_state
 
 pytestmark = pytest.mark.gpu
 
-FEATURE_TOL = 2e-3
+FEATURE_TOL = 1e-4   # rel 1e-4 for GEMM-containing chains; observed values are printed by the tests
+
+GRAD_TOL = 1e-2
 
 GOLDENS = ["gru_gru_aflow_gru", "lstm_cga_linear_maxpool", "maxpool_aflow_lstm_cga", "aflow_x4",
            "linear_none_none_gru", "single_frame"]
@@ -93,11 +96,14 @@ def test_window_matches_reference_golden(name, tmp_path):
         if "out%d" % i in z.files:
             got = outs[i][0].cpu().numpy()
             assert got.shape == z["out%d" % i].shape
-            assert _rel(got, z["out%d" % i]) < FEATURE_TOL, "late-fusion features of frame %d" % i
+            e = _rel(got, z["out%d" % i])
+            print("%s: late-fusion features of frame %d: err/absmax %.2e" % (name, i, e))
+            assert e < FEATURE_TOL, "late-fusion features of frame %d: %g" % (i, e)
     logits = outs[-1][1].cpu().numpy()
     assert logits.shape == z["logits"].shape
     assert np.isfinite(logits).all() == np.isfinite(z["logits"]).all()
     err = _rel(logits, z["logits"])
+    print("%s: logits err/absmax %.2e" % (name, err))
     assert err < FEATURE_TOL, "logits rel-to-absmax error %g" % err
     # class decisions: identical wherever the golden's top-2 margin exceeds the feature tolerance
     g = z["logits"]
@@ -110,7 +116,7 @@ def test_training_step_gradients_match_oracle_autograd(tmp_path):
     """BPTT through a 2-frame window (train_ln.py:163-233): every parameter gradient of the CUDA path
     (conv transpose-as-gather, slice_classify / gather backward kernels, scatter_max, GroupNorm) equals
     torch autograd over the oracle's unfused CPU graph with the same seeded weights, and one AdamW
-    step lowers the loss.  Tolerance: 1e-2 of each gradient's absolute maximum (fp32 accumulation order; observed <= 6e-3)."""
+    step lowers the loss.  Tolerance: GRAD_TOL of each gradient's absolute maximum (fp32 accumulation order; the largest observed is printed)."""
     from oracle import window_oracle as WO
     from temporal_latticenet_b200.config import ConfigParser
     from temporal_latticenet_b200.lattice import Lattice, ModelParams
@@ -150,11 +156,15 @@ def test_training_step_gradients_match_oracle_autograd(tmp_path):
     ls = WO.Lattice.create(cfg, "lattice")
     for i, (p, v) in enumerate(frames):
         out, _, ls = orc.model(ls, torch.from_numpy(p), torch.from_numpy(v), i != 1)
-    oloss = 0.5 * lovasz(out, target) + 0.5 * nll(out, target)
+    # the oracle side uses the oracle's OWN per-class restatement of the Lovasz-softmax loss (oracle/shims), not the product's
+    from latticenet_py.lattice.lovasz_loss import LovaszSoftmax as OracleLovasz
+    import latticenet_py
+    assert os.path.join("oracle", "shims") in os.path.abspath(latticenet_py.__file__ or latticenet_py.__path__[0])
+    oloss = 0.5 * OracleLovasz(ignore_index=0)(out, target) + 0.5 * nll(out, target)
     oloss.backward()
     assert abs(float(loss0) - float(oloss)) < 1e-4 * abs(float(oloss))
     ograds = {k: p.grad for k, p in orc.model.named_parameters()}
-    bad = []
+    bad, worst = [], 0.0
     for k, p in model.named_parameters():
         if ".AFLOW.weight" in k:
             continue  # quirk Q4: created, never used
@@ -162,8 +172,10 @@ def test_training_step_gradients_match_oracle_autograd(tmp_path):
         assert p.grad is not None and og is not None, k
         scale = float(og.abs().max()) + 1e-12
         err = float((p.grad.cpu() - og).abs().max()) / scale
-        if err > 1e-2:
+        worst = max(worst, err)
+        if err > GRAD_TOL:
             bad.append((k, err))
+    print("largest gradient error / absmax over all parameters: %.2e" % worst)
     assert not bad, bad
     opt.step()
     with torch.no_grad():

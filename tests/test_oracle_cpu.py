@@ -215,3 +215,42 @@ def test_host_logic_cfg_seeding_synthetic():
 def test_canonical_order_helper():
     k = np.array([[2, 0, 0], [0, 1, 0], [0, 0, 5]])
     assert canonical_order(k).tolist() == [2, 1, 0]
+
+
+def test_scores_oracle_matches_reference_golden():
+    """oracle/scores_oracle.py against the outputs of the reference's own callbacks/scores.py (tests/golden/make_scores_golden.py)"""
+    import os
+    from oracle.scores_oracle import ScoresOracle
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "scores.npz"))
+    for case in range(3):
+        nr_clouds, K, unl = [int(x) for x in z["c%d_meta" % case]]
+        s = ScoresOracle()
+        for i in range(nr_clouds):
+            s.accumulate_scores(z["c%d_logits%d" % (case, i)], z["c%d_gt%d" % (case, i)], unl)
+        assert s.inter == z["c%d_inter" % case].tolist()
+        assert s.union == z["c%d_union" % case].tolist()
+        avg, per = s.compute_stats()
+        assert avg == float(z["c%d_avg" % case])
+        assert [per.get(i, -1.0) for i in range(K)] == z["c%d_per" % case].tolist()
+
+
+def test_lovasz_matches_independent_oracle():
+    """the product's vectorised Lovasz-softmax (temporal_latticenet_b200/lovasz.py, plain torch) against the oracle's
+    per-class restatement (oracle/shims/latticenet_py/lattice/lovasz_loss.py): value and gradient"""
+    import torch
+    from oracle import window_oracle  # noqa: F401  (puts oracle/shims first on sys.path)
+    from latticenet_py.lattice.lovasz_loss import LovaszSoftmax as OracleLovasz
+    from temporal_latticenet_b200.lovasz import LovaszSoftmax
+    g = torch.Generator().manual_seed(0)
+    for n, k, ignore in ((500, 26, 0), (64, 5, None), (300, 20, 0)):
+        logits = torch.randn(n, k, generator=g, dtype=torch.float64)
+        target = torch.randint(0, k - 1, (n,), generator=g)   # the last class never occurs: absent classes are skipped
+        a = logits.clone().requires_grad_(True)
+        b = logits.clone().requires_grad_(True)
+        la = LovaszSoftmax(ignore)(torch.log_softmax(a, 1), target)
+        lb = OracleLovasz(ignore)(torch.log_softmax(b, 1), target)
+        assert abs(float(la) - float(lb)) < 1e-12
+        la.backward()
+        lb.backward()
+        assert float((a.grad - b.grad).abs().max()) < 1e-12
