@@ -57,15 +57,21 @@ class GraphWindowRunner(WindowRunner):
         caps = {"n": _round_up(n_max * 1.02 + 1024, 4096)}
         vcaps = [_round_up(c * self.headroom + 512, 1024) for c in counts]
         vcaps = [min(v, self.lattice.capacity) for v in vcaps]
-        # row classes must be told apart by their capacity alone; collisions are resolved DOWNWARDS so that a vertex
-        # capacity never exceeds the hash table's (the table clamps its counter there, and the overflow check
-        # `count < cap` must be able to fail)
+        # row classes must be told apart by their capacity alone: collisions move up by 1024 while that stays within the
+        # hash table's own capacity (the table clamps its counter there, and the overflow check `count < cap` must be
+        # able to fail), else down
         used = {caps["n"], 4 * caps["n"]}
         for i, v in enumerate(vcaps):
-            while v in used and v > 1024:
-                v -= 1024
-            if v in used or v > self.lattice.capacity or v < counts[i]:
-                self.supported = False   # no distinct capacity left below the table's: this window runs eagerly
+            up = v
+            while up in used:
+                up += 1024
+            if up <= self.lattice.capacity:
+                v = up
+            else:
+                while v in used and v > 1024:
+                    v -= 1024
+                if v in used or v <= counts[i]:
+                    self.supported = False   # no distinct capacity left below the table's: such windows run eagerly
             used.add(v)
             vcaps[i] = v
         caps["v"] = vcaps

@@ -23,9 +23,9 @@ from tests.helpers import CFG, GOLDEN, canonical_order, seeded_state
 
 pytestmark = pytest.mark.gpu
 
-FEATURE_TOL = 1e-4   # rel 1e-4 for GEMM-containing chains; observed values are printed by the tests
+FEATURE_TOL = 2e-4   # observed on the B200 (printed by the tests): 1.4e-5 ... 4.9e-5 over the six goldens; SURVEY 8(c) asks 1e-4-class for GEMM chains
 
-GRAD_TOL = 1e-2
+GRAD_TOL = 1e-2       # observed: 3.1e-3
 
 GOLDENS = ["gru_gru_aflow_gru", "lstm_cga_linear_maxpool", "maxpool_aflow_lstm_cga", "aflow_x4",
            "linear_none_none_gru", "single_frame"]

@@ -22,6 +22,8 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(REPO, "baseline", "_ref")
 SHIMS = os.path.join(REPO, "temporal_latticenet_b200", "shims")
 FILES = ("seq_lattice/models.py", "seq_lattice/lattice_modules.py", "cfgParser.py")
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
 
 
 def fixture_status():
@@ -42,7 +44,6 @@ def _import_reference():
     why = fixture_status()
     if why:
         raise RuntimeError(why)
-    sys.path.insert(0, REPO)
     sys.path.insert(0, REF)
     sys.path.insert(0, SHIMS)
     import latticenet
