@@ -158,7 +158,7 @@ def cpu_window_seconds(window, repeats=1):
     from oracle import window_oracle as WO
     torch.set_num_threads(os.cpu_count() or 1)
     runner = WO.OracleWindowRunner(CFG, NR_CLASSES)
-    runner.materialise_parameters(window[:1])
+    runner.materialise_parameters(window[:2])
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -177,7 +177,7 @@ def run_reference(args):
     from oracle import window_oracle as WO
     torch.set_num_threads(os.cpu_count() or 1)
     runner = WO.OracleWindowRunner(CFG, NR_CLASSES)
-    runner.materialise_parameters(window[:1])
+    runner.materialise_parameters(window[:2])
     for _ in range(args.warmup):
         runner.infer_window(window)
     t0 = time.perf_counter()

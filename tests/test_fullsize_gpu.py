@@ -117,6 +117,16 @@ OUTLIER_TOL = 5e-2
 def _cmp(name, got, want, tol=FULL_TOL):
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
     assert got.shape == want.shape, (name, got.shape, want.shape)
+    fin = np.isfinite(want)
+    if not fin.all():
+        # quirk Q5 (AFlow's 0/0 on vertices whose whole neighbourhood is zero rows, lattice_modules.py:321): the reference
+        # itself produces NaN there and GroupNorm spreads it; parity then means producing NaN in the same places
+        same = float((np.isfinite(got) == fin).mean())
+        print("%-28s oracle non-finite share %.4f, finite-mask agreement %.6f" % (name, 1.0 - float(fin.mean()), same))
+        assert same > 0.999, (name, same)
+        if not fin.any():
+            return None
+        got, want = got[fin & np.isfinite(got)], want[fin & np.isfinite(got)]
     scale = float(np.abs(want).max()) + 1e-30
     err = np.abs(got - want) / scale
     q999 = float(np.quantile(err, 0.999))
@@ -129,6 +139,10 @@ def _cmp(name, got, want, tol=FULL_TOL):
 
 
 def _decisions(name, got, want, tol=FULL_TOL):
+    ok = np.isfinite(want).all(1) & np.isfinite(got).all(1)
+    if not ok.any():
+        return
+    got, want = got[ok], want[ok]
     top2 = np.sort(want, 1)[:, -2:]
     clear = (top2[:, 1] - top2[:, 0]) > 4 * tol * np.abs(want).max()
     agree = float((got.argmax(1)[clear] == want.argmax(1)[clear]).mean())
@@ -139,7 +153,7 @@ def _decisions(name, got, want, tol=FULL_TOL):
 
 def _oracle_window(cfg, nr_classes, frames):
     from oracle import window_oracle as WO
-    orc = WO.OracleWindowRunner(cfg, nr_classes).materialise_parameters(frames[:1])
+    orc = WO.OracleWindowRunner(cfg, nr_classes).materialise_parameters(frames[:2])  # two frames: the t > 0 branches create AFlow's lazy parameters too
     collect = []
     out = orc.infer_window(frames, collect=collect)
     counts, lvl = [], orc.lattice
