@@ -362,7 +362,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="add a per-entry-point time breakdown (extra untimed pass)")
     ap.add_argument("--eager", action="store_true", help="eager per-op launches instead of CUDA-graph replay")
-    ap.add_argument("--lanes", type=int, default=4, help="independent windows in flight per GPU (one CUDA stream each)")
+    ap.add_argument("--lanes", type=int, default=4, help="independent windows in flight per GPU")
+    ap.add_argument("--streams", action="store_true", help="round-1 execution: one stream + one graph per window in flight "
+                    "(MultiWindowRunner) instead of the lock-step group graph with batched tensor-core launches (LockstepRunner)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer = BASELINE config 3 (headline); train = config 4 (BPTT + AdamW + NCCL gradient all-reduce)")
     args = ap.parse_args()
@@ -384,7 +386,7 @@ def main():
     import __graft_entry__ as G
     G.build()
     from temporal_latticenet_b200 import _lib
-    from temporal_latticenet_b200.engine import GraphWindowRunner, MultiWindowRunner
+    from temporal_latticenet_b200.engine import GraphWindowRunner, LockstepRunner, MultiWindowRunner
     from temporal_latticenet_b200.runner import WindowRunner
     from temporal_latticenet_b200.seeding import seeded_state
     lib = _lib.load()
@@ -403,7 +405,8 @@ def main():
     else:
         # default: static-capacity CUDA-graph replay of each frame (engine.py); capacities are planned on the
         # window with the most points and re-validated after every window (eager fallback when exceeded)
-        multi = MultiWindowRunner(CFG, NR_CLASSES, dev, lanes=max(1, args.lanes)).prepare(devw[0], seeded_state, devw)
+        Runner = MultiWindowRunner if args.streams else LockstepRunner
+        multi = Runner(CFG, NR_CLASSES, dev, lanes=max(1, args.lanes)).prepare(devw[0], seeded_state, devw)
         runner = multi.lanes[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -457,7 +460,10 @@ def main():
     launches = lib.ltn_launch_count() - launches0
     graph_mode = (not args.eager) and runner.supported
     if graph_mode:   # replayed graphs: the library's host-side counter saw the kernels once, at capture
-        launches = args.steps * runner.kernels_per_window(FRAMES)
+        if hasattr(multi, "kernels_per_group"):   # lock-step: one graph per frame kind covers all lanes
+            launches = (args.steps // lanes) * multi.kernels_per_group(FRAMES)
+        else:
+            launches = args.steps * runner.kernels_per_window(FRAMES)
         capacity_ok = multi.counts_ok()
     ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)

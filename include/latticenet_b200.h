@@ -143,6 +143,18 @@ int ltn_conv_tc_f16(const float* x, int Vx, const int* vx_dev, const int* nbr, i
                     int gn_groups, int relu, const float* bias, const float* res, float* out, int ldo, double* out_sums,
                     int out_groups, int* flag, void* stream);
 int ltn_split_f16(const float* w, int K, int F, int transposed_in, int w_log2, void* wt_hi, void* wt_lo, void* stream);
+/* ltn_conv_tc_f16 for nb <= 8 independent problems that share the weights -- the same layer of several windows in
+ * flight (SURVEY.md 8b "Threading: kernels must tolerate B lattices per launch").  One persistent launch walks the
+ * tiles of all problems; x / Vx / vx_dev / nbr / Vq / vq_dev / gn_sums / res / out / out_sums / flag are HOST arrays of nb
+ * entries (device pointers resp. ints), everything else is shared.  Results are bit-identical to nb calls of
+ * ltn_conv_tc_f16 (out; the statistics differ in summation order only). */
+int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const int* const* vx_dev, const int* const* nbr,
+                            const int* Vq, const int* const* vq_dev, int C, int S, const void* wt_hi, const void* wt_lo, int w_log2,
+                            int a_log2, int F, const double* const* gn_sums, const float* gn_gamma, const float* gn_beta,
+                            float gn_eps, int gn_groups, int relu, const float* bias, const float* const* res, float* const* out,
+                            int ldo, double* const* out_sums, int out_groups, int* const* flag, void* stream);
+/* per-CTA [start, end] globaltimer stamps of the following batched launches (NULL switches it off) */
+int ltn_conv_batched_trace(unsigned long long* buf);
 /* phase tracing of the following ltn_conv_tc* launches (NULL switches it off): buf receives 8 globaltimer stamps (ns)
  * per CTA in launch-grid order -- entry, set-up done, first operands staged, producers done, accumulator complete,
  * epilogue stores issued, teardown, (unused) */

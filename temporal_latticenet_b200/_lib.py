@@ -4,6 +4,7 @@ a missing CUDA device raises."""
 import ctypes
 import os
 import re
+import threading
 
 import torch
 
@@ -85,22 +86,26 @@ def check(rc, what):
 # of each lattice level) to the device int32 holding the live count; kernel wrappers look their row
 # counts up here and pass the pointer as the `*_dev` companion of the host bound.
 # ---------------------------------------------------------------------------------------------------
-_static_rows = {}
+# Per THREAD: the lock-step engine runs one host thread per window in flight while it captures a frame (engine.py).
+_static = threading.local()
+
+
+def _rows():
+    return getattr(_static, "rows", None) or {}
 
 
 def set_static_rows(mapping):
-    global _static_rows
-    _static_rows = dict(mapping or {})
+    _static.rows = dict(mapping or {})
 
 
 def static_mode():
-    return bool(_static_rows)
+    return bool(_rows())
 
 
 def rows_tensor(nr_rows):
-    return _static_rows.get(int(nr_rows))
+    return _rows().get(int(nr_rows))
 
 
 def rows_dev(nr_rows):
-    t = _static_rows.get(int(nr_rows))
+    t = _rows().get(int(nr_rows))
     return None if t is None else ctypes.c_void_p(t.data_ptr())

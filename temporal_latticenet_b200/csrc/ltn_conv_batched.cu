@@ -1,0 +1,565 @@
+// Fused lattice convolution for SEVERAL lattices per launch: persistent CTAs over one tile queue.
+//
+//   out_b[v, f] = sum_{s<S} sum_{c<C} act_b( x_b[nbr_b[v,s], c] ) * W[s*C + c, f]  (+ bias[f]) (+ res_b[v, f])      b < nb
+//
+// Same contraction, operands and numerics as k_conv_tc<3, ATMEM, F16> of ltn_conv.cu (fp16 hi/lo split, three
+// tcgen05 passes, A operand written from the gather registers straight into tensor memory, weights streamed by TMA):
+// each output tile sees the same MMAs in the same k order, so the two kernels agree BIT FOR BIT on `out`.
+// What changes is the shape of the launch (SURVEY.md 8b "Threading: B lattices per launch"):
+//  * one launch serves the same layer of all `nb` independent windows in flight (identical weights, per-window
+//    values / neighbour tables / GroupNorm statistics / device-side row counts in a small parameter table); the
+//    window runner used to issue one 108-172-CTA launch per window and layer, each a partial wave of one CTA per SM;
+//  * a fixed grid of at most one CTA per SM walks the tile list (problem, row tile, channel tile) round-robin, so
+//    barrier set-up, tensor-memory allocation and pipeline fill are paid once per CTA instead of once per tile, and the
+//    tail quantisation is that of ALL windows' tiles together;
+//  * warp-specialised roles with register reallocation (setmaxnreg): 2 producer warpgroups (gather -> tensor memory),
+//    1 epilogue warpgroup, and a fourth holding the MMA issuer, the TMA weight streamer and two "tile prologue" warps
+//    that stage the next tile's neighbour slice and folded GroupNorm affine while the producers work on the current one;
+//  * TWO accumulators in tensor memory: tile i's epilogue (TMEM -> registers -> swizzled transpose -> 128-byte lines,
+//    residual, output statistics) runs under tile i+1's main loop.
+#include "ltn_common.cuh"
+#include "ltn_conv_common.cuh"
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kKB = 64;               // fp16 K elements per k-block = one 128-byte swizzle row
+constexpr int kGroups = 2;            // producer warpgroups, alternate k-blocks
+constexpr int kMaxBatch = 8;
+constexpr int kThreadsB = 512;        // 4 warpgroups
+constexpr int kWarpEpi0 = 8, kWarpMma = 12, kWarpTma = 13, kWarpMeta0 = 14;
+constexpr int kMetaThreads = 64;
+constexpr int kMaxSA = 4, kMaxSB = 4;
+constexpr int kRegsProducer = 168, kRegsEpilogue = 96, kRegsAux = 56;
+
+struct BatchParams {
+    const float* x[kMaxBatch];        // [Vx_b, C]
+    const int* nbr[kMaxBatch];        // [Vq_b, S] or null
+    const double* gn_sums[kMaxBatch]; // [G,2] or null
+    const float* res[kMaxBatch];      // [Vq_b, F] or null
+    float* out[kMaxBatch];            // [Vq_b, ldo]
+    double* out_sums[kMaxBatch];      // [Gout,2] or null
+    const int* vq_dev[kMaxBatch];     // device-side row counts (nullable)
+    const int* vx_dev[kMaxBatch];
+    int* flag[kMaxBatch];             // fp16 range flags (nullable)
+    int Vq[kMaxBatch];
+    int Vx[kMaxBatch];
+    int nb;
+    const float* gn_gamma;
+    const float* gn_beta;
+    const float* bias;
+    float gn_eps;
+    int gn_cpg, out_cpg;
+    int C, S, F, ldo, relu, has_gn, has_sums;
+    int n_tile, ny;
+    int stages_a, stages_b, acc_bufs, acc_stride;
+    float a_mul, out_mul;
+    unsigned long long* trace;        // nullable: per CTA [tiles done, first tile start, last tile end] (globaltimer)
+};
+
+struct Tile {
+    int b, row0, n0, N, Nmma;
+};
+
+unsigned long long* g_trace_b = nullptr;
+
+__global__ void __launch_bounds__(kThreadsB, 1)
+k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                  const __grid_constant__ BatchParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // barriers: a_full[4] a_empty[4] b_full[4] b_empty[4] acc_full[2] acc_empty[2] meta_full[2] meta_empty[2]
+    __shared__ __align__(8) uint64_t bars[2 * kMaxSA + 2 * kMaxSB + 8];
+    __shared__ uint32_t tmem_slot;
+    __shared__ int s_prefix[kMaxBatch + 1];   // row tiles before problem b
+    __shared__ int s_vq[kMaxBatch], s_vx[kMaxBatch];
+    __shared__ __align__(16) float s_affine[2][512];          // per meta buffer: scale [256] | shift [256]
+    __shared__ int s_nbr[2][LTN_FEXT * kBlockM];              // per meta buffer: [slot][tile row], -1 = absent
+    __shared__ float s_colsum[2][512];                        // per tile parity: column sums [256] | sums of squares [256]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < p.nb) {
+        s_vq[tid] = p.vq_dev[tid] ? min(p.Vq[tid], __ldg(p.vq_dev[tid])) : p.Vq[tid];
+        s_vx[tid] = p.vx_dev[tid] ? min(p.Vx[tid], __ldg(p.vx_dev[tid])) : p.Vx[tid];
+    }
+    for (int i = tid; i < 2 * 512; i += kThreadsB) (&s_colsum[0][0])[i] = 0.f;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int b = 0; b < p.nb; ++b) {
+            s_prefix[b] = acc;
+            acc += (max(s_vq[b], 0) + kBlockM - 1) / kBlockM;
+        }
+        for (int b = p.nb; b <= kMaxBatch; ++b) s_prefix[b] = acc;
+    }
+    __syncthreads();
+    const int total_tiles = s_prefix[p.nb] * p.ny;
+    if ((int)blockIdx.x >= total_tiles) return;   // uniform per CTA, before any barrier / tensor-memory allocation
+
+    const int C = p.C, S = p.S;
+    const int num_kb = S * C / kKB;
+    const int kb_per_slot = C / kKB;
+    const int SA = p.stages_a, SB = p.stages_b;
+    const uint32_t b_bytes = (uint32_t)p.n_tile * 128u, b_stage = 2u * b_bytes;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smem_epi = smem + (size_t)SB * b_stage;   // 4 x 4 KB: one transpose block per epilogue warp
+
+    const uint32_t bar_afull = smem_u32(&bars[0]), bar_aempty = smem_u32(&bars[kMaxSA]);
+    const uint32_t bar_bfull = smem_u32(&bars[2 * kMaxSA]), bar_bempty = smem_u32(&bars[2 * kMaxSA + kMaxSB]);
+    const uint32_t bar_accfull = smem_u32(&bars[2 * kMaxSA + 2 * kMaxSB]), bar_accempty = bar_accfull + 16;
+    const uint32_t bar_metafull = bar_accfull + 32, bar_metaempty = bar_accfull + 48;
+    const uint32_t a_col0 = (uint32_t)(p.acc_bufs * p.acc_stride);   // A ring behind the accumulators, 64 columns per stage
+    constexpr uint32_t kTmemCols = 512;
+
+    auto tile_at = [&](int it, Tile& t) -> bool {
+        const int idx = (int)blockIdx.x + it * (int)gridDim.x;
+        if (idx >= total_tiles) return false;
+        const int n = idx % p.ny, r = idx / p.ny;
+        int b = 0;
+        while (b + 1 < p.nb && r >= s_prefix[b + 1]) ++b;
+        t.b = b;
+        t.row0 = (r - s_prefix[b]) * kBlockM;
+        t.n0 = n * p.n_tile;
+        t.N = min(p.n_tile, p.F - t.n0);
+        t.Nmma = (t.N + 15) & ~15;
+        return true;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < SA; ++s) {
+            mbar_init(bar_afull + 8 * s, 4);      // one arrive per gather warp of the owning group
+            mbar_init(bar_aempty + 8 * s, 1);     // tcgen05.commit
+        }
+        for (int s = 0; s < SB; ++s) {
+            mbar_init(bar_bfull + 8 * s, 1);      // the TMA thread's expect_tx arrive
+            mbar_init(bar_bempty + 8 * s, 1);     // tcgen05.commit
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_accfull + 8 * s, 1);    // tcgen05.commit
+            mbar_init(bar_accempty + 8 * s, 4);   // the four epilogue warps
+            mbar_init(bar_metafull + 8 * s, 2);   // the two tile-prologue warps
+            mbar_init(bar_metaempty + 8 * s, 8);  // the eight gather warps
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kWarpMma) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    unsigned long long t_first = 0;
+    if (p.trace && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_first));
+
+    if (warp < kWarpEpi0) {
+        // ===================== producers: gather A rows into tensor memory ==================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+        const int group = warp >> 2;
+        const int wrow0 = (warp & 3) * 32;
+        const int ra = lane >> 2, cq = lane & 3;
+        const uint32_t c4 = (uint32_t)C >> 2;
+        const float a_mul = p.a_mul;
+        int c_stage = group % SA;
+        uint32_t c_par = 1u;
+        uint32_t kb_base = 0;
+        for (int it = 0;; ++it) {
+            Tile t;
+            if (!tile_at(it, t)) break;
+            const int q = it & 1;
+            if (lane == 0) mbar_wait(bar_metafull + 8 * q, (uint32_t)(it >> 1) & 1u);
+            __syncwarp();
+            const int* nbr_s = s_nbr[q];
+            const float* aff = s_affine[q];
+            const float4* x4 = reinterpret_cast<const float4*>(p.x[t.b]);
+            const bool affine = p.has_gn != 0;
+            const int first = (group + (int)(kb_base & 1u)) & 1;   // this group owns the k-blocks of its parity in the GLOBAL sequence
+            float4 buf[2][8];
+            uint32_t bmask[2];
+            uint32_t rowidx[4];
+            uint32_t rmask = 0;
+            float amax = 0.f;
+            int i_slot = first / kb_per_slot, i_c0 = (first - i_slot * kb_per_slot) * kKB, i_cur = -1;
+            int c_c0 = i_c0;
+            auto issue = [&](float4* dst, uint32_t& dmask, const int half) {
+                if (i_slot != i_cur) {
+                    i_cur = i_slot;
+                    const int* tap = nbr_s + i_slot * kBlockM + wrow0 + ra;
+                    rmask = 0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int sv = tap[8 * r];
+                        rowidx[r] = (uint32_t)(sv >= 0 ? sv : 0) * c4 + (uint32_t)cq;   // row 0 stands in for an absent neighbour
+                        rmask |= (sv >= 0 ? 1u : 0u) << r;
+                    }
+                }
+                const uint32_t o = (uint32_t)i_c0 >> 2;
+                dmask = half ? (rmask >> 2) : rmask;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t ri = (half ? rowidx[2 + h] : rowidx[h]) + o;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) dst[4 * h + g] = __ldg(x4 + ri + 4 * g);
+                }
+                if (!half) return;
+                i_c0 += kGroups * kKB;
+                while (i_c0 >= C) { i_c0 -= C; ++i_slot; }
+            };
+            auto consume = [&](const float4* cur, uint32_t cmask, const int half) {
+                if (half == 0) {
+                    if (lane == 0) mbar_wait(bar_aempty + 8 * c_stage, c_par);
+                    __syncwarp();
+                    tc_fence_after();
+                }
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float4 sc = make_float4(a_mul, a_mul, a_mul, a_mul), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (affine) {
+                        sc = *reinterpret_cast<const float4*>(aff + c_c0 + 16 * g + 4 * cq);
+                        sh = *reinterpret_cast<const float4*>(aff + 256 + c_c0 + 16 * g + 4 * cq);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float4 v = cur[4 * h + g];
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                        if (p.relu) { v.x = relu_nan(v.x); v.y = relu_nan(v.y); v.z = relu_nan(v.z); v.w = relu_nan(v.w); }
+                        if (!((cmask >> h) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);   // absent neighbour / row beyond the tile
+                        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                        const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+                        hi[4 * g + 2 * h] = *reinterpret_cast<const uint32_t*>(&h01);
+                        hi[4 * g + 2 * h + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                        lo[4 * g + 2 * h] = *reinterpret_cast<const uint32_t*>(&l01);
+                        lo[4 * g + 2 * h + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+                    }
+                }
+                const uint32_t ta = tmem_base + ((uint32_t)(wrow0 + 16 * half) << 16) + a_col0 + (uint32_t)c_stage * 64u;
+                tmem_st_16x256b_x4(ta, hi);
+                tmem_st_16x256b_x4(ta + 32u, lo);
+                if (half == 0) return;
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_afull + 8 * c_stage);
+                c_c0 += kGroups * kKB;
+                while (c_c0 >= C) c_c0 -= C;
+                c_stage += kGroups;
+                while (c_stage >= SA) { c_stage -= SA; c_par ^= 1u; }
+            };
+            if (first < num_kb) issue(buf[0], bmask[0], 0);
+            for (int kb = first; kb < num_kb; kb += kGroups) {
+                issue(buf[1], bmask[1], 1);
+                consume(buf[0], bmask[0], 0);
+                if (kb + kGroups < num_kb) issue(buf[0], bmask[0], 0);
+                consume(buf[1], bmask[1], 1);
+            }
+            if (p.flag[t.b] && !(amax < 65504.f)) atomicOr(p.flag[t.b], 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_metaempty + 8 * q);   // this warp no longer reads the tile's neighbour slice / affine
+            kb_base += (uint32_t)num_kb;
+        }
+    } else if (warp < kWarpMma) {
+        // ===================== epilogue warpgroup: TMEM -> registers -> global ==============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
+        const int qd = warp & 3;
+        const int et = tid - kWarpEpi0 * 32;   // 0..127
+        const int chunk = lane & 7, sub = lane >> 3;
+        float* stage = reinterpret_cast<float*>(smem_epi + qd * 4096);
+        const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
+        const float out_mul = p.out_mul;
+        for (int it = 0;; ++it) {
+            Tile t;
+            if (!tile_at(it, t)) break;
+            const int a = it % p.acc_bufs, use = it / p.acc_bufs;
+            if (lane == 0) mbar_wait(bar_accfull + 8 * a, (uint32_t)use & 1u);
+            __syncwarp();
+            tc_fence_after();
+            const int Vq = s_vq[t.b];
+            float* out = p.out[t.b];
+            const float* res = p.res[t.b];
+            float* colsum = s_colsum[it & 1];
+            for (int cb = 0; cb < t.N; cb += 32) {
+                float acc[32];
+                tmem_ld32(t_lane + (uint32_t)(a * p.acc_stride + cb), acc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                        make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                __syncwarp();
+                const bool col_ok = 4 * chunk < t.N - cb;
+                const int col = t.n0 + cb + 4 * chunk;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq2 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i8 = 0; i8 < 8; ++i8) {
+                    const int r = i8 * 4 + sub;
+                    const int v = t.row0 + qd * 32 + r;
+                    float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((chunk ^ (r & 7)) << 2));
+                    o.x *= out_mul; o.y *= out_mul; o.z *= out_mul; o.w *= out_mul;   // exact: power of two
+                    o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                    if (v < Vq && col_ok) {
+                        if (res) {
+                            const float4 rr = __ldg(reinterpret_cast<const float4*>(res + (size_t)v * p.F + col));
+                            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                        }
+                        *reinterpret_cast<float4*>(out + (size_t)v * p.ldo + col) = o;
+                        cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+                        cq2.x = fmaf(o.x, o.x, cq2.x); cq2.y = fmaf(o.y, o.y, cq2.y); cq2.z = fmaf(o.z, o.z, cq2.z); cq2.w = fmaf(o.w, o.w, cq2.w);
+                    }
+                }
+                __syncwarp();   // the block is consumed before the next chunk overwrites it
+                if (p.has_sums) {
+#pragma unroll
+                    for (int o = 8; o <= 16; o <<= 1) {
+                        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+                        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+                        cq2.x += __shfl_xor_sync(0xffffffffu, cq2.x, o); cq2.y += __shfl_xor_sync(0xffffffffu, cq2.y, o);
+                        cq2.z += __shfl_xor_sync(0xffffffffu, cq2.z, o); cq2.w += __shfl_xor_sync(0xffffffffu, cq2.w, o);
+                    }
+                    if (sub == 0 && col_ok) {
+                        float* sc = colsum + cb + 4 * chunk;
+                        atomicAdd(sc, cs.x); atomicAdd(sc + 1, cs.y); atomicAdd(sc + 2, cs.z); atomicAdd(sc + 3, cs.w);
+                        atomicAdd(sc + 256, cq2.x); atomicAdd(sc + 257, cq2.y); atomicAdd(sc + 258, cq2.z); atomicAdd(sc + 259, cq2.w);
+                    }
+                }
+            }
+            // the accumulator has been read: hand it back to the MMA issuer before the statistics are flushed
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_accempty + 8 * a);
+            if (p.has_sums) {
+                // per-tile column sums -> group sums -> one double atomic per group; the buffer of this tile parity is
+                // cleared here and next used two tiles later, after the next tile's barrier
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                double* osums = p.out_sums[t.b];
+                const int g0 = t.n0 / p.out_cpg, g1 = (t.n0 + t.N) / p.out_cpg;   // n_tile is a multiple of out_cpg
+                for (int g = g0 + et; g < g1; g += 128) {
+                    float sa = 0.f, sb = 0.f;
+                    for (int c = g * p.out_cpg - t.n0; c < (g + 1) * p.out_cpg - t.n0; ++c) {
+                        sa += colsum[c]; sb += colsum[256 + c];
+                        colsum[c] = 0.f; colsum[256 + c] = 0.f;
+                    }
+                    if (osums) {
+                        atomicAdd(osums + 2 * g, (double)sa);
+                        atomicAdd(osums + 2 * g + 1, (double)sb);
+                    }
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));
+        if (warp == kWarpMma) {
+            // ===================== MMA issuer: one thread ================================================
+            if (lane == 0) {
+                int sa = 0, sb = 0;
+                uint32_t pa = 0, pb = 0;
+                for (int it = 0;; ++it) {
+                    Tile t;
+                    if (!tile_at(it, t)) break;
+                    const int a = it % p.acc_bufs, use = it / p.acc_bufs;
+                    mbar_wait(bar_accempty + 8 * a, ((uint32_t)use & 1u) ^ 1u);   // the epilogue has drained this accumulator
+                    tc_fence_after();
+                    // instruction descriptor: D = F32 [4,6), A / B = F16 (0) [7,10) [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+                    const uint32_t idesc = (1u << 4) | ((uint32_t)(t.Nmma >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+                    const uint32_t td = tmem_base + (uint32_t)(a * p.acc_stride);
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(bar_bfull + 8 * sb, pb);
+                        mbar_wait(bar_afull + 8 * sa, pa);
+                        tc_fence_after();
+                        const uint32_t bb = smem_u32(smem + (size_t)sb * b_stage);
+                        const uint64_t b_hi = make_desc(bb), b_lo = make_desc(bb + b_bytes);
+                        const uint32_t ta = tmem_base + a_col0 + (uint32_t)sa * 64u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            umma_ts<true>(td, ta + k * 8, b_hi + adv, idesc, (kb | k) != 0);
+                            umma_ts<true>(td, ta + 32u + k * 8, b_hi + adv, idesc, 1);
+                            umma_ts<true>(td, ta + k * 8, b_lo + adv, idesc, 1);
+                        }
+                        umma_commit(bar_aempty + 8 * sa);
+                        umma_commit(bar_bempty + 8 * sb);
+                        if (++sa == SA) { sa = 0; pa ^= 1u; }
+                        if (++sb == SB) { sb = 0; pb ^= 1u; }
+                    }
+                    umma_commit(bar_accfull + 8 * a);
+                }
+            }
+            __syncwarp();
+        } else if (warp == kWarpTma) {
+            // ===================== TMA: stream the pre-split weight tiles, continuously across tiles ===========
+            if (lane == 0) {
+                int sb = 0;
+                uint32_t pb = 1u;
+                for (int it = 0;; ++it) {
+                    Tile t;
+                    if (!tile_at(it, t)) break;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(bar_bempty + 8 * sb, pb);
+                        const uint32_t bb = smem_u32(smem + (size_t)sb * b_stage);
+                        mbar_arrive_expect_tx(bar_bfull + 8 * sb, b_stage);
+                        tma_load_2d(bb, &map_hi, bar_bfull + 8 * sb, kb * kKB, t.n0);
+                        tma_load_2d(bb + b_bytes, &map_lo, bar_bfull + 8 * sb, kb * kKB, t.n0);
+                        if (++sb == SB) { sb = 0; pb ^= 1u; }
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+            // ===================== tile prologue: neighbour slice + folded GroupNorm of the NEXT tiles ========
+            const int mt = tid - kWarpMeta0 * 32;   // 0..63
+            for (int it = 0;; ++it) {
+                Tile t;
+                if (!tile_at(it, t)) break;
+                const int q = it & 1;
+                if (lane == 0) mbar_wait(bar_metaempty + 8 * q, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                __syncwarp();
+                const int Vq = s_vq[t.b], Vx = s_vx[t.b];
+                const int* nbr = p.nbr[t.b];
+                int* dst = s_nbr[q];
+                for (int i = mt; i < kBlockM * S; i += kMetaThreads) {
+                    const int r = i / S, sl = i - r * S;
+                    int sv = -1;
+                    if (t.row0 + r < Vq) sv = nbr ? __ldg(nbr + (size_t)t.row0 * S + i) : t.row0 + r;
+                    if (sv >= Vx) sv = -1;
+                    dst[sl * kBlockM + r] = sv;
+                }
+                if (p.has_gn) {
+                    const double* sums = p.gn_sums[t.b];
+                    float* aff = s_affine[q];
+                    for (int c = mt; c < C; c += kMetaThreads) {
+                        const int g = c / p.gn_cpg;
+                        const double n = (double)Vx * p.gn_cpg;
+                        const double mean = sums[2 * g] / n;
+                        double var = sums[2 * g + 1] / n - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        const float rstd = (float)(1.0 / sqrt(var + (double)p.gn_eps));
+                        const float sc = rstd * (p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.0f);
+                        const float sh = (p.gn_beta ? __ldg(p.gn_beta + c) : 0.0f) - (float)mean * sc;
+                        aff[c] = sc * p.a_mul;
+                        aff[256 + c] = sh * p.a_mul;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_metafull + 8 * q);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWarpMma) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+    if (p.trace && tid == 0) {
+        unsigned long long t_last;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
+        p.trace[(size_t)blockIdx.x * 2] = t_first;
+        p.trace[(size_t)blockIdx.x * 2 + 1] = t_last;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ltn_conv_batched_trace(unsigned long long* buf) {
+    g_trace_b = buf;
+    return 0;
+}
+
+// The fp16-operand fused convolution of ltn_conv_tc_f16 for nb <= 8 independent problems that share the weights (the same
+// layer of several windows in flight): every per-problem argument is a HOST array of nb entries.  Requirements as
+// ltn_conv_tc_f16 (C % 64 == 0, C <= 256 with a folded GroupNorm, F % 8 == 0, ldo % 4 == 0); an explicit a_scale/a_shift
+// affine is not offered here.
+int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const int* const* vx_dev, const int* const* nbr,
+                            const int* Vq, const int* const* vq_dev, int C, int S, const void* wt_hi, const void* wt_lo, int w_log2,
+                            int a_log2, int F, const double* const* gn_sums, const float* gn_gamma, const float* gn_beta,
+                            float gn_eps, int gn_groups, int relu, const float* bias, const float* const* res, float* const* out,
+                            int ldo, double* const* out_sums, int out_groups, int* const* flag, void* stream) {
+    if (nb <= 0) return 0;
+    if (nb > kMaxBatch) return -2;
+    const bool has_nbr = nbr && nbr[0];
+    const bool has_gn = gn_sums && gn_sums[0];
+    const bool has_sums = out_sums && out_sums[0];
+    if (C <= 0 || C % kKB || (has_gn && C > 256) || F <= 0 || F % 8 || S < 1 || ldo % 4) return -2;
+    if (has_gn && (gn_groups <= 0 || C % gn_groups)) return -2;
+    if (has_sums && (out_groups <= 0 || F % out_groups)) return -2;
+    if (!wt_hi || !wt_lo) return -2;
+    static BatchParams p;   // ~700 bytes, filled per launch (single host thread per process: see SURVEY.md 8b "Threading")
+    memset(&p, 0, sizeof(p));
+    long long row_tiles = 0;
+    int live = 0;
+    for (int b = 0; b < nb; ++b) {
+        if (Vq[b] <= 0) continue;
+        if (Vx[b] <= 0) return -2;   // row 0 of x must be readable (stand-in address of absent neighbours)
+        if ((nbr && nbr[b] != nullptr) != has_nbr || (gn_sums && gn_sums[b] != nullptr) != has_gn ||
+            (out_sums && out_sums[b] != nullptr) != has_sums)
+            return -2;   // the problems of one launch share their structure
+        p.x[live] = x[b]; p.nbr[live] = has_nbr ? nbr[b] : nullptr; p.gn_sums[live] = has_gn ? gn_sums[b] : nullptr;
+        p.res[live] = res ? res[b] : nullptr; p.out[live] = out[b]; p.out_sums[live] = has_sums ? out_sums[b] : nullptr;
+        p.vq_dev[live] = vq_dev ? vq_dev[b] : nullptr; p.vx_dev[live] = vx_dev ? vx_dev[b] : nullptr;
+        p.flag[live] = flag ? flag[b] : nullptr;
+        p.Vq[live] = Vq[b]; p.Vx[live] = Vx[b];
+        row_tiles += (Vq[b] + kBlockM - 1) / kBlockM;
+        ++live;
+    }
+    if (live == 0) return 0;
+    p.nb = live;
+    p.gn_gamma = gn_gamma; p.gn_beta = gn_beta; p.bias = bias; p.gn_eps = gn_eps;
+    p.gn_cpg = has_gn ? C / gn_groups : 1;
+    p.out_cpg = has_sums ? F / out_groups : 1;
+    p.C = C; p.S = has_nbr ? S : 1; p.F = F; p.ldo = ldo; p.relu = relu; p.has_gn = has_gn ? 1 : 0; p.has_sums = has_sums ? 1 : 0;
+    p.a_mul = ldexpf(1.0f, a_log2);
+    p.out_mul = ldexpf(1.0f, -(a_log2 + w_log2));
+    p.trace = g_trace_b;
+    // Output channels per tile: at most 192, so that TWO accumulators and an A ring of >= 2 stages fit the 512 columns of
+    // tensor memory; fewer when the tile list would leave SMs idle (small levels).
+    static const int n_cap = []() { const char* e = getenv("LTN_CONVB_NCAP"); return e && atoi(e) >= 16 ? atoi(e) : 192; }();
+    const int unit = has_sums ? lcm16(p.out_cpg) : 16;
+    int ny = (F + n_cap - 1) / n_cap;
+    while (row_tiles * (ny + 1) <= 148 && (F / (ny + 1)) >= 32) ++ny;
+    int n_tile = ((F + ny - 1) / ny + unit - 1) / unit * unit;
+    if (n_tile > n_cap) n_tile = n_cap / unit * unit;
+    if (n_tile <= 0) return -2;
+    ny = (F + n_tile - 1) / n_tile;
+    p.n_tile = n_tile;
+    p.ny = ny;
+    const int nmma = (n_tile + 15) & ~15;
+    p.acc_stride = (nmma + 31) & ~31;
+    static const int want_bufs = []() { const char* e = getenv("LTN_CONVB_ACC"); return e ? atoi(e) : 2; }();
+    p.acc_bufs = (want_bufs >= 2 && 2 * p.acc_stride + 2 * 64 <= 512) ? 2 : 1;
+    int sa = (512 - p.acc_bufs * p.acc_stride) / 64;
+    if (sa > kMaxSA) sa = kMaxSA;
+    sa &= ~1;   // the two producer groups own alternate stages
+    if (sa < 2) return -3;
+    p.stages_a = sa;
+    const size_t b_stage = 2 * (size_t)n_tile * 128;
+    static const int sb_cap = []() { const char* e = getenv("LTN_CONVB_SB"); return e && atoi(e) >= 2 ? atoi(e) : kMaxSB; }();
+    int sb = (int)((190 * 1024) / b_stage);
+    if (sb > kMaxSB) sb = kMaxSB;
+    if (sb > sb_cap) sb = sb_cap;
+    if (sb < 2) return -3;
+    p.stages_b = sb;
+    const size_t smem = (size_t)sb * b_stage + 4 * 4096 + 1024;
+    alignas(64) CUtensorMap map_hi, map_lo;
+    int rc = make_weight_map(&map_hi, wt_hi, F, p.S * C, n_tile, true);
+    if (rc) return rc;
+    rc = make_weight_map(&map_lo, wt_lo, F, p.S * C, n_tile, true);
+    if (rc) return rc;
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    long long tiles = row_tiles * ny;
+    static const int grid_cap = []() { const char* e = getenv("LTN_CONVB_GRID"); return e && atoi(e) >= 1 ? atoi(e) : 148; }();
+    const int grid = (int)(tiles < grid_cap ? tiles : grid_cap);
+    k_conv_tc_batched<<<grid, kThreadsB, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

@@ -368,3 +368,295 @@ class MultiWindowRunner:
 
     def counts_ok(self):
         return all(l.counts_ok() for l in self.lanes)
+
+
+class _LockstepCoordinator:
+    """Runs the frame code of several lanes as host threads that hand a baton around: a lane runs until its next
+    batchable convolution (ops.conv_tc -> request()) or the end of its frame, then the next lane runs.  When every lane
+    has deposited its request the coordinator (the calling thread) joins the lane streams into the main stream, issues
+    ONE batched launch there and lets the lane streams continue behind it.  Only used while a frame is being CAPTURED
+    (or warmed up): replays involve no Python at all."""
+
+    def __init__(self, main_stream, lane_streams):
+        import threading
+        self.main, self.streams = main_stream, lane_streams
+        self.n = len(lane_streams)
+        self.go = [threading.Semaphore(0) for _ in range(self.n)]
+        self.back = threading.Semaphore(0)
+        self.pending = [None] * self.n
+        self.finished = [False] * self.n
+        self.errors = [None] * self.n
+        self.results = [None] * self.n
+        self.batched_launches = 0
+        self._tl = threading.local()
+
+    # ---- lane side -------------------------------------------------------------------------------------------------
+    def request(self, req):
+        i = self._tl.lane
+        ev = torch.cuda.Event()
+        ev.record(self.streams[i])          # everything this request reads has been queued on the lane's stream
+        self.pending[i] = (req, ev)
+        self.back.release()
+        self.go[i].acquire()
+        done = self.pending[i]
+        self.pending[i] = None
+        self.streams[i].wait_event(done)    # the lane continues behind the batched launch
+
+    def _lane_main(self, i, fn):
+        self._tl.lane = i
+        self.go[i].acquire()
+        try:
+            ops._BATCH.ctx = self
+            with torch.cuda.stream(self.streams[i]):
+                self.results[i] = fn(i)
+        except BaseException as e:  # noqa: BLE001 -- handed to the coordinating thread
+            self.errors[i] = e
+        finally:
+            ops._BATCH.ctx = None
+            self.finished[i] = True
+            self.back.release()
+
+    # ---- coordinator side ------------------------------------------------------------------------------------------
+    def run(self, fn):
+        """fn(lane_index) runs in lane i's thread with lane i's stream current; returns the list of results"""
+        import threading
+        threads = [threading.Thread(target=self._lane_main, args=(i, fn), daemon=True) for i in range(self.n)]
+        for t in threads:
+            t.start()
+        fork = torch.cuda.Event()
+        fork.record(self.main)
+        for s in self.streams:
+            s.wait_event(fork)
+        while True:
+            for i in range(self.n):
+                if not self.finished[i]:
+                    self.go[i].release()
+                    self.back.acquire()
+            if any(e is not None for e in self.errors):
+                break
+            waiting = [i for i in range(self.n) if not self.finished[i]]
+            if not waiting:
+                break
+            if len(waiting) != self.n:
+                self.errors[waiting[0]] = RuntimeError("lock-step lanes diverged: some finished their frame while others wait at a layer")
+                break
+            for i in waiting:
+                self.main.wait_event(self.pending[i][1])
+            with torch.cuda.stream(self.main):
+                ops.conv_tc_batched([self.pending[i][0] for i in waiting])
+                done = torch.cuda.Event()
+                done.record(self.main)
+            self.batched_launches += 1
+            for i in waiting:
+                self.pending[i] = done
+        failed = next((e for e in self.errors if e is not None), None)
+        if failed is not None:
+            for i in range(self.n):          # let the surviving lane threads run to their end without batching
+                while not self.finished[i]:
+                    self.pending[i] = torch.cuda.Event()
+                    self.go[i].release()
+                    self.back.acquire()
+            raise failed
+        for t in threads:
+            t.join()
+        for s in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            self.main.wait_event(ev)
+        return self.results
+
+
+class LockstepRunner:
+    """`lanes` independent windows advance through their frames TOGETHER on one GPU: one CUDA graph per frame kind
+    covers all lanes, and every tensor-core layer is ONE persistent launch over the tiles of all lanes
+    (csrc/ltn_conv_batched.cu) instead of one partial-wave launch per lane -- SURVEY.md 8(b) "B lattices per launch".
+    Everything else of a lane (hash build, PointNet, GroupNorm statistics, gates, AFlow, slicing) stays on that lane's
+    own stream inside the graph, so those small kernels of different windows still overlap.
+
+    Each lane is a GraphWindowRunner (own model copy, lattice, hidden-state buffers, static capacities); windows that
+    do not fit the static capacities, and groups smaller than `lanes`, go through the lanes' own per-window paths."""
+
+    def __init__(self, cfg_path, nr_classes=26, device=None, lanes=4, operands="f16"):
+        if lanes < 1 or lanes > ops.MAX_BATCH:
+            raise RuntimeError("between 1 and %d lanes" % ops.MAX_BATCH)
+        self.lanes = [GraphWindowRunner(cfg_path, nr_classes, device, operands=operands) for _ in range(lanes)]
+        self.device = self.lanes[0].device
+        self.main = torch.cuda.Stream(device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(lanes)]
+        self.supported = self.lanes[0].supported
+        self.graphs = {}       # frame kind -> (graph, [per-lane static output])
+        self.kernels = {}      # frame kind -> kernel launches inside the graph (all lanes)
+        self.batched = {}      # frame kind -> batched tensor-core launches among them
+        self.pool = None
+        self._host_out = {}
+        self._slot = 0
+
+    # ---- preparation -----------------------------------------------------------------------------------------------
+    def prepare(self, frames_dev, state_dict_fn, plan_windows=None):
+        for lane in self.lanes:
+            lane.materialise_parameters(frames_dev, state_dict_fn)
+            for w in (plan_windows or [frames_dev]):
+                if lane.caps is None or max(p.shape[0] for p, _ in w) > lane.caps["n"]:
+                    lane.plan(w)
+        self.supported = all(l.supported for l in self.lanes)
+        torch.cuda.synchronize()
+        if self.supported:
+            self.capture([frames_dev] * len(self.lanes))
+        return self
+
+    def _load_inputs(self, lane, p, v):
+        n = p.shape[0]
+        if n > lane.caps["n"]:
+            raise OverflowError("frame has more points than the static capacity")
+        lane.pos_buf[:n].copy_(p, non_blocking=True)
+        lane.val_buf[:n].copy_(v, non_blocking=True)
+        _lib.check(_lib.load().ltn_set_int2(_lib.ptr(lane.sizes), n, 4 * n, _lib.stream()), "ltn_set_int2")
+
+    def _lane_frame(self, i, kind):
+        lane = self.lanes[i]
+        _lib.set_static_rows(lane._registry())
+        try:
+            with torch.no_grad():
+                return lane._frame(kind)
+        finally:
+            _lib.set_static_rows(None)
+
+    def _capture_kind(self, kind):
+        """the lanes' inputs are loaded; warms the kind up (eager, static mode, lock-step) and captures it"""
+        cur = torch.cuda.current_stream()
+        self.main.wait_stream(cur)
+        with torch.cuda.stream(self.main):
+            # executed once outside the capture: creates lazy buffers / weight splits and ADVANCES the recurrent state
+            # like the real frame would, so the kinds captured next see a consistent state
+            _LockstepCoordinator(self.main, self.streams).run(lambda i: self._lane_frame(i, kind))
+            self.main.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = _lib.load().ltn_launch_count()
+            coord = _LockstepCoordinator(self.main, self.streams)
+            with torch.cuda.graph(graph, pool=self.pool, stream=self.main, capture_error_mode="thread_local"):
+                outs = coord.run(lambda i: self._lane_frame(i, kind))
+            self.kernels[kind] = _lib.load().ltn_launch_count() - l0
+            self.batched[kind] = coord.batched_launches
+            if self.pool is None:
+                self.pool = graph.pool()
+        cur.wait_stream(self.main)
+        self.graphs[kind] = (graph, outs)
+
+    def capture(self, windows_dev):
+        """captures every frame kind of these windows (one per lane, equal frame counts) that is not captured yet"""
+        T = len(windows_dev[0])
+        for t in range(T):
+            kind = (t == 0, t == T - 1)
+            with torch.cuda.stream(self.main):
+                for lane, w in zip(self.lanes, windows_dev):
+                    self._load_inputs(lane, w[t][0], w[t][1])
+            if kind in self.graphs:
+                with torch.cuda.stream(self.main):
+                    self.graphs[kind][0].replay()
+            else:
+                torch.cuda.current_stream().wait_stream(self.main)
+                self._capture_kind(kind)
+                # the capture only RECORDED the frame; the warm-up run before it advanced the state once, which is what
+                # the following kinds need
+        torch.cuda.synchronize()
+        return self
+
+    # ---- execution -------------------------------------------------------------------------------------------------
+    def _fits(self, windows):
+        T = len(windows[0])
+        return (self.supported and len(windows) == len(self.lanes) and all(len(w) == T for w in windows)
+                and all(p.shape[0] <= lane.caps["n"] for lane, w in zip(self.lanes, windows) for p, _ in w))
+
+    def _run_group(self, windows_dev):
+        """queues one full group on the main stream; returns the per-lane static outputs of the last frame"""
+        T = len(windows_dev[0])
+        kinds = [(t == 0, t == T - 1) for t in range(T)]
+        if any(k not in self.graphs for k in kinds):
+            self.capture(windows_dev)
+        outs = None
+        with torch.cuda.stream(self.main):
+            for t, kind in enumerate(kinds):
+                for lane, w in zip(self.lanes, windows_dev):
+                    self._load_inputs(lane, w[t][0], w[t][1])
+                graph, outs = self.graphs[kind]
+                graph.replay()
+        return outs
+
+    def infer_windows_device(self, windows_dev):
+        """windows_dev: lists of (positions, values) CUDA tensors, one per lane.  Returns the log-softmax of each window's
+        last frame (views of the graphs' static outputs: valid until the next group runs; clone to keep).  The caller's
+        stream waits for the group."""
+        cur = torch.cuda.current_stream()
+        if not self._fits(windows_dev):
+            return [self.lanes[i % len(self.lanes)].infer_window_device(w) for i, w in enumerate(windows_dev)]
+        self.main.wait_stream(cur)
+        outs = self._run_group(windows_dev)
+        cur.wait_stream(self.main)
+        return [o[: w[-1][0].shape[0]] for o, w in zip(outs, windows_dev)]
+
+    def submit(self, windows_host):
+        """queues one group of windows given as PINNED host tensors; returns a ticket for collect().  The host -> device
+        copies run on a copy stream, so the next group's inputs travel while the current group computes."""
+        dev = self.device
+        ticket = {"host": windows_host, "labels": None, "counts": None, "event": None, "staged": None}
+        if not self._fits(windows_host):
+            return ticket
+        with torch.cuda.stream(self.copy_stream):
+            staged = [[(p.to(dev, non_blocking=True), v.to(dev, non_blocking=True)) for p, v in w] for w in windows_host]
+            copied = torch.cuda.Event()
+            copied.record()
+        self.main.wait_event(copied)
+        outs = self._run_group(staged)
+        slot, self._slot = self._slot, self._slot ^ 1
+        labels, counts = [], []
+        with torch.cuda.stream(self.main):
+            for i, (lane, w) in enumerate(zip(self.lanes, windows_host)):
+                n = w[-1][0].shape[0]
+                lab = outs[i][:n].argmax(1)
+                buf = self._host_out.get((i, slot))
+                if buf is None:
+                    buf = (torch.empty(lane.caps["n"], dtype=torch.int64).pin_memory(),
+                           torch.zeros(4 * len(lane.caps["v"]) + 1, dtype=torch.int32).pin_memory())
+                    self._host_out[(i, slot)] = buf
+                buf[0][:n].copy_(lab, non_blocking=True)
+                lane._copy_checks(buf[1])
+                labels.append(buf[0][:n])
+                counts.append(buf[1])
+            ev = torch.cuda.Event()
+            ev.record()
+        ticket.update(labels=labels, counts=counts, event=ev, staged=staged)
+        return ticket
+
+    def collect(self, ticket):
+        """waits for a ticket; returns the predicted labels per window (pinned host int64, valid until the slot is reused
+        two submissions later).  Windows that outgrew the static capacities (or raised the fp16 range flag) are re-run on
+        the lane's eager path."""
+        if ticket["event"] is None:
+            return [WindowRunner.infer_window(self.lanes[i % len(self.lanes)], w).clone() for i, w in enumerate(ticket["host"])]
+        ticket["event"].synchronize()
+        out = []
+        for i, lane in enumerate(self.lanes):
+            if lane._checks_ok(ticket["counts"][i]):
+                out.append(ticket["labels"][i])
+            else:
+                lane.fallbacks += 1
+                lane._force_eager = True
+                try:
+                    out.append(WindowRunner.infer_window(lane, ticket["host"][i]).clone())
+                finally:
+                    lane._force_eager = False
+        ticket["staged"] = None
+        return out
+
+    def infer_windows(self, windows_host):
+        return self.collect(self.submit(windows_host))
+
+    def counts_ok(self):
+        return all(l.counts_ok() for l in self.lanes)
+
+    def kernels_per_group(self, nr_frames):
+        return sum(self.kernels.get((t == 0, t == nr_frames - 1), 0) for t in range(nr_frames))
+
+    def batched_per_group(self, nr_frames):
+        return sum(self.batched.get((t == 0, t == nr_frames - 1), 0) for t in range(nr_frames))

@@ -1,5 +1,7 @@
 """Dense / reduction primitives shared by the lattice modules: fp32 matmul, GroupNorm(+ReLU) over
 lattice vertices, segmented max / add / mean.  GPU only."""
+import ctypes
+import threading
 import weakref
 
 import torch
@@ -144,7 +146,27 @@ A_LOG2 = 5     # fp16 operands: activations are staged as x * 2^5 (overflow flag
 # the tensor rate).  fp16's exponent range is handled by exact power-of-two scaling plus a device-side range flag,
 # so "f16" is only selected by callers that CHECK the flag and redo the window with "tf32" when it is raised
 # (runner.py / engine.py); modules called directly stay on "tf32".
-_TC = {"mode": "tf32", "flag": None}
+class _ThreadLocalDict:
+    """dict-like view of per-thread state (the lock-step engine runs one host thread per window in flight while capturing)"""
+
+    def __init__(self, **defaults):
+        self._defaults = defaults
+        self._tl = threading.local()
+
+    def _d(self):
+        d = getattr(self._tl, "d", None)
+        if d is None:
+            d = self._tl.d = dict(self._defaults)
+        return d
+
+    def __getitem__(self, k): return self._d()[k]
+    def __setitem__(self, k, v): self._d()[k] = v
+    def update(self, other): self._d().update(other)
+    def keys(self): return self._d().keys()
+    def __iter__(self): return iter(self._d())
+
+
+_TC = _ThreadLocalDict(mode="tf32", flag=None)
 
 
 class tc_operands:
@@ -158,7 +180,7 @@ class tc_operands:
         self.new = {"mode": mode, "flag": flag}
 
     def __enter__(self):
-        self.old = dict(_TC)
+        self.old = {k: _TC[k] for k in ("mode", "flag")}
         _TC.update(self.new)
         return self
 
@@ -280,6 +302,16 @@ def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, gn=None, relu=
         if flag is None:
             raise RuntimeError("fp16 operands need a range flag")
         hi, lo, w_log2 = wt.f16()
+        ctx = getattr(_BATCH, "ctx", None)
+        if ctx is not None and a_scale is None and x.shape[0] > 0 and Vq > 0:
+            # lock-step capture (engine.LockstepRunner): this window's request joins the same layer's requests of the
+            # other windows in flight; the coordinator issues ONE launch for all of them (conv_tc_batched) and resumes us
+            ctx.request(dict(x=x, Vx=x.shape[0], vx_dev=vx_dev, nbr=nbr, Vq=Vq, vq_dev=vq_dev, C=C, S=S, hi=hi, lo=lo, w_log2=int(w_log2),
+                             F=F, g_sums=g_sums, g_gamma=g_gamma, g_beta=g_beta, g_eps=float(g_eps), g_groups=int(g_groups),
+                             relu=1 if relu else 0, bias=bias, res=res, out=out, ldo=out.stride(0), out_sums=out_sums, flag=flag))
+            if out_sums is not None:
+                out._ltn_gn_sums = (_FRAME["id"], out_sums)
+            return out
         rc = _lib.load().ltn_conv_tc_f16(p(x), x.shape[0], vx_dev, p(nbr), Vq, vq_dev, C, S, p(hi), p(lo),
                                          int(w_log2), int(A_LOG2), F, p(a_scale), p(a_shift), p(g_sums), p(g_gamma), p(g_beta),
                                          float(g_eps), int(g_groups), 1 if relu else 0, p(bias), p(res), p(out), out.stride(0),
@@ -298,8 +330,42 @@ def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, gn=None, relu=
     return out
 
 
+_BATCH = threading.local()   # .ctx: coordinator of a lock-step capture (engine.LockstepRunner), absent otherwise
+MAX_BATCH = 8
+
+
+def _ptr_array(items):
+    return (ctypes.c_void_p * len(items))(*[None if t is None else (t.value if isinstance(t, ctypes.c_void_p) else t.data_ptr()) for t in items])
+
+
+def conv_tc_batched(reqs):
+    """ONE launch of the fused fp16-operand convolution for the same layer of several independent windows
+    (csrc/ltn_conv_batched.cu).  reqs: the dicts conv_tc hands to the lock-step coordinator, one per window; weights,
+    bias and GroupNorm parameters are taken from the first (the windows' models hold identical values)."""
+    nb = len(reqs)
+    if nb < 1 or nb > MAX_BATCH:
+        raise RuntimeError("between 1 and %d problems per batched launch" % MAX_BATCH)
+    r0 = reqs[0]
+    same = ("C", "S", "F", "w_log2", "g_eps", "g_groups", "relu", "ldo")
+    for r in reqs[1:]:
+        if any(r[k] != r0[k] for k in same) or (r["nbr"] is None) != (r0["nbr"] is None) or (r["g_sums"] is None) != (r0["g_sums"] is None) \
+                or (r["out_sums"] is None) != (r0["out_sums"] is None) or (r["res"] is None) != (r0["res"] is None) \
+                or (r["bias"] is None) != (r0["bias"] is None):
+            raise RuntimeError("the windows of a lock-step group reached different layers")
+    ints = lambda k: (ctypes.c_int * nb)(*[int(r[k]) for r in reqs])   # noqa: E731
+    arr = lambda k: _ptr_array([r[k] for r in reqs])                    # noqa: E731
+    p = _lib.ptr
+    rc = _lib.load().ltn_conv_tc_f16_batched(nb, arr("x"), ints("Vx"), arr("vx_dev"), arr("nbr"), ints("Vq"), arr("vq_dev"), r0["C"], r0["S"],
+                                             p(r0["hi"]), p(r0["lo"]), r0["w_log2"], int(A_LOG2), r0["F"], arr("g_sums"), p(r0["g_gamma"]),
+                                             p(r0["g_beta"]), r0["g_eps"], r0["g_groups"], r0["relu"], p(r0["bias"]), arr("res"), arr("out"),
+                                             r0["ldo"], arr("out_sums"), 0 if r0["out_sums"] is None else r0["out_sums"].shape[0],
+                                             arr("flag"), _lib.stream())
+    _lib.check(rc, "ltn_conv_tc_f16_batched")
+
+
 _SUMS_SLOTS = 96   # accumulators handed out per frame before falling back to individual allocations
-_FRAME = {"arena": None, "used": 0, "id": 0}
+_FRAME = _ThreadLocalDict(arena=None, used=0, id=0)
+_FRAME_IDS = [0]   # frame ids are unique across threads: statistics attached to a tensor are trusted within their frame only
 
 
 def begin_frame(owner, device):
@@ -313,7 +379,8 @@ def begin_frame(owner, device):
     else:
         buf.zero_()
     _FRAME["arena"], _FRAME["used"] = buf, 0
-    _FRAME["id"] += 1
+    _FRAME_IDS[0] += 1
+    _FRAME["id"] = _FRAME_IDS[0]
 
 
 def new_sums(nr_channels, device):

@@ -281,3 +281,99 @@ def test_conv_tc_is_bit_reproducible(dev, lattice, operands):
                 assert torch.equal(first, o), (C, F, S, folded, "concurrent")
                 assert torch.allclose(sm, want_sums, rtol=1e-5, atol=1e-3), (C, F, S, folded, "statistics")
     assert int(flag.item()) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Batched persistent kernel (csrc/ltn_conv_batched.cu): one launch for the same layer of several windows must give
+# the SAME BITS as one ltn_conv_tc_f16 launch per window (same MMAs, same k order per tile), for every model shape,
+# ragged problem sizes, device-side row counts, folded GroupNorm, bias, residual, output statistics.
+# ---------------------------------------------------------------------------------------------------------------
+class _Collector:
+    def __init__(self):
+        self.reqs = []
+
+    def request(self, d):
+        self.reqs.append(d)
+
+
+def _batched_vs_single(dev, ls, V, shape, nb, folded, with_res, with_bias, with_sums, seed, dev_counts=False):
+    from temporal_latticenet_b200 import ops
+    C, F, S = shape
+    nbr_full = ls.neighbours()
+    g = torch.Generator().manual_seed(seed)
+    W = (torch.randn(S * C, F, generator=g) / (S * C) ** 0.5).to(dev)
+    wt = ops.k_major(W)
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).to(dev), torch.randn(C, generator=g).to(dev)
+    bias = torch.randn(F, generator=g).to(dev) if with_bias else None
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    probs = []
+    for b in range(nb):
+        Vb = max(1, V - 137 * b - (b * V) // 7)                       # ragged: every problem has its own row count
+        x = torch.randn(V, C, generator=g).to(dev) * (1.0 + 0.3 * b)
+        nbr = nbr_full[:Vb].contiguous() if S == 9 else None
+        res = torch.randn(Vb, F, generator=g).to(dev) if with_res else None
+        live = Vb - 5 * b if dev_counts else Vb                        # device-side count below the host bound
+        cnt = torch.tensor([live], dtype=torch.int32, device=dev) if dev_counts else None
+        probs.append((x, nbr, res, Vb, live, cnt))
+    import ctypes
+
+    def run(batched):
+        outs, sums = [], []
+        col = _Collector()
+        ops._BATCH.ctx = col if batched else None
+        try:
+            for x, nbr, res, Vb, live, cnt in probs:
+                gn = (ops.gn_sums(x, ops.gn_groups(C)), gamma, beta, 1e-5) if folded else None
+                sm = torch.zeros(ops.gn_groups(F), 2, dtype=torch.float64, device=dev) if with_sums else None
+                out = torch.zeros(Vb, F, device=dev)
+                rd = ctypes.c_void_p(cnt.data_ptr()) if cnt is not None else None
+                o = ops.conv_tc(x, nbr, wt, nr_rows=Vb, gn=gn, relu=folded, bias=bias, res=res, out=out, out_sums=sm, operands="f16",
+                                flag=flag, rows_dev=rd if S == 1 else None)
+                if cnt is not None and S == 9:   # gather form: the count bounds the QUERY rows only
+                    pass
+                outs.append(o)
+                sums.append(sm)
+        finally:
+            ops._BATCH.ctx = None
+        if batched:
+            assert len(col.reqs) == nb
+            if dev_counts and S == 9:
+                for r, (_, _, _, _, _, cnt) in zip(col.reqs, probs):
+                    r["vq_dev"] = ctypes.c_void_p(cnt.data_ptr())
+            ops.conv_tc_batched(col.reqs)
+        torch.cuda.synchronize()
+        return outs, sums
+    if dev_counts and S == 9:
+        return None   # exercised through the S == 1 form (rows_dev) and the engine tests
+    a, sa = run(False)
+    b, sb = run(True)
+    for i, (o1, o2) in enumerate(zip(a, b)):
+        live = probs[i][4]
+        assert torch.equal(o1[:live], o2[:live]), (shape, nb, i, "out differs")
+        if with_sums:
+            assert torch.allclose(sa[i], sb[i], rtol=1e-6, atol=1e-3), (shape, nb, i, "statistics differ")
+    assert int(flag.item()) == 0
+
+
+@pytest.mark.parametrize("nb", [1, 3, 4, 8])
+def test_batched_conv_is_bit_identical_to_single_launches(dev, lattice, nb):
+    ls, tab = lattice
+    V = tab.size()
+    for k, shape in enumerate(MODEL_SHAPES):
+        C, F, S = shape
+        if C % 64:
+            continue
+        folded = C <= 256 and k % 2 == 0
+        _batched_vs_single(dev, ls, V, shape, nb, folded, with_res=(k % 3 == 0), with_bias=(k % 2 == 1), with_sums=(F % 32 == 0 and k % 4 != 3),
+                           seed=100 * nb + k)
+
+
+def test_batched_conv_device_side_counts_and_tiny_problems(dev, lattice):
+    ls, tab = lattice
+    V = tab.size()
+    for shape in [(64, 64, 1), (128, 384, 1), (192, 192, 1), (64, 192, 1)]:
+        _batched_vs_single(dev, ls, V, shape, 4, folded=True, with_res=True, with_bias=True, with_sums=shape[1] % 32 == 0, seed=7,
+                           dev_counts=True)
+    # problems smaller than one tile, and a group in which most CTAs have nothing to do
+    _batched_vs_single(dev, ls, 150, (64, 64, 9), 3, folded=True, with_res=False, with_bias=False, with_sums=True, seed=9)
+    _batched_vs_single(dev, ls, 40, (192, 192, 9), 2, folded=False, with_res=True, with_bias=True, with_sums=True, seed=10)

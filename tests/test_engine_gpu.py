@@ -307,3 +307,42 @@ def test_submit_captures_a_frame_kind_it_has_not_seen():
         want = eager.infer_window_device(to_dev(w)).argmax(1).cpu()
         assert (l == want).float().mean() > 0.999
     assert sum(l.fallbacks for l in multi.lanes) == 0
+
+
+def test_lockstep_runner_matches_eager_runner():
+    """four windows advancing together, one graph per frame kind for all of them, every tensor-core layer one batched
+    launch: same vertex counts and log-softmax (1e-4 of abs-max; only the order of the statistics' atomics differs) as
+    running the windows one after the other eagerly; replayed with the windows rotated over the lanes"""
+    from temporal_latticenet_b200.engine import LockstepRunner
+    from temporal_latticenet_b200.runner import WindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    dev = torch.device("cuda:0")
+    wins = [_window(31), _window(32, n=5200), _window(33, n=4800), _window(34, n=5600)]
+    to_dev = lambda w: [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]  # noqa: E731
+    devw = [to_dev(w) for w in wins]
+    eager = WindowRunner(CFG, 26, dev).materialise_parameters(devw[0], seeded_state)
+    ls = LockstepRunner(CFG, 26, dev, lanes=4).prepare(devw[0], seeded_state, devw)
+    assert ls.supported and len(ls.graphs) == 3
+    assert all(ls.batched[k] > 20 for k in ls.graphs)          # the layers really went through the batched kernel
+    want = [eager.infer_window_device(w).cpu().numpy() for w in devw]
+    for rep in range(3):
+        order = devw[rep:] + devw[:rep]
+        outs = ls.infer_windows_device(order)
+        torch.cuda.synchronize()
+        assert ls.counts_ok()
+        for o, w in zip(outs, (want[rep:] + want[:rep])):
+            got = o.cpu().numpy()
+            assert got.shape == w.shape
+            assert float(np.abs(got - w).max()) / float(np.abs(w).max()) < 1e-4
+    host = [[(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in w] for w in wins]
+    t1 = ls.submit(host)
+    t2 = ls.submit(host[1:] + host[:1])
+    for labels, ws in ((ls.collect(t1), want), (ls.collect(t2), want[1:] + want[:1])):
+        for l, w in zip(labels, ws):
+            assert (l.numpy() == w.argmax(1)).mean() > 0.999
+    assert sum(l.fallbacks for l in ls.lanes) == 0
+    # a group that does not fill the lanes goes through the lanes' own per-window graphs
+    outs = ls.infer_windows_device(devw[:2])
+    torch.cuda.synchronize()
+    for o, w in zip(outs, want[:2]):
+        assert float(np.abs(o.cpu().numpy() - w).max()) / float(np.abs(w).max()) < 1e-4
