@@ -7,6 +7,8 @@ synthetic SemanticKITTI-shaped scans (~125k points each) pushed through the wind
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one process per GPU)
   python bench.py --impl reference ...                            CPU arm: the scalar oracle + torch CPU
+  python bench.py --workload config5|config5-accumulated|config2  the other BASELINE configs (same contract)
+  python bench.py --mode train                                    BASELINE config 4 (training step, NCCL all-reduce)
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -26,8 +28,15 @@ CFG = os.path.join(REPO, "configs", "lnn_eval_semantic_kitti.cfg")
 METRIC = "4-frame scans/sec"
 UNIT = "scans/s"
 FRAMES = 4
-NR_CLASSES = 26
-WORKLOAD = "config3: LNN_SEQ [gru,gru,aflow,gru], 4 frames, scope 3, sigma 0.6, 26 classes, inference, fp32"
+WORKLOADS = {
+    # name: (description, rnn_modules or None = cfg default, nr_classes, frames per window, accumulate)
+    "config3": ("config3: LNN_SEQ [gru,gru,aflow,gru], 4 frames, scope 3, sigma 0.6, 26 classes, inference, fp32", None, 26, 4, False),
+    "config5": ("config5: LNN_SEQ [aflow,aflow,aflow,aflow], 4 frames, scope 3, sigma 0.6, 26 classes, inference, fp32",
+                ["aflow", "aflow", "aflow", "aflow"], 26, 4, False),
+    "config5-accumulated": ("config5 (accumulate_clouds): the window's 4 scans as ONE ~500k-point lattice, [aflow x4], 26 classes, inference, fp32",
+                            ["aflow", "aflow", "aflow", "aflow"], 26, 1, True),
+    "config2": ("config2: single-frame LatticeNet forward (conv/coarsen/finefy/slice_classify), 20 classes, inference, fp32", None, 20, 1, False),
+}
 
 
 def peaks():
@@ -46,8 +55,8 @@ def peaks():
 class Clocks:
     """SM clock / throttle-reason samples DURING the timed regions.  In-process NVML (the library nvidia-smi itself
     queries) from a background thread every 50 ms: a `nvidia-smi -lms` child process was measured to stall the
-    launching thread for tens of milliseconds per query -- a third of a 75 ms timed region.  Falls back to the
-    nvidia-smi child when the NVML binding is unavailable."""
+    launching thread for tens of milliseconds per query.  Falls back to the nvidia-smi child when the NVML binding is
+    unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -141,168 +150,184 @@ class Clocks:
 
 
 # ------------------------------------------------------------------------------------------------
-# inputs
+# inputs and configuration (IDENTICAL for both arms: the driver compares the `config` objects)
 # ------------------------------------------------------------------------------------------------
-def make_windows(nr_windows, seed0):
+def make_windows(nr_windows, seed0, frames=FRAMES, accumulate=False):
+    import numpy as np
     from temporal_latticenet_b200 import synthetic
-    return [synthetic.window(seed0 + i, frames=FRAMES, scope=3) for i in range(nr_windows)]
+    out = []
+    for i in range(nr_windows):
+        w = synthetic.window(seed0 + i, frames=FRAMES if accumulate else frames, scope=3)
+        if accumulate:   # kitti_dataloader.py:198-201: the window's scans concatenated into one cloud
+            w = [(np.ascontiguousarray(np.concatenate([p for p, _ in w], 0)), np.ascontiguousarray(np.concatenate([v for _, v in w], 0)))]
+        out.append(w)
+    return out
+
+
+def workload_cfg(name):
+    """cfg file of a workload (the KITTI eval cfg with rnn_modules / table capacity varied) -> (path, description, classes, frames, accumulate)"""
+    desc, rnn, classes, frames, accumulate = WORKLOADS[name]
+    if rnn is None and not accumulate:
+        return CFG, desc, classes, frames, accumulate
+    import hjson
+    with open(CFG) as f:
+        cfg = hjson.loads(f.read())
+    if rnn is not None:
+        cfg["model"]["rnn_modules"] = rnn
+    if accumulate:
+        cfg["lattice_gpu"]["hash_table_capacity"] = 200000
+        cfg["loader_semantic_kitti"]["accumulate_clouds"] = True
+    path = os.path.join("/tmp", "bench_%s_%d.cfg" % (name, os.getpid()))
+    with open(path, "w") as f:
+        f.write(hjson.dumps(cfg))
+    return path, desc, classes, frames, accumulate
+
+
+def config_of(args, desc, windows_np, scans_per_step):
+    """the workload description both arms print verbatim"""
+    return {"workload": desc, "points_per_scan": [[int(p.shape[0]) for p, _ in w] for w in windows_np], "scans_per_step": scans_per_step,
+            "windows_cycled": len(windows_np), "window_seeds": "1000 + rank * windows + i"}
 
 
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: oracle on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_window_seconds(window, repeats=1):
-    """Times the oracle's window executor (oracle/window_oracle.py: the reference's model recipe in
-    plain torch-CPU over the scalar C lattice oracle) on one 4-frame window with all host threads."""
+def cpu_window(cfg, classes, window):
+    """One window through the oracle's executor (oracle/window_oracle.py: the reference's model recipe in plain
+    torch-CPU over the scalar C lattice oracle) with all host threads.  Returns (seconds, threads, log-softmax)."""
     import torch
     from oracle import window_oracle as WO
     torch.set_num_threads(os.cpu_count() or 1)
-    runner = WO.OracleWindowRunner(CFG, NR_CLASSES)
+    runner = WO.OracleWindowRunner(cfg, classes)
     runner.materialise_parameters(window[:2])
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        runner.infer_window(window)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return best, torch.get_num_threads()
+    t0 = time.perf_counter()
+    out = runner.infer_window(window)
+    return time.perf_counter() - t0, torch.get_num_threads(), out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    window = make_windows(1, 1000)[0]
+    cfg, desc, classes, frames, accumulate = workload_cfg(args.workload)
+    windows = make_windows(args.windows, 1000, frames, accumulate)
+    scans = FRAMES if accumulate else frames
     import torch
     from oracle import window_oracle as WO
     torch.set_num_threads(os.cpu_count() or 1)
-    runner = WO.OracleWindowRunner(CFG, NR_CLASSES)
-    runner.materialise_parameters(window[:2])
-    for _ in range(args.warmup):
-        runner.infer_window(window)
+    runner = WO.OracleWindowRunner(cfg, classes)
+    runner.materialise_parameters(windows[0][:2])
+    for i in range(args.warmup):
+        runner.infer_window(windows[i % len(windows)])
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        runner.infer_window(window)
+    for i in range(args.steps):
+        runner.infer_window(windows[i % len(windows)])
     dt = time.perf_counter() - t0
-    value = FRAMES * args.steps / dt
-    pts = [int(p.shape[0]) for p, _ in window]
+    value = scans * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points_per_scan": pts, "frames": FRAMES},
+            "config": config_of(args, desc, windows, scans),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "%d whole 4-frame window(s) of the same synthetic workload" % args.steps},
+                             "sample": "%d whole window(s) of the same synthetic workload (oracle/window_oracle.py)" % args.steps},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
-# our arm
+# HBM-side kernels of the metric
 # ------------------------------------------------------------------------------------------------
-class Probe:
-    """CUDA-event brackets around chosen C-ABI entry points / ops on torch's current stream (the
-    stream every kernel of the library is launched on)."""
-
-    def __init__(self):
-        self.records = {}
-
-    def wrap(self, name, fn, work_fn):
-        import torch
-
-        def wrapped(*a, **kw):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = fn(*a, **kw)
-            e1.record()
-            self.records.setdefault(name, []).append((e0, e1, work_fn(*a) if work_fn else 0.0))
-            return r
-        return wrapped
-
-    def summary(self):
-        out = {}
-        for name, recs in self.records.items():
-            ms = [a.elapsed_time(b) for a, b, _ in recs]
-            work = sum(w for _, _, w in recs)
-            out[name] = {"launches": len(recs), "ms_total": sum(ms), "work": work}
-        return out
-
-
 def hbm_kernels(dev, window_np, pk):
-    """The metric's second half: splat / slice / im2row (and distribute) HBM GB/s against the measured copy peak.
-    One scan moves too few bytes to say anything about bandwidth (distribute on 125k points = 16 MB = 2.4 us at
-    peak), so these are timed on the window's 4 scans ACCUMULATED into one cloud (~500k points, the
-    accumulate_clouds shape of BASELINE config 5), 20 back-to-back launches inside a CUDA graph, CUDA events around
-    the replay.  Algorithmic bytes per SURVEY.md 8(d): compulsory traffic only."""
+    """The metric's second half: splat / slice / im2row (and distribute) HBM GB/s against the measured copy peak, on
+    (a) ONE scan of the headline configuration and (b) the window's 4 scans accumulated into one cloud (~500k points,
+    the accumulate_clouds shape of BASELINE config 5).  Every kernel is timed COLD: a CUDA graph alternates a 256 MB L2
+    flush with the kernel 20 times, the time of the same graph with the flushes alone is subtracted.  Algorithmic bytes per
+    SURVEY.md 8(d): compulsory traffic only."""
     import numpy as np
     import torch
-    from temporal_latticenet_b200 import _lib, funcs
+    from temporal_latticenet_b200 import _lib
     from temporal_latticenet_b200.lattice import Lattice
     lib = _lib.load()
     p = _lib.ptr
-    pos = torch.from_numpy(np.concatenate([f[0] for f in window_np], 0)).to(dev)
-    val = torch.from_numpy(np.concatenate([f[1] for f in window_np], 0)).to(dev)
-    N = pos.shape[0]
-    ls = Lattice(100000, 0.6, device=dev)
-    rows, idx, w = ls.distribute(pos, val, True)
-    V = ls.nr_lattice_vertices()
-    nbr = ls.neighbours()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def graph_ms(fn, n=20):
-        fn()
-        torch.cuda.synchronize()
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
+            fn()
+            torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):
                 for _ in range(n):
                     fn()
         torch.cuda.synchronize()
-        g.replay()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
+        best = None
+        for _ in range(3):
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            best = ms if best is None else min(best, ms)
+        return best
+
+    flush_ms = graph_ms(lambda: flush.zero_())
+
+    def cold_ms(fn):
+        def both():
+            flush.zero_()
+            fn()
+        return max(graph_ms(both) - flush_ms, 1e-6)
 
     out = []
 
-    def add(name, ms, nbytes, note):
+    def add(cloud, name, ms, nbytes, note):
         gbs = nbytes / (ms * 1e-3) / 1e9
-        out.append({"kernel": name, "us": 1e3 * ms, "algorithmic_mb": nbytes / 1e6, "achieved": gbs, "unit": "GB/s", "peak": pk["hbm_gbs"],
-                    "frac": gbs / pk["hbm_gbs"], "shape": note})
-    C = 64
-    feat = torch.randn(V, C, device=dev)
-    rows_out = torch.empty(V, 9 * C, device=dev)
-    add("k_im2row", graph_ms(lambda: lib.ltn_im2row(p(feat), V, None, p(nbr), V, None, C, p(rows_out), _lib.stream())),
-        V * (12 + 40 * C), "V=%d C=%d" % (V, C))
-    C = 192
-    feat = torch.randn(V, C, device=dev)
-    rows_out = torch.empty(V, 9 * C, device=dev)
-    add("k_im2row", graph_ms(lambda: lib.ltn_im2row(p(feat), V, None, p(nbr), V, None, C, p(rows_out), _lib.stream())),
-        V * (12 + 40 * C), "V=%d C=%d" % (V, C))
-    Cs = 32
-    vals = torch.randn(V, Cs, device=dev)
-    sl = torch.empty(N, Cs, device=dev)
-    add("k_slice", graph_ms(lambda: lib.ltn_slice(p(vals), V, Cs, p(idx), p(w), N, p(sl), _lib.stream())),
-        4 * N * 8 + V * 4 * Cs + N * 4 * Cs, "N=%d V=%d C=%d" % (N, V, Cs))
-    Cin = 1
-    acc = torch.zeros(V, Cin + 1, device=dev)
-    add("k_splat", graph_ms(lambda: lib.ltn_splat(p(val), N, Cin, p(idx), p(w), p(acc), V, _lib.stream())),
-        N * (4 * Cin) + 4 * N * 8 + V * 4 * (Cin + 1), "N=%d V=%d C_in=%d (atomics on ~%d rows per vertex)" % (N, V, Cin, 4 * N // max(V, 1)))
-    ht = ls.hash_table
+        out.append({"kernel": name, "cloud": cloud, "us": 1e3 * ms, "algorithmic_mb": nbytes / 1e6, "achieved": gbs, "unit": "GB/s",
+                    "peak": pk["hbm_gbs"], "frac": gbs / pk["hbm_gbs"], "shape": note, "l2": "flushed before every launch"})
 
-    def dist():
-        lib.ltn_hash_clear(p(ht.slot_keys), p(ht.slot_ids), p(ht.slot_first), ht.nslots, p(ht.counters), _lib.stream())
-        sx, sy, sz = ls.scale()
-        lib.ltn_distribute(p(pos), p(val), N, None, 1, sx, sy, sz, p(ht.slot_keys), p(ht.slot_ids), p(ht.slot_first), ht.nslots,
-                           p(ht.counters), p(ht.keys_tensor), ls.capacity, p(ls._row_slot), p(ls._block_sums), p(ls._vert_acc),
-                           p(rows), p(idx), p(w), 1, _lib.stream())
-    add("ltn_distribute (hash build + rows + local mean, 6 kernels incl. table clear)", graph_ms(dist), 128 * N, "N=%d -> V=%d" % (N, V))
+    clouds = [("one scan (headline config)", window_np[0][0], window_np[0][1]),
+              ("4 scans accumulated", np.concatenate([f[0] for f in window_np], 0), np.concatenate([f[1] for f in window_np], 0))]
+    for cloud, pos_np, val_np in clouds:
+        pos, val = torch.from_numpy(np.ascontiguousarray(pos_np)).to(dev), torch.from_numpy(np.ascontiguousarray(val_np)).to(dev)
+        N = pos.shape[0]
+        ls = Lattice(100000, 0.6, device=dev)
+        rows, idx, w = ls.distribute(pos, val, True)
+        V = ls.nr_lattice_vertices()
+        nbr = ls.neighbours()
+        for C in (64, 192):
+            feat = torch.randn(V, C, device=dev)
+            rows_out = torch.empty(V, 9 * C, device=dev)
+            add(cloud, "k_im2row", cold_ms(lambda: lib.ltn_im2row(p(feat), V, None, p(nbr), V, None, C, p(rows_out), _lib.stream())),
+                V * (12 + 40 * C), "V=%d C=%d" % (V, C))
+        for Cs in (32, 64, 192):
+            vals = torch.randn(V, Cs, device=dev)
+            sl = torch.empty(N, Cs, device=dev)
+            add(cloud, "k_slice", cold_ms(lambda: lib.ltn_slice(p(vals), V, Cs, p(idx), p(w), N, p(sl), _lib.stream())),
+                4 * N * 8 + V * 4 * Cs + N * 4 * Cs, "N=%d V=%d C=%d" % (N, V, Cs))
+        for Cin in (1, 3):
+            src = torch.randn(N, Cin, device=dev)
+            acc = torch.zeros(V, Cin + 1, device=dev)
+            add(cloud, "k_splat", cold_ms(lambda: lib.ltn_splat(p(src), N, Cin, p(idx), p(w), p(acc), V, _lib.stream())),
+                N * (4 * Cin) + 4 * N * 8 + V * 4 * (Cin + 1), "N=%d V=%d C_in=%d (~%d rows per vertex)" % (N, V, Cin, 4 * N // max(V, 1)))
+        ht = ls.hash_table
+
+        def dist():
+            lib.ltn_hash_clear(p(ht.slot_keys), p(ht.slot_ids), p(ht.slot_first), ht.nslots, p(ht.counters), _lib.stream())
+            sx, sy, sz = ls.scale()
+            lib.ltn_distribute(p(pos), p(val), N, None, 1, sx, sy, sz, p(ht.slot_keys), p(ht.slot_ids), p(ht.slot_first), ht.nslots,
+                               p(ht.counters), p(ht.keys_tensor), ls.capacity, p(ls._row_slot), p(ls._block_sums), p(ls._vert_acc),
+                               p(rows), p(idx), p(w), 1, _lib.stream())
+        add(cloud, "ltn_distribute (table clear + hash build + rows + local mean)", cold_ms(dist), 128 * N, "N=%d -> V=%d" % (N, V))
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# training arm (BASELINE config 4)
+# ------------------------------------------------------------------------------------------------
 def run_train(args, rank, world, dev, devw, windows_np, lib, seeded_state):
     """BASELINE config 4: the same 4-frame gru-gru-aflow-gru window as a TRAINING step (BPTT through the 4
     frames, 0.5 Lovasz + 0.5 NLL, AdamW amsgrad), data-parallel over the ranks with one flattened
@@ -311,8 +336,8 @@ def run_train(args, rank, world, dev, devw, windows_np, lib, seeded_state):
     import torch.distributed as dist
     from temporal_latticenet_b200 import synthetic
     from temporal_latticenet_b200.train import WindowTrainer
-    targets = [torch.from_numpy(synthetic.labels(w[-1][0].shape[0], NR_CLASSES, seed=i)).to(dev) for i, w in enumerate(windows_np)]
-    tr = WindowTrainer(CFG, NR_CLASSES, dev)
+    targets = [torch.from_numpy(synthetic.labels(w[-1][0].shape[0], 26, seed=i)).to(dev) for i, w in enumerate(windows_np)]
+    tr = WindowTrainer(CFG, 26, dev)
     tr.materialise(devw[0], targets[0], seeded_state)
 
     def barrier():
@@ -346,10 +371,19 @@ def run_train(args, rank, world, dev, devw, windows_np, lib, seeded_state):
                           "config": {"workload": "config4: same window, training step (BPTT, 0.5 Lovasz + 0.5 NLL, AdamW amsgrad), "
                                                  "data-parallel over windows, one flattened gradient all-reduce per step",
                                      "parameters": nparams, "allreduce_bytes_per_step": 4 * nparams,
+                                     "allreduce_ms": getattr(tr, "allreduce_ms", None),
                                      "l2": "activations of a 4-frame window exceed L2"},
                           "gpu_launches": int(launches), "clocks": clk, "final_loss": float(loss)}))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def stats_ms(xs):
+    xs = sorted(xs)
+    return {"min": xs[0], "median": xs[len(xs) // 2], "max": xs[-1], "n": len(xs)}
 
 
 def main():
@@ -358,19 +392,24 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--windows", type=int, default=2, help="distinct synthetic windows cycled through")
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--windows", type=int, default=4, help="distinct synthetic windows cycled through (per rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--breakdown", action="store_true", help="add a per-entry-point time breakdown (extra untimed pass)")
+    ap.add_argument("--no-hbm", action="store_true", help="skip the splat / slice / im2row / distribute bandwidth table")
     ap.add_argument("--eager", action="store_true", help="eager per-op launches instead of CUDA-graph replay")
     ap.add_argument("--lanes", type=int, default=4, help="independent windows in flight per GPU")
     ap.add_argument("--streams", action="store_true", help="round-1 execution: one stream + one graph per window in flight "
                     "(MultiWindowRunner) instead of the lock-step group graph with batched tensor-core launches (LockstepRunner)")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="the K-step timed loop is repeated until it has run this long")
+    ap.add_argument("--driver", default="mirror", choices=["mirror", "reference"],
+                    help="reference: ALSO time the reference's own seq_lattice/models.py over the shims (tools/reference_driver.py)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer = BASELINE config 3 (headline); train = config 4 (BPTT + AdamW + NCCL gradient all-reduce)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -386,28 +425,33 @@ def main():
     import __graft_entry__ as G
     G.build()
     from temporal_latticenet_b200 import _lib
-    from temporal_latticenet_b200.engine import GraphWindowRunner, LockstepRunner, MultiWindowRunner
+    from temporal_latticenet_b200.engine import LockstepRunner, MultiWindowRunner
     from temporal_latticenet_b200.runner import WindowRunner
     from temporal_latticenet_b200.seeding import seeded_state
     lib = _lib.load()
 
-    # inputs: every rank owns its windows (sharded by window); pinned host + device copies
-    windows_np = make_windows(args.windows, 1000)   # the same synthetic windows on every rank: per-GPU work is identical (weak scaling)
+    cfg, desc, classes, frames, accumulate = workload_cfg(args.workload)
+    scans = FRAMES if accumulate else frames
+    # every rank owns its OWN windows (sharded by window): per-rank spread of the window sizes is part of the number
+    windows_np = make_windows(args.windows, 1000 + rank * args.windows, frames, accumulate)
     host = [[(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in w] for w in windows_np]
     devw = [[(p.to(dev), v.to(dev)) for p, v in w] for w in host]
-    pts = [int(p.shape[0]) for p, _ in windows_np[0]]
 
     if args.mode == "train":
         return run_train(args, rank, world, dev, devw, windows_np, lib, seeded_state)
+    lanes = max(1, args.lanes)
+    # capacities are planned on every window of this rank and re-validated after every window (eager fallback when exceeded)
     if args.eager:
-        runner = WindowRunner(CFG, NR_CLASSES, dev)
+        runner = WindowRunner(cfg, classes, dev)
         runner.materialise_parameters(devw[0], seeded_state)
+        multi, lanes = None, 1
     else:
-        # default: static-capacity CUDA-graph replay of each frame (engine.py); capacities are planned on the
-        # window with the most points and re-validated after every window (eager fallback when exceeded)
         Runner = MultiWindowRunner if args.streams else LockstepRunner
-        multi = Runner(CFG, NR_CLASSES, dev, lanes=max(1, args.lanes)).prepare(devw[0], seeded_state, devw)
+        multi = Runner(cfg, classes, dev, lanes=lanes).prepare(devw[0], seeded_state, devw)
         runner = multi.lanes[0]
+        if not multi.supported:
+            multi, lanes = None, 1
+    lockstep = isinstance(multi, LockstepRunner)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -415,205 +459,227 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    lanes = 1 if args.eager or not runner.supported else max(1, args.lanes)
+    nw = len(devw)
 
     def run_group(i0, n):
         """windows i0 .. i0+n-1 in flight together (one per lane); device-resident inputs"""
-        if lanes == 1:
+        if multi is None:
             for j in range(n):
-                runner.infer_window_device(devw[(i0 + j) % len(devw)])
+                runner.infer_window_device(devw[(i0 + j) % nw])
         else:
-            multi.infer_windows_device([devw[(i0 + j) % len(devw)] for j in range(n)])
-
-    def run_group_host(i0, n):
-        if lanes == 1:
-            out = None
-            for j in range(n):
-                out = runner.infer_window(host[(i0 + j) % len(host)])
-            return out
-        return multi.infer_windows([host[(i0 + j) % len(host)] for j in range(n)])[-1]
+            multi.infer_windows_device([devw[(i0 + j) % nw] for j in range(n)])
 
     for i in range(0, max(args.warmup, 3), lanes):
-        run_group(i, min(lanes, max(args.warmup, 3) - i))
+        run_group(i, lanes)
     torch.cuda.synchronize()
-    lvl = runner.static_lattice if getattr(runner, "caps", None) and runner.supported else runner.lattice
-    v_counts = []
-    while lvl is not None:
-        v_counts.append(int(lvl.hash_table.count_tensor().cpu()))
-        lvl = lvl._coarse
 
-    # ---- timed region 1: device-resident inputs ------------------------------------------------------
+    # ---- timed region 1: device-resident inputs; EXACTLY `steps` windows per repeat, repeated until >= min_seconds ------
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
     barrier()
     launches0 = lib.ltn_launch_count()
-    evs = []
-    for i in range(0, args.steps, lanes):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        run_group(i, min(lanes, args.steps - i))   # the lanes fork from / join into the current stream
-        e1.record()
-        evs.append((e0, e1))
+    evs, repeats, t_wall = [], 0, time.perf_counter()
+    while True:
+        for i in range(0, args.steps, lanes):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run_group(i, min(lanes, args.steps - i))
+            e1.record()
+            evs.append((e0, e1, min(lanes, args.steps - i)))
+        repeats += 1
+        torch.cuda.synchronize()
+        done = torch.tensor([1.0 if time.perf_counter() - t_wall >= args.min_seconds else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(done, op=dist.ReduceOp.MIN)   # every rank runs the same number of repeats
+        if float(done.item()) > 0 or repeats >= 50:
+            break
     barrier()
     launches = lib.ltn_launch_count() - launches0
-    graph_mode = (not args.eager) and runner.supported
+    graph_mode = multi is not None
+    capacity_ok = None
     if graph_mode:   # replayed graphs: the library's host-side counter saw the kernels once, at capture
-        if hasattr(multi, "kernels_per_group"):   # lock-step: one graph per frame kind covers all lanes
-            launches = (args.steps // lanes) * multi.kernels_per_group(FRAMES)
+        if lockstep:
+            launches = sum((multi.kernels_per_group(frames) if n == lanes else n * runner.kernels_per_window(frames)) for _, _, n in evs)
         else:
-            launches = args.steps * runner.kernels_per_window(FRAMES)
+            launches = sum(n for _, _, n in evs) * runner.kernels_per_window(frames)
         capacity_ok = multi.counts_ok()
-    ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    group_ms = [a.elapsed_time(b) for a, b, _ in evs]
+    ms_rank = sum(group_ms)
+    t = torch.tensor([ms_rank], dtype=torch.float64, device=dev)
+    per_rank = [t.clone() for _ in range(world)]
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+        dist.all_gather(per_rank, t)
+    per_rank_ms = [float(x.item()) for x in per_rank]
+    ms_max = max(per_rank_ms)
+    timed_steps = args.steps * repeats
 
     # ---- timed region 2: end to end through the runner with pinned HOST buffers ----------------------
-    run_group_host(0, lanes)   # untimed: first use allocates the pinned label / counter buffers of this path
+    def e2e_pass():
+        labels = None
+        if multi is None:
+            for i in range(args.steps):
+                labels = runner.infer_window(host[i % nw])
+        else:   # one group of windows is always queued behind the one the host is waiting for
+            pending = None
+            for i in range(0, args.steps, lanes):
+                ticket = multi.submit([host[(i + j) % nw] for j in range(min(lanes, args.steps - i))])
+                if pending is not None:
+                    labels = multi.collect(pending)[-1]
+                pending = ticket
+            labels = multi.collect(pending)[-1]
+        torch.cuda.synchronize()
+        return labels
+    e2e_pass()   # untimed: first use allocates the pinned label / counter buffers of this path
     barrier()
     t0 = time.perf_counter()
-    if lanes == 1:
-        for i in range(args.steps):
-            labels = run_group_host(i, 1)
-    else:   # one group of windows is always queued behind the one the host is waiting for
-        pending = None
-        for i in range(0, args.steps, lanes):
-            ticket = multi.submit([host[(i + j) % len(host)] for j in range(min(lanes, args.steps - i))])
-            if pending is not None:
-                labels = multi.collect(pending)[-1]
-            pending = ticket
-        labels = multi.collect(pending)[-1]
-    torch.cuda.synchronize()
+    for _ in range(repeats):
+        labels = e2e_pass()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     clk = clocks.stop() if rank == 0 else None
-    h2d = sum(p.numel() * 4 + v.numel() * 4 for p, v in host[0])
+    h2d = sum(sum(p.numel() * 4 + v.numel() * 4 for p, v in w) for w in host) // nw
     d2h = int(labels.numel() * 8)
-
-    # ---- roofline of the dominant kernel: CUDA events around its launches in a repeat of the timed steps
-    probe = Probe()
-    names = {}
-    if args.breakdown:
-        for name, _ in _lib.declared_functions():
-            if name not in ("ltn_version", "ltn_launch_count"):
-                names[name] = None
-    # fused convolution entry points: (x, Vx, vx_dev, nbr, Vq, vq_dev, C, S, wt_hi, wt_lo, [w_log2, a_log2,] F, ...)
-    conv_entries = {"ltn_conv_tc": 10, "ltn_conv_tc_f16": 12}
-
-    def conv_slots(a):
-        return a[7] if a[3] is not None and getattr(a[3], "value", 1) else 1
-
-    def conv_flops(f_idx):
-        return lambda *a: 2.0 * a[4] * a[6] * conv_slots(a) * a[f_idx]
-    for cname, f_idx in conv_entries.items():
-        names[cname] = conv_flops(f_idx)
-    if graph_mode:
-        runner._force_eager = True   # the probe brackets individual C-ABI calls, so this pass launches op by op
-    originals = {}
-    if args.breakdown:   # one probe entry per convolution shape
-        def per_shape(cname, f_idx, orig):
-            def wrapped(*a):
-                key = "conv_tc%s Vq~%dk C%d S%d F%d" % ("_f16" if cname.endswith("f16") else "", round(a[4] / 1000.0), a[6], conv_slots(a), a[f_idx])
-                return probe.wrap(key, orig, conv_flops(f_idx))(*a)
-            return wrapped
-        for cname, f_idx in conv_entries.items():
-            names.pop(cname, None)
-            originals[cname] = getattr(lib, cname)
-            setattr(lib, cname, per_shape(cname, f_idx, originals[cname]))
-    for name, wf in names.items():
-        originals[name] = getattr(lib, name)
-        setattr(lib, name, probe.wrap(name, originals[name], wf))
-    import temporal_latticenet_b200.ops as ops
-    mm_orig, lin_orig = ops.matmul, ops.linear
-    ops.matmul = probe.wrap("torch.mm(cuBLAS sgemm)", mm_orig, lambda a, b: 2.0 * a.shape[0] * a.shape[1] * b.shape[1])
-    ops.linear = probe.wrap("torch.linear(cuBLAS sgemm)", lin_orig,
-                            lambda x, w, b=None, *r: 2.0 * x.shape[0] * x.shape[1] * w.shape[0])
-    for i in range(min(args.steps, 4)):
-        flush.zero_()
-        runner.infer_window_device(devw[i % len(devw)])
-    torch.cuda.synchronize()
-    if graph_mode:
-        runner._force_eager = False
-    for name, fn in originals.items():
-        setattr(lib, name, fn)
-    ops.matmul, ops.linear = mm_orig, lin_orig
-    summ = probe.summary()
-    pk = peaks()
-    traffic, traffic_note = None, None
-    tpath = os.path.join(REPO, "profiles", "r1_conv_tc_f16_192_ncu_full.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic = tj["traffic_bytes"]
-        traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (%s) from ncu --set full: %.2f MB against %.2f MB "
-                        "algorithmic for that launch" % (tj["launch"], tj["traffic_bytes"] / 1e6, tj["algorithmic_bytes"] / 1e6))
-    conv = [v for k, v in summ.items() if k.startswith("conv_tc") or k.startswith("ltn_conv_tc")]
-    conv16 = [v for k, v in summ.items() if k.startswith("conv_tc_f16") or k == "ltn_conv_tc_f16"]
-    roofline = None
-    if conv and sum(v["ms_total"] for v in conv) > 0:
-        ms_c, fl_c, n_c = sum(v["ms_total"] for v in conv), sum(v["work"] for v in conv), sum(v["launches"] for v in conv)
-        achieved = fl_c / (ms_c * 1e-3) / 1e12
-        fl16 = sum(v["work"] for v in conv16)
-        roofline = {"kernel": "k_conv_tc (fused gather + GroupNorm/ReLU + tcgen05 GEMM, fp32-parity 3-pass hi/lo split; fp16 operands "
-                              "where C %% 64 == 0 [%.0f %% of the flop], tf32 operands otherwise)" % (100.0 * fl16 / max(fl_c, 1.0)), "bound": "tensor",
-                    "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"] + " (bf16 sustained)",
-                    "note": "achieved = algorithmic 2*V*S*C*F flop / CUDA-event time over every launch of the kernel in a repeat "
-                            "of the timed steps (op-by-op launches); the parity mode issues 3 MMAs per product (fp16 operands at the "
-                            "bf16 rate, tf32 at half of it), so 1/3 (fp16) resp. 1/6 (tf32) of the bf16 peak is this kernel's ceiling",
-                    "tensor_flops_issued_tflops": 3 * achieved, "launches_per_step": n_c / min(args.steps, 4),
-                    "avg_launch_us": 1e3 * ms_c / n_c, "share_of_step_ms": ms_c / min(args.steps, 4)}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    pk = peaks()
+    # ---- roofline of the dominant kernel, measured INSIDE the replayed graphs of the timed configuration -------------
+    roofline = roofline_of(multi if lockstep else None, runner, devw, frames, lanes, pk, ms_max / timed_steps, lib, args)
+
     hbm = None
-    try:
-        hbm = hbm_kernels(dev, windows_np[0], pk)
-    except Exception as e:
-        hbm = [{"failed": repr(e)}]
-    cpu = None
+    if not args.no_hbm:
+        try:
+            hbm = hbm_kernels(dev, make_windows(1, 1000)[0], pk)
+        except Exception as e:
+            hbm = [{"failed": repr(e)}]
+
+    # ---- CPU baseline (the oracle on the host cores) + label agreement of the timed window with it ---------------------
+    cpu, parity = None, None
     if not args.no_cpu_baseline and world == 1:
         try:
-            sec, cores = cpu_window_seconds(windows_np[0])
-            cpu = {"value": FRAMES / sec, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "one whole 4-frame window of the same workload (oracle/window_oracle.py), %.1f s" % sec}
+            sec, cores, want = cpu_window(cfg, classes, windows_np[0])
+            cpu = {"value": scans / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "one whole window of the same workload (oracle/window_oracle.py), %.1f s" % sec}
+            got = (multi.infer_windows_device([devw[j % nw] for j in range(lanes)])[0] if multi is not None
+                   else runner.infer_window_device(devw[0])).float().cpu().numpy()
+            want = want.numpy()
+            fin = np.isfinite(want).all(1) & np.isfinite(got).all(1)
+            agree = float((got[fin].argmax(1) == want[fin].argmax(1)).mean()) if fin.any() else None
+            err = float(np.abs(got[fin] - want[fin]).max() / (np.abs(want[fin]).max() + 1e-30)) if fin.any() else None
+            parity = {"window": "first timed window (seed 1000), last frame", "label_agreement_with_cpu_oracle": agree,
+                      "log_softmax_max_err_over_absmax": err, "finite_rows": float(fin.mean()),
+                      "nonfinite_mask_agreement": float((np.isfinite(want) == np.isfinite(got)).mean())}
+            if agree is not None and agree < 0.999:
+                raise AssertionError("the timed window's labels disagree with the CPU oracle: %r" % (parity,))
+        except AssertionError:
+            raise
         except Exception as e:  # the baseline leg must never take the GPU number down with it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
 
-    total_scans = FRAMES * args.steps * world
+    ref_driver = None
+    if args.driver == "reference" and world == 1:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "reference_driver.py"), "bench", "12", "3"],
+                               capture_output=True, text=True, timeout=900)
+            ref_driver = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1]) if r.returncode == 0 else {"failed": r.stderr[-500:]}
+        except Exception as e:
+            ref_driver = {"failed": repr(e)}
+
+    lvl = runner.static_lattice if getattr(runner, "caps", None) and graph_mode else runner.lattice
+    v_counts = []
+    while lvl is not None:
+        v_counts.append(int(lvl.hash_table.count_tensor().cpu()))
+        lvl = lvl._coarse
+    total_scans = scans * timed_steps * world
+    if lockstep:
+        execution = ("lock-step group of %d windows per GPU: ONE CUDA graph per frame kind covers all of them, every tensor-core layer is one "
+                     "persistent batched launch (k_conv_tc_batched), the other kernels run on per-window streams inside the graph" % lanes)
+    elif graph_mode:
+        execution = "CUDA-graph replay per frame kind, %d window(s) in flight per GPU (one stream + one graph each)" % lanes
+    else:
+        execution = "eager op-by-op launches"
     line = {"metric": METRIC, "value": total_scans / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / timed_steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points_per_scan": pts, "frames": FRAMES, "vertices_per_level_after_4_frames": v_counts,
-                       "precision": "fp32 results: every tensor-core product is the 3-pass hi/lo split (fp16 operands, exact power-of-two "
-                                    "scaling, fp32 accumulation; range-flagged with a tf32 hi/lo re-run), 2e-5 * sum|a||w| of float64 in the tests",
-                       "l2": "256 MB flush between steps; per-step working set (im2row buffers) also exceeds L2",
-                       "parallelism": "windows sharded over %d rank(s) (every rank runs its own copy of the same synthetic windows), no data-path collective" % world,
-                       "execution": ("CUDA-graph replay per frame kind, %d window(s) in flight per GPU (one stream each), "
-                                     "static capacities %s, capacities respected: %s" % (lanes, runner.caps, capacity_ok))
-                       if graph_mode else "eager op-by-op launches"},
+            "config": config_of(args, desc, windows_np, scans),
+            "details": {"vertices_per_level_after_last_window": v_counts,
+                        "precision": "fp32 results: every tensor-core product is the 3-pass hi/lo split (fp16 operands, exact power-of-two "
+                                     "scaling, fp32 accumulation; range-flagged with a tf32 hi/lo re-run), 2e-5 * sum|a||w| of float64 in the tests",
+                        "l2": "256 MB flush between groups; the per-window working set also exceeds L2",
+                        "parallelism": "windows sharded over %d rank(s), each rank cycles its own %d windows, no data-path collective" % (world, nw),
+                        "execution": execution, "static_capacities": getattr(runner, "caps", None), "capacities_respected": capacity_ok,
+                        "timing": {"repeats_of_the_K_step_loop": repeats, "timed_steps_total": timed_steps, "timed_ms_total": ms_max,
+                                   "ms_per_group_of_%d" % lanes: stats_ms([m for m, (_, _, n) in zip(group_ms, evs) if n == lanes] or group_ms),
+                                   "per_rank_ms_total": per_rank_ms}},
             "e2e": {"value": total_scans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "hbm_kernels": hbm, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "hbm_kernels": hbm, "cpu_baseline": cpu, "parity": parity}
+    if ref_driver is not None:
+        line["reference_driver"] = ref_driver
     if graph_mode:   # windows that left the graph path: static capacities exceeded / fp16 operand range flag raised
         line["fallbacks"] = {"eager_reruns": sum(l.fallbacks for l in multi.lanes), "fp16_range": sum(l.range_fallbacks for l in multi.lanes)}
-    if args.breakdown:
-        line["breakdown_ms_per_step"] = {k: v["ms_total"] / min(args.steps, 4) for k, v in
-                                         sorted(summ.items(), key=lambda kv: -kv[1]["ms_total"])}
-        line["gemm_tflops"] = {k: v["work"] / (v["ms_total"] * 1e-3) / 1e12 for k, v in summ.items()
-                               if (k.startswith("torch.") or k.startswith("conv_tc")) and v["ms_total"] > 0}
-        line["launches_per_step"] = {k: v["launches"] / min(args.steps, 4) for k, v in summ.items()}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def roofline_of(lockstep_runner, runner, devw, frames, lanes, pk, ms_per_step, lib, args):
+    """Tensor roofline of the dominant kernel.  Lock-step mode: every batched launch stamps %globaltimer at the entry and
+    exit of each CTA into a trace buffer (csrc/ltn_conv_batched.cu), so the durations are those of the launches INSIDE
+    the replayed graphs of the timed configuration -- with the other windows' small kernels running beside them, warm
+    weights, real data.  duration of a launch = last CTA exit - first CTA entry."""
+    note3 = ("the parity mode issues 3 MMAs per product (fp16 operands at the bf16 rate), so 1/3 of the bf16 peak is this kernel's ceiling")
+    traffic, traffic_note = None, None
+    for name in ("r2_conv_batched_192_ncu_full.json", "r1_conv_tc_f16_192_ncu_full.json"):
+        tpath = os.path.join(REPO, "profiles", name)
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["traffic_bytes"]
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (%s) from ncu --set full (profiles/%s): %.2f MB "
+                            "against %.2f MB algorithmic for that launch" % (tj["launch"], name, tj["traffic_bytes"] / 1e6, tj["algorithmic_bytes"] / 1e6))
+            break
+    if lockstep_runner is None or not hasattr(lockstep_runner, "trace_group"):
+        return {"kernel": "k_conv_tc", "bound": "tensor", "achieved": None, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": None,
+                "traffic": traffic, "note": "per-launch timing is only available in the lock-step execution mode"}
+    nw = len(devw)
+    rec = lockstep_runner.trace_group([devw[j % nw] for j in range(lanes)])
+    if not rec:
+        return None
+    total_us = sum(r["us"] for r in rec)
+    total_fl = sum(r["flop"] for r in rec)
+    by_shape = {}
+    for r in rec:
+        k = "C%d S%d F%d rows~%dk" % (r["C"], r["S"], r["F"], round(r["rows"] / 1000.0))
+        e = by_shape.setdefault(k, {"launches": 0, "us": 0.0, "flop": 0.0})
+        e["launches"] += 1
+        e["us"] += r["us"]
+        e["flop"] += r["flop"]
+    shapes = {k: {"launches": v["launches"], "us_total": v["us"], "tflops": v["flop"] / (v["us"] * 1e-6) / 1e12 if v["us"] > 0 else None,
+                  "frac_of_bf16_sustained": v["flop"] / (v["us"] * 1e-6) / 1e12 / pk["bf16_tflops_sustained"] if v["us"] > 0 else None}
+              for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1]["us"])}
+    achieved = total_fl / (total_us * 1e-6) / 1e12
+    ceiling = pk["bf16_tflops_sustained"] / 3.0
+    step_tf = (total_fl / lanes) / (ms_per_step * 1e-3) / 1e12
+    return {"kernel": "k_conv_tc_batched (fused gather + GroupNorm/ReLU + tcgen05 GEMM, fp32-parity 3-pass fp16 hi/lo split; one persistent "
+                      "launch per layer for the %d windows in flight)" % lanes,
+            "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
+            "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"] + " (bf16 sustained)",
+            "frac_of_3pass_ceiling": achieved / ceiling, "ceiling_3pass": ceiling,
+            "note": "achieved = algorithmic 2*V*S*C*F flop of every batched launch of one group of %d windows / the sum of their in-graph durations "
+                    "(globaltimer stamps of the first CTA entry and last CTA exit); %s" % (lanes, note3),
+            "launches_per_group": len(rec), "avg_launch_us": total_us / len(rec),
+            "kernel_ms_per_group": total_us / 1e3, "share_of_group_time": (total_us / 1e3) / (ms_per_step * lanes),
+            "whole_step": {"gflop_per_window": total_fl / lanes / 1e9, "tflops": step_tf, "frac": step_tf / pk["bf16_tflops_sustained"],
+                           "note": "algorithmic conv flop of a window / ms_per_step: what the whole step achieves, everything included"},
+            "tensor_flops_issued_tflops": 3 * achieved, "per_shape": shapes}
 
 
 if __name__ == "__main__":

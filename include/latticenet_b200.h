@@ -153,8 +153,11 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
                             int a_log2, int F, const double* const* gn_sums, const float* gn_gamma, const float* gn_beta,
                             float gn_eps, int gn_groups, int relu, const float* bias, const float* const* res, float* const* out,
                             int ldo, double* const* out_sums, int out_groups, int* const* flag, void* stream);
-/* per-CTA [start, end] globaltimer stamps of the following batched launches (NULL switches it off) */
-int ltn_conv_batched_trace(unsigned long long* buf);
+/* tracing of the following batched launches: launch i < nr_records writes record i of buf ([nr_records, 2 + 2*148] u64,
+ * zeroed by the caller): live rows, tiles, then (entry, exit) globaltimer ns per CTA; the record address is baked into the
+ * launch (captured launches keep writing on every replay).  NULL switches it off.  Returns the records used since the
+ * previous call. */
+int ltn_conv_batched_trace(unsigned long long* buf, int nr_records);
 /* phase tracing of the following ltn_conv_tc* launches (NULL switches it off): buf receives 8 globaltimer stamps (ns)
  * per CTA in launch-grid order -- entry, set-up done, first operands staged, producers done, accumulator complete,
  * epilogue stores issued, teardown, (unused) */

@@ -56,14 +56,16 @@ struct BatchParams {
     int n_tile, ny;
     int stages_a, stages_b, acc_bufs, acc_stride;
     float a_mul, out_mul;
-    unsigned long long* trace;        // nullable: per CTA [tiles done, first tile start, last tile end] (globaltimer)
+    unsigned long long* trace;        // nullable: this launch's trace record: [sum of live rows, tiles, then per CTA (entry, exit)] globaltimer ns
 };
 
 struct Tile {
     int b, row0, n0, N, Nmma;
 };
 
+constexpr int kTraceStride = 2 + 2 * 148;   // u64 per launch record
 unsigned long long* g_trace_b = nullptr;
+int g_trace_slots = 0, g_trace_next = 0;
 
 __global__ void __launch_bounds__(kThreadsB, 1)
 k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
@@ -459,8 +461,14 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     if (p.trace && tid == 0) {
         unsigned long long t_last;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
-        p.trace[(size_t)blockIdx.x * 2] = t_first;
-        p.trace[(size_t)blockIdx.x * 2 + 1] = t_last;
+        p.trace[2 + (size_t)blockIdx.x * 2] = t_first;
+        p.trace[3 + (size_t)blockIdx.x * 2] = t_last;
+        if (blockIdx.x == 0) {
+            unsigned long long rows = 0;
+            for (int b = 0; b < p.nb; ++b) rows += (unsigned long long)max(s_vq[b], 0);
+            p.trace[0] = rows;
+            p.trace[1] = (unsigned long long)total_tiles;
+        }
     }
 }
 
@@ -468,9 +476,16 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
 
 extern "C" {
 
-int ltn_conv_batched_trace(unsigned long long* buf) {
+// Tracing of the following batched launches: launch i (i < nr_records) writes record i of buf ([nr_records, 2 + 2*148] u64,
+// zeroed by the caller): [0] = live rows summed over its problems, [1] = tiles, then (entry, exit) %globaltimer stamps per
+// CTA.  The record address is baked into the launch, so launches captured into a CUDA graph keep writing their record on
+// every replay.  buf = NULL switches tracing off.  Returns the number of records handed out since the last call.
+int ltn_conv_batched_trace(unsigned long long* buf, int nr_records) {
+    const int used = g_trace_next;
     g_trace_b = buf;
-    return 0;
+    g_trace_slots = buf ? nr_records : 0;
+    g_trace_next = 0;
+    return used;
 }
 
 // The fp16-operand fused convolution of ltn_conv_tc_f16 for nb <= 8 independent problems that share the weights (the same
@@ -517,7 +532,7 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
     p.C = C; p.S = has_nbr ? S : 1; p.F = F; p.ldo = ldo; p.relu = relu; p.has_gn = has_gn ? 1 : 0; p.has_sums = has_sums ? 1 : 0;
     p.a_mul = ldexpf(1.0f, a_log2);
     p.out_mul = ldexpf(1.0f, -(a_log2 + w_log2));
-    p.trace = g_trace_b;
+    p.trace = (g_trace_b && g_trace_next < g_trace_slots) ? g_trace_b + (size_t)kTraceStride * g_trace_next++ : nullptr;
     // Output channels per tile: at most 192, so that TWO accumulators and an A ring of >= 2 stages fit the 512 columns of
     // tensor memory; fewer when the tile list would leave SMs idle (small levels).
     static const int n_cap = []() { const char* e = getenv("LTN_CONVB_NCAP"); return e && atoi(e) >= 16 ? atoi(e) : 192; }();

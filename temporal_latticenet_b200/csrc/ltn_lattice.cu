@@ -26,7 +26,9 @@ __global__ void k_hash_clear(uint64_t* slot_keys, int* slot_ids, int* slot_first
     if (i < 8) counters[i] = 0;
 }
 
-// one thread per point; 4 dedupe rounds per warp
+// one thread per point; 4 dedupe rounds per warp.  The four ranks of a point are INDEPENDENT table operations, so their
+// dependent L2 round trips (first probe -> id of the slot -> atomicMin) are issued rank-interleaved: 3-4 latencies per
+// warp instead of 12.
 __global__ void __launch_bounds__(kThreads)
 k_insert_points(const float* __restrict__ pos, int N, const int* __restrict__ n_dev, float sx, float sy, float sz,
                 uint64_t* slot_keys, const int* __restrict__ slot_ids, int* slot_first, int nslots, int* counters,
@@ -40,36 +42,57 @@ k_insert_points(const float* __restrict__ pos, int N, const int* __restrict__ n_
         ltn_simplex(pos[(size_t)p * 3], pos[(size_t)p * 3 + 1], pos[(size_t)p * 3 + 2], sx, sy, sz, key, bary);
     }
     const unsigned lane = threadIdx.x & 31u;
-    int slots[LTN_D1];
+    const uint32_t m = (uint32_t)nslots - 1u;
+    uint64_t k[LTN_D1], first[LTN_D1];
+    uint32_t h[LTN_D1];
+    int leader[LTN_D1];
+    bool ok[LTN_D1], mine[LTN_D1];
+    int nbad = 0;
 #pragma unroll
     for (int r = 0; r < LTN_D1; ++r) {
-        bool ok = valid && ltn_in_range(key[r][0], key[r][1], key[r][2]);
+        ok[r] = valid && ltn_in_range(key[r][0], key[r][1], key[r][2]);
+        nbad += (valid && !ok[r]) ? 1 : 0;
         // lanes without a key take a private dummy so they never match a real one
-        uint64_t k = ok ? ltn_pack(key[r][0], key[r][1], key[r][2]) : (LTN_EMPTY - 1ull - lane);
-        unsigned peers = __match_any_sync(0xffffffffu, k);
-        int leader = __ffs(peers) - 1;
-        int slot = -1;
-        if ((int)lane == leader && ok) {
-            slot = ltn_claim_slot(k, slot_keys, nslots);
-            // rows grow with the lane index, so the leader holds the group's smallest row
-            if (slot >= 0 && __ldcg(slot_ids + slot) < 0) atomicMin(slot_first + slot, p * LTN_D1 + r);
-        }
-        slot = __shfl_sync(0xffffffffu, slot, leader);
-        if (valid && !ok) atomicAdd(counters + LTN_CNT_RANGE, 1);
-        slots[r] = ok ? slot : -1;
+        k[r] = ok[r] ? ltn_pack(key[r][0], key[r][1], key[r][2]) : (LTN_EMPTY - 1ull - lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, k[r]);
+        leader[r] = __ffs(peers) - 1;
+        mine[r] = ((int)lane == leader[r]) && ok[r];
+        h[r] = ltn_hash(k[r]) & m;
     }
+#pragma unroll
+    for (int r = 0; r < LTN_D1; ++r) first[r] = mine[r] ? __ldcg(slot_keys + h[r]) : 0ull;   // four probes in flight
+    int slots[LTN_D1], ids[LTN_D1];
+#pragma unroll
+    for (int r = 0; r < LTN_D1; ++r) {
+        int slot = -1;
+        if (mine[r]) slot = (first[r] == k[r]) ? (int)h[r] : ltn_claim_slot(k[r], slot_keys, nslots);
+        slots[r] = slot;
+    }
+#pragma unroll
+    for (int r = 0; r < LTN_D1; ++r) ids[r] = (mine[r] && slots[r] >= 0) ? __ldcg(slot_ids + slots[r]) : 0;
+#pragma unroll
+    for (int r = 0; r < LTN_D1; ++r) {
+        // rows grow with the lane index, so the leader holds the group's smallest row
+        if (mine[r] && slots[r] >= 0 && ids[r] < 0) atomicMin(slot_first + slots[r], p * LTN_D1 + r);
+        const int sl = __shfl_sync(0xffffffffu, slots[r], leader[r]);
+        slots[r] = ok[r] ? sl : -1;
+    }
+    if (nbad) atomicAdd(counters + LTN_CNT_RANGE, nbad);
     if (valid) {
         *reinterpret_cast<int4*>(row_slot + (size_t)p * LTN_D1) = make_int4(slots[0], slots[1], slots[2], slots[3]);
         if (row_w) *reinterpret_cast<float4*>(row_w + (size_t)p * LTN_D1) = make_float4(bary[0], bary[1], bary[2], bary[3]);
     }
 }
 
+// Is `row` the first appearance of a vertex that is new in this batch?  slot_first[s] is only ever lowered (atomicMin in
+// k_insert_points) for slots that have no id yet and is put back to INT_MAX when the id is assigned, so
+// slot_first[s] == row says both "new" and "first": ONE random table read per row.
 __device__ __forceinline__ int is_first_row(int row, int R, const int* __restrict__ row_slot,
                                             const int* __restrict__ slot_ids, const int* __restrict__ slot_first) {
     if (row >= R) return 0;
     int s = row_slot[row];
     if (s < 0) return 0;
-    return (__ldcg(slot_ids + s) < 0 && __ldcg(slot_first + s) == row) ? 1 : 0;
+    return __ldcg(slot_first + s) == row ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(kScanBlock)
@@ -159,40 +182,31 @@ k_number_assign(const int* __restrict__ row_slot, int R, const int* __restrict__
     }
 }
 
-// distribute, second half: slot -> id, rows [4N, 3+vd+1], per-vertex position sums (double) + count.
+// distribute, second half (a): slot -> id, per-vertex position sums (double) + count.  No row is written yet: the
+// local mean has to be known first, and every [4N, 3+vd+1] row is then written exactly once (k_distribute_write).
 // The sums are warp-aggregated: the 32 points of a warp are scan neighbours and mostly share their simplex
 // vertices, so lanes with the same vertex id add up inside the warp and one lane issues the double atomics.
+// (Sums of <= 2^29 float32 values in double are exact, so the result does not depend on the order of the atomics.)
 __global__ void __launch_bounds__(kThreads)
-k_distribute_rows(const float* __restrict__ pos, const float* __restrict__ val, int N, const int* __restrict__ n_dev, int vd,
-                  const int* __restrict__ row_slot, const float* __restrict__ row_w,
-                  const int* __restrict__ slot_ids, float* __restrict__ rows, int* __restrict__ idx,
-                  double* vert_acc) {
+k_distribute_sums(const float* __restrict__ pos, int N, const int* __restrict__ n_dev, const int* __restrict__ row_slot,
+                  const int* __restrict__ slot_ids, int* __restrict__ idx, double* vert_acc) {
     if (n_dev) N = min(N, *n_dev);
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = p < N;   // no early return: the warp-wide aggregation below needs every lane
-    const int width = LTN_D + vd + 1;
     float px = 0.f, py = 0.f, pz = 0.f;
     int s[4] = {-1, -1, -1, -1};
-    float w[4] = {0.f, 0.f, 0.f, 0.f};
     if (valid) {
         px = pos[(size_t)p * 3]; py = pos[(size_t)p * 3 + 1]; pz = pos[(size_t)p * 3 + 2];
         int4 s4 = *reinterpret_cast<const int4*>(row_slot + (size_t)p * LTN_D1);
-        float4 w4 = *reinterpret_cast<const float4*>(row_w + (size_t)p * LTN_D1);
         s[0] = s4.x; s[1] = s4.y; s[2] = s4.z; s[3] = s4.w;
-        w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
     }
     int ids[4];
 #pragma unroll
+    for (int r = 0; r < LTN_D1; ++r) ids[r] = (s[r] >= 0) ? __ldg(slot_ids + s[r]) : -1;   // four lookups in flight
+    if (valid) *reinterpret_cast<int4*>(idx + (size_t)p * LTN_D1) = make_int4(ids[0], ids[1], ids[2], ids[3]);
+#pragma unroll
     for (int r = 0; r < LTN_D1; ++r) {
-        int id = (s[r] >= 0) ? __ldg(slot_ids + s[r]) : -1;
-        ids[r] = id;
-        if (valid) {
-            float* o = rows + ((size_t)p * LTN_D1 + r) * width;
-            o[0] = px; o[1] = py; o[2] = pz;
-            for (int i = 0; i < vd; ++i) o[LTN_D + i] = val[(size_t)p * vd + i];
-            o[LTN_D + vd] = w[r];
-        }
-        const int a = valid ? (id < 0 ? 0 : id) : -1;  // ids < 0 fold onto vertex 0 (lattice_modules.py:479-480)
+        const int a = valid ? (ids[r] < 0 ? 0 : ids[r]) : -1;  // ids < 0 fold onto vertex 0 (lattice_modules.py:479-480)
         float sum[3] = {px, py, pz};
         int cnt;
         if (ltn_warp_group_sum<3>(a, sum, cnt)) {
@@ -202,24 +216,49 @@ k_distribute_rows(const float* __restrict__ pos, const float* __restrict__ val, 
             atomicAdd(vert_acc + (size_t)a * 4 + 3, (double)cnt);
         }
     }
-    if (valid) *reinterpret_cast<int4*>(idx + (size_t)p * LTN_D1) = make_int4(ids[0], ids[1], ids[2], ids[3]);
 }
 
+// distribute, second half (b): rows[4p + r] = [pos - mean(vertex), val..., w_r], written ONCE.  A block stages the rows
+// of its 256 points in shared memory (thread = point) and streams them out as one contiguous run of 128-bit stores.
 __global__ void __launch_bounds__(kThreads)
-k_local_mean_sub(float* __restrict__ rows, const int* __restrict__ idx, int R, const int* __restrict__ n_dev, int width,
-                 const double* __restrict__ vert_acc) {
-    if (n_dev) R = min(R, *n_dev * LTN_D1);
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    int id = idx[r];
-    id = id < 0 ? 0 : id;
-    double cnt = vert_acc[(size_t)id * 4 + 3];
-    float* o = rows + (size_t)r * width;
+k_distribute_write(const float* __restrict__ pos, const float* __restrict__ val, int N, const int* __restrict__ n_dev, int vd,
+                   const int* __restrict__ idx, const float* __restrict__ row_w, const double* __restrict__ vert_acc,
+                   int subtract_mean, float* __restrict__ rows) {
+    extern __shared__ __align__(16) float s_rows[];
+    if (n_dev) N = min(N, *n_dev);
+    const int width = LTN_D + vd + 1;
+    const int p0 = blockIdx.x * kThreads;
+    const int p = p0 + threadIdx.x;
+    if (p < N) {
+        const float px = pos[(size_t)p * 3], py = pos[(size_t)p * 3 + 1], pz = pos[(size_t)p * 3 + 2];
+        const int4 i4 = *reinterpret_cast<const int4*>(idx + (size_t)p * LTN_D1);
+        const float4 w4 = *reinterpret_cast<const float4*>(row_w + (size_t)p * LTN_D1);
+        const int ids[4] = {i4.x, i4.y, i4.z, i4.w};
+        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-    for (int i = 0; i < LTN_D; ++i) {
-        float mean = (float)(vert_acc[(size_t)id * 4 + i] / cnt);
-        o[i] = __fsub_rn(o[i], mean);
+        for (int r = 0; r < LTN_D1; ++r) {
+            float* o = s_rows + ((size_t)threadIdx.x * LTN_D1 + r) * width;
+            float mx = 0.f, my = 0.f, mz = 0.f;
+            if (subtract_mean) {
+                const int id = ids[r] < 0 ? 0 : ids[r];
+                const double* a = vert_acc + (size_t)id * 4;
+                const double cnt = a[3];
+                mx = (float)(a[0] / cnt); my = (float)(a[1] / cnt); mz = (float)(a[2] / cnt);
+            }
+            o[0] = __fsub_rn(px, mx); o[1] = __fsub_rn(py, my); o[2] = __fsub_rn(pz, mz);
+            for (int i = 0; i < vd; ++i) o[LTN_D + i] = val[(size_t)p * vd + i];
+            o[LTN_D + vd] = w[r];
+        }
     }
+    __syncthreads();
+    const int npts = min(kThreads, N - p0);
+    if (npts <= 0) return;
+    const int nfl = npts * LTN_D1 * width;                    // floats of this block's contiguous run
+    float* dst = rows + (size_t)p0 * LTN_D1 * width;          // 256 * 4 * width floats per block: 16-byte aligned
+    const int n4 = nfl >> 2;
+    for (int i = threadIdx.x; i < n4; i += kThreads)
+        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_rows)[i];
+    for (int i = (n4 << 2) + threadIdx.x; i < nfl; i += kThreads) dst[i] = s_rows[i];
 }
 
 __global__ void k_vertex_counts(const double* __restrict__ vert_acc, int V, float* __restrict__ counts) {
@@ -311,14 +350,17 @@ int ltn_distribute(const float* pos, const float* val, int N, const int* n_dev, 
     if (rc) return rc;
     cudaError_t e = cudaMemsetAsync(vert_acc, 0, sizeof(double) * 4 * (size_t)cap, st);
     if (e != cudaSuccess) return (int)e;
-    k_distribute_rows<<<ltn_blocks(N, kThreads), kThreads, 0, st>>>(pos, val, N, n_dev, val_dim, row_slot, w, slot_ids, rows,
-                                                                    idx, vert_acc);
+    k_distribute_sums<<<ltn_blocks(N, kThreads), kThreads, 0, st>>>(pos, N, n_dev, row_slot, slot_ids, idx, vert_acc);
     LTN_CHECK_LAUNCH();
-    if (subtract_mean) {
-        int R = N * LTN_D1;
-        k_local_mean_sub<<<ltn_blocks(R, kThreads), kThreads, 0, st>>>(rows, idx, R, n_dev, LTN_D + val_dim + 1, vert_acc);
-        LTN_CHECK_LAUNCH();
+    const int width = LTN_D + val_dim + 1;
+    const size_t smem = sizeof(float) * kThreads * LTN_D1 * (size_t)width;
+    if (smem > 200 * 1024) return -2;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(k_distribute_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
     }
+    k_distribute_write<<<ltn_blocks(N, kThreads), kThreads, smem, st>>>(pos, val, N, n_dev, val_dim, idx, w, vert_acc, subtract_mean, rows);
+    LTN_CHECK_LAUNCH();
     return 0;
 }
 

@@ -388,6 +388,7 @@ class _LockstepCoordinator:
         self.errors = [None] * self.n
         self.results = [None] * self.n
         self.batched_launches = 0
+        self.log = []            # (C, S, F) of every batched launch, in issue order
         self._tl = threading.local()
 
     # ---- lane side -------------------------------------------------------------------------------------------------
@@ -447,6 +448,8 @@ class _LockstepCoordinator:
                 done = torch.cuda.Event()
                 done.record(self.main)
             self.batched_launches += 1
+            r0 = self.pending[waiting[0]][0]
+            self.log.append((int(r0["C"]), int(r0["S"]) if r0["nbr"] is not None else 1, int(r0["F"])))
             for i in waiting:
                 self.pending[i] = done
         failed = next((e for e in self.errors if e is not None), None)
@@ -476,9 +479,15 @@ class LockstepRunner:
     Each lane is a GraphWindowRunner (own model copy, lattice, hidden-state buffers, static capacities); windows that
     do not fit the static capacities, and groups smaller than `lanes`, go through the lanes' own per-window paths."""
 
-    def __init__(self, cfg_path, nr_classes=26, device=None, lanes=4, operands="f16"):
+    TRACE_RECORDS = 192      # batched launches per frame kind that can be traced
+    TRACE_STRIDE = 2 + 2 * 148
+
+    def __init__(self, cfg_path, nr_classes=26, device=None, lanes=4, operands="f16", trace=True):
         if lanes < 1 or lanes > ops.MAX_BATCH:
             raise RuntimeError("between 1 and %d lanes" % ops.MAX_BATCH)
+        self.trace = trace       # every batched launch stamps its CTAs' entry / exit times into a per-kind record (trace_group)
+        self.trace_bufs = {}
+        self.layer_log = {}
         self.lanes = [GraphWindowRunner(cfg_path, nr_classes, device, operands=operands) for _ in range(lanes)]
         self.device = self.lanes[0].device
         self.main = torch.cuda.Stream(device=self.device)
@@ -534,8 +543,16 @@ class LockstepRunner:
             graph = torch.cuda.CUDAGraph()
             l0 = _lib.load().ltn_launch_count()
             coord = _LockstepCoordinator(self.main, self.streams)
-            with torch.cuda.graph(graph, pool=self.pool, stream=self.main, capture_error_mode="thread_local"):
-                outs = coord.run(lambda i: self._lane_frame(i, kind))
+            if self.trace:
+                self.trace_bufs[kind] = torch.zeros(self.TRACE_RECORDS, self.TRACE_STRIDE, dtype=torch.int64, device=self.device)
+                _lib.load().ltn_conv_batched_trace(_lib.ptr(self.trace_bufs[kind]), self.TRACE_RECORDS)
+            try:
+                with torch.cuda.graph(graph, pool=self.pool, stream=self.main, capture_error_mode="thread_local"):
+                    outs = coord.run(lambda i: self._lane_frame(i, kind))
+            finally:
+                if self.trace:
+                    _lib.load().ltn_conv_batched_trace(None, 0)
+            self.layer_log[kind] = list(coord.log)
             self.kernels[kind] = _lib.load().ltn_launch_count() - l0
             self.batched[kind] = coord.batched_launches
             if self.pool is None:
@@ -651,6 +668,39 @@ class LockstepRunner:
 
     def infer_windows(self, windows_host):
         return self.collect(self.submit(windows_host))
+
+    def trace_group(self, windows_dev):
+        """Runs one full group and returns one record per batched tensor-core launch, measured INSIDE the replayed graphs:
+        {kind, C, S, F, rows (live, summed over the windows), tiles, ctas, us (first CTA entry -> last CTA exit), flop}."""
+        if not self.trace or not self._fits(windows_dev):
+            return []
+        T = len(windows_dev[0])
+        kinds = [(t == 0, t == T - 1) for t in range(T)]
+        out = []
+        cur = torch.cuda.current_stream()
+        self.main.wait_stream(cur)
+        with torch.cuda.stream(self.main):
+            for t, kind in enumerate(kinds):
+                if kind not in self.graphs:
+                    return []
+                for lane, w in zip(self.lanes, windows_dev):
+                    self._load_inputs(lane, w[t][0], w[t][1])
+                self.trace_bufs[kind].zero_()
+                self.graphs[kind][0].replay()
+                self.main.synchronize()   # the records of this kind are read before the next frame of the same kind overwrites them
+                rec = self.trace_bufs[kind].cpu().numpy()
+                for j, (C, S, F) in enumerate(self.layer_log[kind][: self.TRACE_RECORDS]):
+                    rows, tiles = int(rec[j, 0]), int(rec[j, 1])
+                    stamps = rec[j, 2:].reshape(-1, 2)
+                    live = stamps[:, 0] > 0
+                    if tiles <= 0 or not live.any():
+                        continue
+                    us = float(stamps[live, 1].max() - stamps[live, 0].min()) / 1e3
+                    out.append({"frame": t, "C": C, "S": S, "F": F, "rows": rows, "tiles": tiles, "ctas": int(live.sum()), "us": us,
+                                "flop": 2.0 * rows * S * C * F,
+                                "cta_us_mean": float((stamps[live, 1] - stamps[live, 0]).mean()) / 1e3})
+        cur.wait_stream(self.main)
+        return out
 
     def counts_ok(self):
         return all(l.counts_ok() for l in self.lanes)
