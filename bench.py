@@ -397,7 +397,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm", action="store_true", help="skip the splat / slice / im2row / distribute bandwidth table")
     ap.add_argument("--eager", action="store_true", help="eager per-op launches instead of CUDA-graph replay")
-    ap.add_argument("--lanes", type=int, default=4, help="independent windows in flight per GPU")
+    ap.add_argument("--lanes", type=int, default=4, help="windows per lock-step group (one batched launch per layer serves them)")
+    ap.add_argument("--groups", type=int, default=1, help="lock-step groups in flight per GPU (each with its own graphs and streams)")
     ap.add_argument("--streams", action="store_true", help="round-1 execution: one stream + one graph per window in flight "
                     "(MultiWindowRunner) instead of the lock-step group graph with batched tensor-core launches (LockstepRunner)")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="the K-step timed loop is repeated until it has run this long")
@@ -425,7 +426,7 @@ def main():
     import __graft_entry__ as G
     G.build()
     from temporal_latticenet_b200 import _lib
-    from temporal_latticenet_b200.engine import LockstepRunner, MultiWindowRunner
+    from temporal_latticenet_b200.engine import GroupedLockstepRunner, LockstepRunner, MultiWindowRunner
     from temporal_latticenet_b200.runner import WindowRunner
     from temporal_latticenet_b200.seeding import seeded_state
     lib = _lib.load()
@@ -446,12 +447,18 @@ def main():
         runner.materialise_parameters(devw[0], seeded_state)
         multi, lanes = None, 1
     else:
-        Runner = MultiWindowRunner if args.streams else LockstepRunner
-        multi = Runner(cfg, classes, dev, lanes=lanes).prepare(devw[0], seeded_state, devw)
+        if args.streams:
+            multi = MultiWindowRunner(cfg, classes, dev, lanes=lanes)
+        elif args.groups > 1:
+            multi = GroupedLockstepRunner(cfg, classes, dev, lanes=lanes, groups=args.groups)
+            lanes = lanes * args.groups      # windows in flight per GPU
+        else:
+            multi = LockstepRunner(cfg, classes, dev, lanes=lanes)
+        multi.prepare(devw[0], seeded_state, devw)
         runner = multi.lanes[0]
         if not multi.supported:
             multi, lanes = None, 1
-    lockstep = isinstance(multi, LockstepRunner)
+    lockstep = isinstance(multi, (LockstepRunner, GroupedLockstepRunner))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -501,7 +508,9 @@ def main():
     capacity_ok = None
     if graph_mode:   # replayed graphs: the library's host-side counter saw the kernels once, at capture
         if lockstep:
-            launches = sum((multi.kernels_per_group(frames) if n == lanes else n * runner.kernels_per_window(frames)) for _, _, n in evs)
+            one = multi.groups[0] if hasattr(multi, "groups") else multi
+            per = len(one.lanes)
+            launches = sum((n // per) * one.kernels_per_group(frames) + (n % per) * runner.kernels_per_window(frames) for _, _, n in evs)
         else:
             launches = sum(n for _, _, n in evs) * runner.kernels_per_window(frames)
         capacity_ok = multi.counts_ok()
@@ -552,7 +561,8 @@ def main():
 
     pk = peaks()
     # ---- roofline of the dominant kernel, measured INSIDE the replayed graphs of the timed configuration -------------
-    roofline = roofline_of(multi if lockstep else None, runner, devw, frames, lanes, pk, ms_max / timed_steps, lib, args)
+    roofline = roofline_of(multi if lockstep else None, runner, devw, frames, lanes, max(1, args.groups) if lockstep else 1, pk,
+                           ms_max / timed_steps, lib, args)
 
     hbm = None
     if not args.no_hbm:
@@ -600,8 +610,9 @@ def main():
         lvl = lvl._coarse
     total_scans = scans * timed_steps * world
     if lockstep:
-        execution = ("lock-step group of %d windows per GPU: ONE CUDA graph per frame kind covers all of them, every tensor-core layer is one "
-                     "persistent batched launch (k_conv_tc_batched), the other kernels run on per-window streams inside the graph" % lanes)
+        execution = ("%d lock-step group(s) of %d windows per GPU: ONE CUDA graph per frame kind covers a group, every tensor-core layer is one "
+                     "persistent batched launch (k_conv_tc_batched), the other kernels run on per-window streams inside the graph"
+                     % (max(1, args.groups), lanes // max(1, args.groups)))
     elif graph_mode:
         execution = "CUDA-graph replay per frame kind, %d window(s) in flight per GPU (one stream + one graph each)" % lanes
     else:
@@ -630,7 +641,7 @@ def main():
         dist.destroy_process_group()
 
 
-def roofline_of(lockstep_runner, runner, devw, frames, lanes, pk, ms_per_step, lib, args):
+def roofline_of(lockstep_runner, runner, devw, frames, lanes, groups, pk, ms_per_step, lib, args):
     """Tensor roofline of the dominant kernel.  Lock-step mode: every batched launch stamps %globaltimer at the entry and
     exit of each CTA into a trace buffer (csrc/ltn_conv_batched.cu), so the durations are those of the launches INSIDE
     the replayed graphs of the timed configuration -- with the other windows' small kernels running beside them, warm
@@ -667,17 +678,19 @@ def roofline_of(lockstep_runner, runner, devw, frames, lanes, pk, ms_per_step, l
               for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1]["us"])}
     achieved = total_fl / (total_us * 1e-6) / 1e12
     ceiling = pk["bf16_tflops_sustained"] / 3.0
-    step_tf = (total_fl / lanes) / (ms_per_step * 1e-3) / 1e12
+    per = lanes // groups    # windows whose launches `rec` holds (one lock-step group)
+    step_tf = (total_fl / per) / (ms_per_step * 1e-3) / 1e12
     return {"kernel": "k_conv_tc_batched (fused gather + GroupNorm/ReLU + tcgen05 GEMM, fp32-parity 3-pass fp16 hi/lo split; one persistent "
-                      "launch per layer for the %d windows in flight)" % lanes,
+                      "launch per layer for the %d windows of a lock-step group)" % per,
             "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
             "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"] + " (bf16 sustained)",
             "frac_of_3pass_ceiling": achieved / ceiling, "ceiling_3pass": ceiling,
             "note": "achieved = algorithmic 2*V*S*C*F flop of every batched launch of one group of %d windows / the sum of their in-graph durations "
-                    "(globaltimer stamps of the first CTA entry and last CTA exit); %s" % (lanes, note3),
+                    "(globaltimer stamps of the first CTA entry and last CTA exit); %s" % (per, note3),
             "launches_per_group": len(rec), "avg_launch_us": total_us / len(rec),
-            "kernel_ms_per_group": total_us / 1e3, "share_of_group_time": (total_us / 1e3) / (ms_per_step * lanes),
-            "whole_step": {"gflop_per_window": total_fl / lanes / 1e9, "tflops": step_tf, "frac": step_tf / pk["bf16_tflops_sustained"],
+            "kernel_ms_per_group": total_us / 1e3, "share_of_step": (total_us / 1e3 / per) / ms_per_step,
+            "share_note": "kernel time per window / ms_per_step; with several groups in flight the groups' launches overlap, so this can exceed 1/groups but never 1",
+            "whole_step": {"gflop_per_window": total_fl / per / 1e9, "tflops": step_tf, "frac": step_tf / pk["bf16_tflops_sustained"],
                            "note": "algorithmic conv flop of a window / ms_per_step: what the whole step achieves, everything included"},
             "tensor_flops_issued_tflops": 3 * achieved, "per_shape": shapes}
 

@@ -111,6 +111,11 @@ int ltn_gn_apply(const float* x, int V, const int* v_dev, int C, int G, const do
 
 /* ---- fused convolution on the tensor cores (csrc/ltn_conv.cu) ------------------------------------- */
 
+/* GroupNorm(+ReLU) backward of the modules above (train_ln.py:229-231 loss.backward()): y (nullable) = forward output when
+ * ReLU was fused; sums [G,2] = forward statistics; chan [C,2] double returns (grad beta, grad gamma) per channel; gx [V,C] */
+int ltn_gn_bwd(const float* x, const float* gy, const float* y, int V, int C, int G, const double* sums, const float* gamma,
+               float eps, double* chan, float* gx, void* stream);
+
 /* ConvLatticeModule / CoarsenLattice / FinefyLattice (lattice_modules.py:440,573; models.py:353,398) and
  * the dense layers around them (GnRelu1x1, Conv1x1, nn.Linear, GRU/LSTM gate GEMMs) WITHOUT the [V,9C]
  * im2row buffer:  out[v,f] = sum_{s<S} sum_c act(x[nbr[v,s],c]) * W[s*C+c, f] (+bias[f]) (+res[v,f]),

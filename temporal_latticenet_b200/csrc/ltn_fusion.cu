@@ -42,6 +42,43 @@ k_gru_pointwise(const float* __restrict__ gi, const float* __restrict__ gh, cons
     }
 }
 
+// the same, four channels per thread (C % 4 == 0): seven 128-bit loads and one 128-bit store instead of 28 + 4 scalar ones
+__device__ __forceinline__ float gru_gate(float gir, float giz, float gin, float hr, float hz, float hn, float hp) {
+    const float r = sigmoidf_(gir + hr);
+    const float z = sigmoidf_(giz + hz);
+    const float n = tanhf(gin + r * hn);
+    return (1.0f - z) * n + z * hp;
+}
+__global__ void __launch_bounds__(kThreads)
+k_gru_pointwise4(const float4* __restrict__ gi, const float4* __restrict__ gh, const float4* __restrict__ h,
+                 const float4* __restrict__ b_hh, int V, int Vh, const int* __restrict__ v_dev,
+                 const int* __restrict__ vh_dev, int C4, float4* __restrict__ out) {
+    if (v_dev) V = min(V, *v_dev);
+    if (vh_dev) Vh = min(Vh, *vh_dev);
+    const long long total = (long long)V * C4;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(t / C4);
+        const int c = (int)(t - (long long)v * C4);
+        const float4* gi_v = gi + (size_t)v * 3 * C4;
+        const float4 a = __ldg(gi_v + c), b = __ldg(gi_v + C4 + c), d = __ldg(gi_v + 2 * C4 + c);
+        float4 hr, hz, hn, hp;
+        if (v < Vh) {
+            const float4* gh_v = gh + (size_t)v * 3 * C4;
+            hr = __ldg(gh_v + c); hz = __ldg(gh_v + C4 + c); hn = __ldg(gh_v + 2 * C4 + c);
+            hp = __ldg(h + t);
+        } else {
+            hr = __ldg(b_hh + c); hz = __ldg(b_hh + C4 + c); hn = __ldg(b_hh + 2 * C4 + c);
+            hp = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float4 o;
+        o.x = gru_gate(a.x, b.x, d.x, hr.x, hz.x, hn.x, hp.x);
+        o.y = gru_gate(a.y, b.y, d.y, hr.y, hz.y, hn.y, hp.y);
+        o.z = gru_gate(a.z, b.z, d.z, hr.z, hz.z, hn.z, hp.z);
+        o.w = gru_gate(a.w, b.w, d.w, hr.w, hz.w, hn.w, hp.w);
+        out[t] = o;
+    }
+}
+
 // LSTMCell pointwise with c_prev = 0 (lattice_modules.py:36; gate order i,f,g,o):
 //   c' = s(i)*tanh(g) ; h' = s(o)*tanh(c')
 __global__ void __launch_bounds__(kThreads)
@@ -150,6 +187,13 @@ extern "C" {
 int ltn_gru_pointwise(const float* gi, const float* gh, const float* h, const float* b_hh, int V, int Vh, const int* v_dev,
                       const int* vh_dev, int C, float* out, void* stream) {
     if (V <= 0) return 0;
+    if (C % 4 == 0) {
+        k_gru_pointwise4<<<grid_for((long long)V * (C / 4), kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(gi), reinterpret_cast<const float4*>(gh), reinterpret_cast<const float4*>(h),
+            reinterpret_cast<const float4*>(b_hh), V, Vh, v_dev, vh_dev, C / 4, reinterpret_cast<float4*>(out));
+        LTN_CHECK_LAUNCH();
+        return 0;
+    }
     k_gru_pointwise<<<grid_for((long long)V * C, kThreads), kThreads, 0, (cudaStream_t)stream>>>(gi, gh, h, b_hh, V, Vh, v_dev,
                                                                                                   vh_dev, C, out);
     LTN_CHECK_LAUNCH();

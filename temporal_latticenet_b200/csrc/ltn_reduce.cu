@@ -130,6 +130,101 @@ k_gn_apply(const float* __restrict__ x, int V, const int* __restrict__ v_dev, in
     }
 }
 
+// ---- GroupNorm(+ReLU) backward (torch.nn.GroupNorm over [1,C,V] as the lattice modules use it) -------------------------
+// With xh = (x - mean_g) * rstd_g and gy' = gy * [y > 0] (ReLU fused in the forward):
+//   per channel:  A_c = sum_v gy'[v,c]  (= grad beta),   B_c = sum_v gy'[v,c] * xh[v,c]  (= grad gamma)
+//   per group:    m1_g = sum_{c in g} gamma_c A_c / n,   m2_g = sum_{c in g} gamma_c B_c / n,   n = V * C/G
+//   grad x[v,c] = (gamma_c gy'[v,c] - m1_g - xh[v,c] m2_g) * rstd_g
+// Pass 1 (k_gn_bwd_stats) reduces A, B in double (same shape as k_gn_stats); pass 2 (k_gn_bwd_apply) is one
+// read-modify-write pass.  Replaces ~10 eager torch ops with [V,C] temporaries.
+__device__ __forceinline__ void gn_group_stats(const double* __restrict__ sums, int g, double n, float eps, float& mean, float& rstd) {
+    const double m = sums[2 * g] / n;
+    double var = sums[2 * g + 1] / n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_gn_bwd_stats(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ y, int V, int C, int cpg,
+               const double* __restrict__ sums, float eps, double* chan /*[C,2]*/) {
+    extern __shared__ double sh[];  // [C][2]
+    const int C4 = C >> 2;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const int rpb = blockDim.x / C4;
+    const int col = threadIdx.x % C4, rph = threadIdx.x / C4;
+    const int rows_per_block = (V + gridDim.x - 1) / gridDim.x;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(V, r0 + rows_per_block);
+    if (rph < rpb) {
+        float mean[4], rstd[4];
+        const double n = (double)V * cpg;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gn_group_stats(sums, (col * 4 + q) / cpg, n, eps, mean[q], rstd[q]);
+        double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int r = r0 + rph; r < r1; r += rpb * 8) {
+            float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = r + u * rpb;
+                if (rr < r1) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(x + (size_t)rr * C) + col);
+                    float4 g = __ldg(reinterpret_cast<const float4*>(gy + (size_t)rr * C) + col);
+                    if (y) {
+                        const float4 o = __ldg(reinterpret_cast<const float4*>(y + (size_t)rr * C) + col);
+                        if (!(o.x > 0.f)) g.x = 0.f;
+                        if (!(o.y > 0.f)) g.y = 0.f;
+                        if (!(o.z > 0.f)) g.z = 0.f;
+                        if (!(o.w > 0.f)) g.w = 0.f;
+                    }
+                    f1[0] += g.x; f1[1] += g.y; f1[2] += g.z; f1[3] += g.w;
+                    f2[0] = fmaf(g.x, (a.x - mean[0]) * rstd[0], f2[0]); f2[1] = fmaf(g.y, (a.y - mean[1]) * rstd[1], f2[1]);
+                    f2[2] = fmaf(g.z, (a.z - mean[2]) * rstd[2], f2[2]); f2[3] = fmaf(g.w, (a.w - mean[3]) * rstd[3], f2[3]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s1[q] += (double)f1[q]; s2[q] += (double)f2[q]; }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            atomicAdd(&sh[2 * (col * 4 + q)], s1[q]);
+            atomicAdd(&sh[2 * (col * 4 + q) + 1], s2[q]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(chan + i, sh[i]);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_gn_bwd_apply(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ y, int V, int C, int cpg,
+               const double* __restrict__ sums, const double* __restrict__ chan, const float* __restrict__ gamma, float eps,
+               float* __restrict__ gx) {
+    extern __shared__ float k[];  // per channel: mean, rstd, gamma, m1, m2
+    const double n = (double)V * cpg;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float mean, rstd;
+        gn_group_stats(sums, g, n, eps, mean, rstd);
+        double m1 = 0.0, m2 = 0.0;
+        for (int j = g * cpg; j < (g + 1) * cpg; ++j) {
+            const double gj = gamma ? (double)__ldg(gamma + j) : 1.0;
+            m1 += gj * chan[2 * j];
+            m2 += gj * chan[2 * j + 1];
+        }
+        k[c] = mean; k[C + c] = rstd; k[2 * C + c] = gamma ? __ldg(gamma + c) : 1.0f;
+        k[3 * C + c] = (float)(m1 / n); k[4 * C + c] = (float)(m2 / n);
+    }
+    __syncthreads();
+    const long long total = (long long)V * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(t % C);
+        float g = __ldg(gy + t);
+        if (y && !(__ldg(y + t) > 0.f)) g = 0.f;
+        const float xh = (__ldg(x + t) - k[c]) * k[C + c];
+        gx[t] = (k[2 * C + c] * g - k[3 * C + c] - xh * k[4 * C + c]) * k[C + c];
+    }
+}
+
 inline int grid_for(long long work_items, int threads) {
     long long b = (work_items + threads - 1) / threads;
     const long long cap = 148LL * 32;
@@ -246,6 +341,28 @@ int ltn_scores_accumulate(const float* scores, const long long* gt, int N, const
         LTN_CHECK_LAUNCH();
     }
     k_scores_fold<<<1, 64, 0, st>>>(conf, K, unlabeled, inter, uni);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+// GroupNorm(+ReLU) backward.  x, gy [V,C]; y (nullable) = the forward's output when ReLU was fused (its sign is the mask);
+// sums [G,2] = the forward's statistics; chan [C,2] double scratch (zeroed here) returns (grad beta, grad gamma) per
+// channel; gx [V,C].  C % 4 == 0, C/4 <= 256.
+int ltn_gn_bwd(const float* x, const float* gy, const float* y, int V, int C, int G, const double* sums, const float* gamma,
+               float eps, double* chan, float* gx, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (G <= 0 || C % G || C % 4 || C / 4 > kThreads) return -2;
+    cudaError_t e = cudaMemsetAsync(chan, 0, sizeof(double) * 2 * (size_t)C, st);
+    if (e != cudaSuccess) return (int)e;
+    if (V <= 0) return 0;
+    int rpb = kThreads / (C / 4);
+    int blocks = (V + rpb * 8 - 1) / (rpb * 8);
+    if (blocks > 148) blocks = 148;
+    if (blocks < 1) blocks = 1;
+    k_gn_bwd_stats<<<blocks, kThreads, sizeof(double) * 2 * C, st>>>(x, gy, y, V, C, C / G, sums, eps, chan);
+    LTN_CHECK_LAUNCH();
+    k_gn_bwd_apply<<<grid_for((long long)V * C, kThreads), kThreads, sizeof(float) * 5 * C, st>>>(x, gy, y, V, C, C / G, sums, chan, gamma,
+                                                                                                 eps, gx);
     LTN_CHECK_LAUNCH();
     return 0;
 }

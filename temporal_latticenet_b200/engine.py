@@ -13,7 +13,7 @@ reused across windows (Lattice.reset empties them), so the captured addresses st
 
 Safety net: after each window the real vertex counts are compared with the capacities (they ride back
 with the labels); a window that outgrew them is re-run on the eager path, and so is any configuration
-whose fusion modules have no static-capacity implementation.
+whose PointNet widths are not the fused front end's.
 """
 import torch
 
@@ -21,7 +21,7 @@ from . import _lib, ops
 from .lattice import Lattice
 from .runner import WindowRunner
 
-_STATIC_FUSION = ("gru", "lstm", "aflow", "none")
+_STATIC_FUSION = ("gru", "lstm", "aflow", "linear", "maxpool", "cga", "none")
 
 
 def _round_up(x, m):
@@ -710,3 +710,59 @@ class LockstepRunner:
 
     def batched_per_group(self, nr_frames):
         return sum(self.batched.get((t == 0, t == nr_frames - 1), 0) for t in range(nr_frames))
+
+
+class GroupedLockstepRunner:
+    """`groups` lock-step groups of `lanes` windows each, every group with its own graphs and streams, in flight
+    together.  A persistent batched launch ends with a tail (CTAs that got one tile fewer, the last epilogue) and the
+    next layer's launch cannot start before it: with a second group queued behind, that group's CTAs take the SMs the
+    first one releases, so the per-layer fixed costs of one group hide under the other's work.  Same interface as
+    LockstepRunner; a full set is groups x lanes windows."""
+
+    def __init__(self, cfg_path, nr_classes=26, device=None, lanes=4, groups=2, operands="f16", trace=True):
+        self.groups = [LockstepRunner(cfg_path, nr_classes, device, lanes=lanes, operands=operands, trace=trace) for _ in range(groups)]
+        self.device = self.groups[0].device
+        self.per_group = lanes
+        self.lanes = [l for g in self.groups for l in g.lanes]
+        self.supported = all(g.supported for g in self.groups)
+
+    def prepare(self, frames_dev, state_dict_fn, plan_windows=None):
+        for g in self.groups:
+            g.prepare(frames_dev, state_dict_fn, plan_windows)
+        self.supported = all(g.supported for g in self.groups)
+        return self
+
+    def _split(self, windows):
+        k = self.per_group
+        return [windows[i:i + k] for i in range(0, len(windows), k)]
+
+    def infer_windows_device(self, windows_dev):
+        outs = []
+        for g, part in zip(self.groups, self._split(windows_dev)):
+            outs += g.infer_windows_device(part)     # queued asynchronously: the groups overlap on the device
+        return outs
+
+    def submit(self, windows_host):
+        return [g.submit(part) for g, part in zip(self.groups, self._split(windows_host))]
+
+    def collect(self, tickets):
+        out = []
+        for g, t in zip(self.groups, tickets):
+            out += g.collect(t)
+        return out
+
+    def infer_windows(self, windows_host):
+        return self.collect(self.submit(windows_host))
+
+    def counts_ok(self):
+        return all(g.counts_ok() for g in self.groups)
+
+    def kernels_per_group(self, nr_frames):
+        return sum(g.kernels_per_group(nr_frames) for g in self.groups)
+
+    def trace_group(self, windows_dev):
+        """records of ONE group's launches with the other groups running beside it (the timed configuration)"""
+        parts = self._split(windows_dev)
+        for g, part in zip(self.groups[1:], parts[1:]):
+            g.infer_windows_device(part)
+        return self.groups[0].trace_group(parts[0])

@@ -41,10 +41,27 @@ def row2im_raw(grad_rows, nbr_t, nr_vals, C):
     return out
 
 
+_FLIP = (1, 0, 3, 2, 5, 4, 7, 6, 8)   # slot pairs swap under transposition (2a <-> 2a+1), the centre stays
+
+
+def transposed_weight(weight, C, F):
+    """[9C, F] slot-major conv weight -> the weight of the TRANSPOSED convolution, [9F, C]:
+    Wt[s'*F + f, c] = W[flip(s')*C + c, f]; cached per parameter version (ops.k_major on the result)."""
+    def make():
+        wt = weight.detach().view(FEXT, C, F)[list(_FLIP)].transpose(1, 2).contiguous().view(FEXT * F, C)
+        return ops.SplitWeight(wt.float(), False)
+    return ops._cached_split(weight, (id(weight), "transposed"), make)
+
+
 class _GatherConv(Function):
     """out = im2row(values, nbr) @ weight.  nbr_t is the opposite-direction table used to run the
     transpose as a gather (see csrc/ltn_gather.cu::k_row2im).  The [V,9C] buffer is not kept for
-    backward; it is rebuilt (bandwidth is cheaper than holding 200 MB per conv alive)."""
+    backward; it is rebuilt (bandwidth is cheaper than holding 200 MB per conv alive).
+
+    Backward wrt the values (`ltn_conv_bwd_data` of SURVEY.md 8b) is the FORWARD tensor-core kernel run over the
+    transposed neighbour table with the transposed weight: grad_x[u, c] = sum_s' sum_f grad_out[nbr_t[u, s'], f] *
+    W[flip(s')*C + c, f] -- no [V, 9C] gradient buffer, no row2im pass.  Shapes the tensor-core kernel does not take
+    (F % 32 != 0) keep the materialised path."""
 
     @staticmethod
     def forward(ctx, values, weight, nbr, nbr_t):
@@ -58,9 +75,16 @@ class _GatherConv(Function):
         values, weight, nbr, nbr_t = ctx.saved_tensors
         grad_out = _f32c(grad_out)
         gv = gw = None
+        C, F = values.shape[1], weight.shape[1]
         if ctx.needs_input_grad[0]:
-            grad_rows = ops.matmul(grad_out, weight.t())
-            gv = row2im_raw(grad_rows, nbr_t, values.shape[0], values.shape[1])
+            if ops.conv_tc_supported(F, C, False) and grad_out.shape[0] > 0 and values.shape[0] > 0:
+                vu = min(values.shape[0], nbr_t.shape[0])
+                gv = torch.zeros(values.shape[0], C, dtype=torch.float32, device=grad_out.device) if vu < values.shape[0] else \
+                    torch.empty(values.shape[0], C, dtype=torch.float32, device=grad_out.device)
+                ops.conv_tc(grad_out, nbr_t, transposed_weight(weight, C, F), nr_rows=vu, out=gv, operands="tf32")
+            else:
+                grad_rows = ops.matmul(grad_out, weight.t())
+                gv = row2im_raw(grad_rows, nbr_t, values.shape[0], values.shape[1])
         if ctx.needs_input_grad[1]:
             rows = im2row_raw(values, nbr)
             gw = ops.matmul(rows.t(), grad_out)

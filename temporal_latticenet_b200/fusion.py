@@ -58,6 +58,12 @@ class _HiddenState:
             return _lib.ptr(self._h_rows)
         return None
 
+    def _has_history(self, nr_rows):
+        """static-capacity mode: bool [capacity, 1], true for the rows the hidden state really covers (the rows of the frame
+        that wrote it); the buffer beyond them is stale and stands for the reference's padding"""
+        rows = torch.arange(nr_rows, dtype=torch.int32, device=self._h_rows.device)
+        return (rows < self._h_rows).unsqueeze(1)
+
 
 class GRUModule(torch.nn.Module, _HiddenState):
     """lattice_modules.py:42-66"""
@@ -132,7 +138,7 @@ class LSTMModule(torch.nn.Module, _HiddenState):
         return new_lv, ls
 
 
-class CrossframeGlobalAttentionModule(torch.nn.Module):
+class CrossframeGlobalAttentionModule(torch.nn.Module, _HiddenState):
     """lattice_modules.py:70-116 (quirk Q6: the same 1x1 conv twice, "pooling" = 1/(rows+cols))"""
 
     def __init__(self, nr_output_channels):
@@ -147,23 +153,34 @@ class CrossframeGlobalAttentionModule(torch.nn.Module):
 
     def forward(self, lv, ls):
         if self.h_lv is None:
-            self.h_lv = lv
+            self._store(lv)
             return lv, ls
-        h = ops.linear(self.h_lv, self.hidden_linear.weight, self.hidden_linear.bias)
+        static = _lib.static_mode()
+        h = ops.linear(self.h_lv, self.hidden_linear.weight, self.hidden_linear.bias, rows_dev=self._rows_dev())
         Vh, V = h.shape[0], lv.shape[0]
-        a = torch.relu(self.conv(_pad_rows(h, V)))
+        if static:   # same row capacity; the live counts are on the device
+            known = self._has_history(V)
+            hp = torch.where(known, h, torch.zeros_like(h))
+            nr_rows = _lib.rows_tensor(V).to(torch.float32)
+        else:
+            hp = _pad_rows(h, V)
+        a = torch.relu(self.conv(hp))
         a, _ = self.groupnorm(a, ls)
         a = self.conv(a)
-        a = torch.sigmoid(a * (1.0 / (a.shape[0] + a.shape[1])))
-        if Vh < V:
-            a = torch.cat([a[:Vh], torch.ones(V - Vh, a.shape[1], dtype=a.dtype, device=a.device)], 0)
+        if static:
+            a = torch.sigmoid(a * (1.0 / (nr_rows + float(a.shape[1]))))
+            a = torch.where(known, a, torch.ones_like(a))
+        else:
+            a = torch.sigmoid(a * (1.0 / (a.shape[0] + a.shape[1])))
+            if Vh < V:
+                a = torch.cat([a[:Vh], torch.ones(V - Vh, a.shape[1], dtype=a.dtype, device=a.device)], 0)
         lv = a * lv
-        self.h_lv = lv
+        self._store(lv)
         ls.set_values(lv)
         return lv, ls
 
 
-class TemporalMaxPoolModule(torch.nn.Module):
+class TemporalMaxPoolModule(torch.nn.Module, _HiddenState):
     """lattice_modules.py:119-145"""
 
     def __init__(self):
@@ -175,7 +192,11 @@ class TemporalMaxPoolModule(torch.nn.Module):
 
     def forward(self, lv, ls):
         if self.h_lv is None:
-            self.h_lv = lv
+            self._store(lv)
+        elif _lib.static_mode():
+            hp = torch.where(self._has_history(lv.shape[0]), self.h_lv, torch.full_like(self.h_lv, -9999.0))
+            lv = torch.maximum(hp, lv)
+            self._store(lv)
         else:
             n = max(self.h_lv.shape[0], lv.shape[0])
             hp = _pad_rows(self.h_lv, n, -9999.0)
@@ -185,7 +206,7 @@ class TemporalMaxPoolModule(torch.nn.Module):
         return lv, ls
 
 
-class TemporalLinearModule(torch.nn.Module):
+class TemporalLinearModule(torch.nn.Module, _HiddenState):
     """lattice_modules.py:149-185"""
 
     def __init__(self, nr_output_channels):
@@ -202,12 +223,16 @@ class TemporalLinearModule(torch.nn.Module):
         if self.h_lv is None:
             if lv.shape[1] != self.nr_output_channels:
                 raise RuntimeError("lv has %d channels, the module was built for %d" % (lv.shape[1], self.nr_output_channels))
-            self.h_lv = lv
+            self._store(lv)
         else:
-            h = ops.linear(self.h_lv, self.hidden_linear.weight, self.hidden_linear.bias)
-            hp = _pad_rows(h, lv.shape[0])
-            lv = 0.0 * hp + torch.relu(ops.linear(torch.cat([hp, lv], 1), self.linear.weight, self.linear.bias))
-            self.h_lv = lv
+            h = ops.linear(self.h_lv, self.hidden_linear.weight, self.hidden_linear.bias, rows_dev=self._rows_dev())
+            if _lib.static_mode():
+                hp = torch.where(self._has_history(lv.shape[0]), h, torch.zeros_like(h))
+                lv = torch.relu(ops.linear(torch.cat([hp, lv], 1), self.linear.weight, self.linear.bias))
+            else:
+                hp = _pad_rows(h, lv.shape[0])
+                lv = 0.0 * hp + torch.relu(ops.linear(torch.cat([hp, lv], 1), self.linear.weight, self.linear.bias))
+            self._store(lv)
         ls.set_values(lv)
         return lv, ls
 

@@ -65,23 +65,14 @@ class _GroupNormRelu(Function):
         x, gamma, sums, y = ctx.saved_tensors
         groups, eps, relu = ctx.cfg
         V, C = x.shape
-        cpg = C // groups
-        n = float(V * cpg)
         gy = gy.contiguous().float()
-        if relu:
-            gy = gy * (y > 0).to(gy.dtype)
-        mean = (sums[:, 0] / n)
-        var = (sums[:, 1] / n - mean * mean).clamp(min=0.0)
-        rstd = (1.0 / torch.sqrt(var + eps)).float()
-        mean = mean.float()
-        xh = ((x.view(V, groups, cpg) - mean.view(1, groups, 1)) * rstd.view(1, groups, 1))
-        g3 = (gy * gamma.view(1, C)).view(V, groups, cpg)
-        m1 = g3.sum(dim=(0, 2), keepdim=True) / n
-        m2 = (g3 * xh).sum(dim=(0, 2), keepdim=True) / n
-        gx = ((g3 - m1 - xh * m2) * rstd.view(1, groups, 1)).reshape(V, C)
-        ggamma = (gy * xh.reshape(V, C)).sum(0)
-        gbeta = gy.sum(0)
-        return gx, ggamma, gbeta, None, None, None
+        chan = torch.empty(C, 2, dtype=torch.float64, device=x.device)
+        gx = torch.empty_like(x)
+        p = _lib.ptr
+        _lib.check(_lib.load().ltn_gn_bwd(p(x), p(gy), p(y) if relu else None, V, C, groups, p(sums), p(gamma), float(eps), p(chan), p(gx),
+                                          _lib.stream()), "ltn_gn_bwd")
+        chan = chan.float()
+        return gx, chan[:, 1].contiguous(), chan[:, 0].contiguous(), None, None, None
 
 
 def group_norm(x, gamma, beta, groups, eps=1e-5, relu=False):

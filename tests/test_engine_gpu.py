@@ -101,7 +101,8 @@ def test_multi_window_runner_matches_eager_runner():
         assert (l.numpy() == w.argmax(1)).mean() > 0.999
 
 
-@pytest.mark.parametrize("rnn", [["aflow", "aflow", "aflow", "aflow"], ["lstm", "none", "none", "gru"], ["gru", "gru", "aflow", "gru"]])
+@pytest.mark.parametrize("rnn", [["aflow", "aflow", "aflow", "aflow"], ["lstm", "none", "none", "gru"], ["gru", "gru", "aflow", "gru"],
+                                 ["maxpool", "cga", "linear", "gru"], ["linear", "maxpool", "cga", "lstm"], ["cga", "linear", "maxpool", "maxpool"]])
 def test_graph_runner_other_fusion_configs(rnn, tmp_path):
     """static-capacity graphs for every fusion kind that has a device-side-size implementation (BASELINE config 5
     uses aflow x4); 3-frame windows exercise first / middle / last graphs"""
@@ -136,7 +137,8 @@ def test_graph_runner_other_fusion_configs(rnn, tmp_path):
             assert err < 1e-4, err
 
 
-def test_unsupported_fusion_falls_back_to_eager(tmp_path):
+def test_every_fusion_kind_has_a_static_capacity_path(tmp_path):
+    """linear / maxpool / cga (lattice_modules.py:70-185) run inside the captured graphs too (round 1 sent them to the eager runner)"""
     import hjson
     import os
     from temporal_latticenet_b200.engine import GraphWindowRunner
@@ -144,17 +146,17 @@ def test_unsupported_fusion_falls_back_to_eager(tmp_path):
     with open(CFG) as f:
         cfg = hjson.loads(f.read())
     cfg["model"]["rnn_modules"] = ["maxpool", "cga", "linear", "gru"]
-    path = os.path.join(str(tmp_path), "cfg_unsupported.cfg")
+    path = os.path.join(str(tmp_path), "cfg_all_kinds.cfg")
     with open(path, "w") as f:
         f.write(hjson.dumps(cfg))
     dev = torch.device("cuda:0")
     w = _window(13, frames=3, n=3000)
     fd = [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]
     g = GraphWindowRunner(path, 26, dev).materialise_parameters(fd, seeded_state)
-    assert not g.supported
+    assert g.supported
     g.capture(fd)
     out = g.infer_window_device(fd)
-    assert out.shape == (w[-1][0].shape[0], 26) and len(g.graphs) == 0
+    assert out.shape == (w[-1][0].shape[0], 26) and len(g.graphs) == 3 and g.counts_ok()
 
 
 def test_more_points_than_planned_runs_eagerly():

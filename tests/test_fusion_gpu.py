@@ -257,3 +257,29 @@ def test_scores_iou_matches_oracle():
         o.accumulate_scores(logits, gt, 0)
     assert s.intersection_per_class == o.inter and s.union_per_class == o.union
     assert s.compute_stats() == o.compute_stats()
+
+
+@pytest.mark.parametrize("C,relu", [(64, True), (192, True), (36, True), (128, False), (8, False)])
+def test_group_norm_backward_kernel_matches_torch_autograd(C, relu):
+    """ltn_gn_bwd (two kernels) against torch.nn.functional.group_norm (+ReLU) under autograd in float64; also the conv
+    backward-data path through the tensor-core kernel over the transposed table is covered by test_golden_gpu's gradient test"""
+    from temporal_latticenet_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(C)
+    V = 3001
+    x = torch.randn(V, C, generator=g).to(dev)
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).to(dev), torch.randn(C, generator=g).to(dev)
+    gy = torch.randn(V, C, generator=g).to(dev)
+    G = ops.gn_groups(C)
+    xa, ga, ba = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = ops.group_norm(xa, ga, ba, G, 1e-5, relu)
+    y.backward(gy)
+    xd, gd, bd = x.double().clone().requires_grad_(True), gamma.double().clone().requires_grad_(True), beta.double().clone().requires_grad_(True)
+    yd = torch.nn.functional.group_norm(xd.t().unsqueeze(0), G, gd, bd, 1e-5).squeeze(0).t()
+    if relu:
+        yd = torch.relu(yd)
+    yd.backward(gy.double())
+    assert float((y.double() - yd).abs().max()) < 1e-4
+    for got, want in ((xa.grad, xd.grad), (ga.grad, gd.grad), (ba.grad, bd.grad)):
+        scale = float(want.abs().max()) + 1e-12
+        assert float((got.double() - want).abs().max()) / scale < 1e-4
