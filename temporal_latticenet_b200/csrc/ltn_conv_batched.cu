@@ -28,11 +28,18 @@ constexpr int kBlockM = 128;
 constexpr int kKB = 64;               // fp16 K elements per k-block = one 128-byte swizzle row
 constexpr int kGroups = 2;            // producer warpgroups, alternate k-blocks
 constexpr int kMaxBatch = 8;
-constexpr int kThreadsB = 512;        // 4 warpgroups
-constexpr int kWarpEpi0 = 8, kWarpMma = 12, kWarpTma = 13, kWarpMeta0 = 14;
+#ifndef LTN_CONVB_EPI_WARPS
+#define LTN_CONVB_EPI_WARPS 8       // epilogue warps: 4 (one warpgroup) or 8 (two: alternate 32-column chunks)
+#endif
+constexpr int kEpiWarps = LTN_CONVB_EPI_WARPS;
+constexpr int kWarpEpi0 = 8, kWarpMma = kWarpEpi0 + kEpiWarps, kWarpTma = kWarpMma + 1, kWarpMeta0 = kWarpMma + 2;
+constexpr int kThreadsB = 32 * (kWarpMma + 4);   // producers (2 warpgroups) + epilogue (1 or 2) + auxiliary warpgroup
 constexpr int kMetaThreads = 64;
+constexpr int kMetaBufs = 3;          // neighbour-slice buffers: the gather's issue cursor runs up to two tiles ahead of its consume cursor
+constexpr int kNbrPerMeta = (LTN_FEXT * kBlockM + kMetaThreads - 1) / kMetaThreads;
 constexpr int kMaxSA = 4, kMaxSB = 4;
-constexpr int kRegsProducer = 168, kRegsEpilogue = 96, kRegsAux = 56;
+// register budgets after setmaxnreg (the block starts at 65536 / threads per thread, rounded down to a multiple of 8)
+constexpr int kRegsProducer = kEpiWarps == 8 ? 144 : 168, kRegsEpilogue = kEpiWarps == 8 ? 80 : 96, kRegsAux = kEpiWarps == 8 ? 64 : 56;
 
 struct BatchParams {
     const float* x[kMaxBatch];        // [Vx_b, C]
@@ -71,13 +78,13 @@ __global__ void __launch_bounds__(kThreadsB, 1)
 k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                   const __grid_constant__ BatchParams p) {
     extern __shared__ uint8_t smem_raw[];
-    // barriers: a_full[4] a_empty[4] b_full[4] b_empty[4] acc_full[2] acc_empty[2] meta_full[2] meta_empty[2]
-    __shared__ __align__(8) uint64_t bars[2 * kMaxSA + 2 * kMaxSB + 8];
+    // barriers: a_full[4] a_empty[4] b_full[4] b_empty[4] acc_full[2] acc_empty[2] meta_full[3] meta_empty[3]
+    __shared__ __align__(8) uint64_t bars[2 * kMaxSA + 2 * kMaxSB + 4 + 2 * kMetaBufs];
     __shared__ uint32_t tmem_slot;
     __shared__ int s_prefix[kMaxBatch + 1];   // row tiles before problem b
     __shared__ int s_vq[kMaxBatch], s_vx[kMaxBatch];
-    __shared__ __align__(16) float s_affine[2][512];          // per meta buffer: scale [256] | shift [256]
-    __shared__ int s_nbr[2][LTN_FEXT * kBlockM];              // per meta buffer: [slot][tile row], -1 = absent
+    __shared__ __align__(16) float s_affine[kMaxBatch][512];  // per PROBLEM: folded GroupNorm scale [256] | shift [256], computed once per CTA
+    __shared__ int s_nbr[kMetaBufs][LTN_FEXT * kBlockM];      // per meta buffer: [slot][tile row], -1 = absent
     __shared__ float s_colsum[2][512];                        // per tile parity: column sums [256] | sums of squares [256]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -87,6 +94,23 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     }
     for (int i = tid; i < 2 * 512; i += kThreadsB) (&s_colsum[0][0])[i] = 0.f;
     __syncthreads();
+    if (p.has_gn) {
+        // GroupNorm folded to scale = rstd*gamma, shift = beta - mean*scale (statistics over all Vx rows), x the fp16 pre-scale
+        for (int i = tid; i < p.nb * p.C; i += kThreadsB) {
+            const int b = i / p.C, c = i - b * p.C;
+            const int g = c / p.gn_cpg;
+            const double* sums = p.gn_sums[b];
+            const double n = (double)s_vx[b] * p.gn_cpg;
+            const double mean = sums[2 * g] / n;
+            double var = sums[2 * g + 1] / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)p.gn_eps));
+            const float sc = rstd * (p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.0f);
+            const float sh = (p.gn_beta ? __ldg(p.gn_beta + c) : 0.0f) - (float)mean * sc;
+            s_affine[b][c] = sc * p.a_mul;
+            s_affine[b][256 + c] = sh * p.a_mul;
+        }
+    }
     if (tid == 0) {
         int acc = 0;
         for (int b = 0; b < p.nb; ++b) {
@@ -105,12 +129,12 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     const int SA = p.stages_a, SB = p.stages_b;
     const uint32_t b_bytes = (uint32_t)p.n_tile * 128u, b_stage = 2u * b_bytes;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* smem_epi = smem + (size_t)SB * b_stage;   // 4 x 4 KB: one transpose block per epilogue warp
+    uint8_t* smem_epi = smem + (size_t)SB * b_stage;   // kEpiWarps x 4 KB: one transpose block per epilogue warp
 
     const uint32_t bar_afull = smem_u32(&bars[0]), bar_aempty = smem_u32(&bars[kMaxSA]);
     const uint32_t bar_bfull = smem_u32(&bars[2 * kMaxSA]), bar_bempty = smem_u32(&bars[2 * kMaxSA + kMaxSB]);
     const uint32_t bar_accfull = smem_u32(&bars[2 * kMaxSA + 2 * kMaxSB]), bar_accempty = bar_accfull + 16;
-    const uint32_t bar_metafull = bar_accfull + 32, bar_metaempty = bar_accfull + 48;
+    const uint32_t bar_metafull = bar_accfull + 32, bar_metaempty = bar_metafull + 8 * kMetaBufs;
     const uint32_t a_col0 = (uint32_t)(p.acc_bufs * p.acc_stride);   // A ring behind the accumulators, 64 columns per stage
     constexpr uint32_t kTmemCols = 512;
 
@@ -138,8 +162,10 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             mbar_init(bar_bempty + 8 * s, 1);     // tcgen05.commit
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar_accfull + 8 * s, 1);    // tcgen05.commit
-            mbar_init(bar_accempty + 8 * s, 4);   // the four epilogue warps
+            mbar_init(bar_accfull + 8 * s, 1);            // tcgen05.commit
+            mbar_init(bar_accempty + 8 * s, kEpiWarps);   // the epilogue warps
+        }
+        for (int s = 0; s < kMetaBufs; ++s) {
             mbar_init(bar_metafull + 8 * s, 2);   // the two tile-prologue warps
             mbar_init(bar_metaempty + 8 * s, 8);  // the eight gather warps
         }
@@ -164,114 +190,163 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         const int ra = lane >> 2, cq = lane & 3;
         const uint32_t c4 = (uint32_t)C >> 2;
         const float a_mul = p.a_mul;
+        const bool affine = p.has_gn != 0;
+        // The gather is ONE software pipeline over all tiles of this CTA: the loads of the next unit (16 tile rows x 64
+        // channels) are in flight while the current one is converted and written to tensor memory -- also across a tile
+        // boundary, so the L2 latency of a tile's first rows hides under the previous tile's last k-block.  Two cursors walk
+        // the k-blocks this group owns (those of its parity in the GLOBAL k-block sequence): `i_*` where loads are issued,
+        // `c_*` (one k-block behind) where they are consumed.
         int c_stage = group % SA;
         uint32_t c_par = 1u;
-        uint32_t kb_base = 0;
-        for (int it = 0;; ++it) {
-            Tile t;
-            if (!tile_at(it, t)) break;
-            const int q = it & 1;
-            if (lane == 0) mbar_wait(bar_metafull + 8 * q, (uint32_t)(it >> 1) & 1u);
-            __syncwarp();
-            const int* nbr_s = s_nbr[q];
-            const float* aff = s_affine[q];
-            const float4* x4 = reinterpret_cast<const float4*>(p.x[t.b]);
-            const bool affine = p.has_gn != 0;
-            const int first = (group + (int)(kb_base & 1u)) & 1;   // this group owns the k-blocks of its parity in the GLOBAL sequence
-            float4 buf[2][8];
-            uint32_t bmask[2];
-            uint32_t rowidx[4];
-            uint32_t rmask = 0;
-            float amax = 0.f;
-            int i_slot = first / kb_per_slot, i_c0 = (first - i_slot * kb_per_slot) * kKB, i_cur = -1;
-            int c_c0 = i_c0;
-            auto issue = [&](float4* dst, uint32_t& dmask, const int half) {
-                if (i_slot != i_cur) {
-                    i_cur = i_slot;
-                    const int* tap = nbr_s + i_slot * kBlockM + wrow0 + ra;
-                    rmask = 0;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int sv = tap[8 * r];
-                        rowidx[r] = (uint32_t)(sv >= 0 ? sv : 0) * c4 + (uint32_t)cq;   // row 0 stands in for an absent neighbour
-                        rmask |= (sv >= 0 ? 1u : 0u) << r;
-                    }
+        // issue cursor
+        int i_it = -1, i_left = 0, i_slot = 0, i_c0 = 0, i_cur = -1;
+        uint32_t i_base = 0;
+        bool i_valid = false;
+        const float4* i_x4 = nullptr;
+        const int* i_nbr = nullptr;
+        uint32_t rowidx[4];
+        uint32_t rmask = 0;
+        // consume cursor
+        int c_it = -1, c_left = 0, c_c0 = 0;
+        uint32_t c_base = 0;
+        bool c_valid = false;
+        const float* c_aff = s_affine[0];
+        int* c_flag = nullptr;
+        float amax = 0.f;
+        auto issue_next_tile = [&]() {
+            for (;;) {
+                if (i_it >= 0) i_base += (uint32_t)num_kb;
+                ++i_it;
+                Tile t;
+                if (!tile_at(i_it, t)) { i_valid = false; return; }
+                const int q = i_it % kMetaBufs;
+                if (lane == 0) mbar_wait(bar_metafull + 8 * q, (uint32_t)(i_it / kMetaBufs) & 1u);   // every tile, owned or not
+                __syncwarp();
+                const int first = (group + (int)(i_base & 1u)) & 1;
+                if (first >= num_kb) continue;
+                i_left = (num_kb - first + 1) >> 1;
+                i_x4 = reinterpret_cast<const float4*>(p.x[t.b]);
+                i_nbr = s_nbr[q];
+                i_slot = first / kb_per_slot;
+                i_c0 = (first - i_slot * kb_per_slot) * kKB;
+                i_cur = -1;
+                i_valid = true;
+                return;
+            }
+        };
+        auto consume_next_tile = [&]() {
+            for (;;) {
+                if (c_it >= 0) {   // leaving tile c_it: its neighbour slice is no longer read by this warp (the issue cursor is ahead)
+                    if (c_flag && !(amax < 65504.f)) atomicOr(c_flag, 1);
+                    amax = 0.f;
+                    c_flag = nullptr;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_metaempty + 8 * (c_it % kMetaBufs));
+                    c_base += (uint32_t)num_kb;
                 }
-                const uint32_t o = (uint32_t)i_c0 >> 2;
-                dmask = half ? (rmask >> 2) : rmask;
+                ++c_it;
+                Tile t;
+                if (!tile_at(c_it, t)) { c_valid = false; return; }
+                const int first = (group + (int)(c_base & 1u)) & 1;
+                if (first >= num_kb) continue;
+                c_left = (num_kb - first + 1) >> 1;
+                c_aff = s_affine[t.b];
+                c_flag = p.flag[t.b];
+                const int sl = first / kb_per_slot;
+                c_c0 = (first - sl * kb_per_slot) * kKB;
+                c_valid = true;
+                return;
+            }
+        };
+        float4 buf[2][8];
+        uint32_t bmask[2];
+        auto issue = [&](float4* dst, uint32_t& dmask, const int half) {
+            if (i_slot != i_cur) {
+                i_cur = i_slot;
+                const int* tap = i_nbr + i_slot * kBlockM + wrow0 + ra;
+                rmask = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int sv = tap[8 * r];
+                    rowidx[r] = (uint32_t)(sv >= 0 ? sv : 0) * c4 + (uint32_t)cq;   // row 0 stands in for an absent neighbour
+                    rmask |= (sv >= 0 ? 1u : 0u) << r;
+                }
+            }
+            const uint32_t o = (uint32_t)i_c0 >> 2;
+            dmask = half ? (rmask >> 2) : rmask;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t ri = (half ? rowidx[2 + h] : rowidx[h]) + o;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) dst[4 * h + g] = __ldg(i_x4 + ri + 4 * g);
+            }
+            if (!half) return;
+            if (--i_left == 0) { issue_next_tile(); return; }
+            i_c0 += kGroups * kKB;
+            while (i_c0 >= C) { i_c0 -= C; ++i_slot; }
+        };
+        auto consume = [&](const float4* cur, uint32_t cmask, const int half) {
+            if (half == 0) {
+                if (lane == 0) mbar_wait(bar_aempty + 8 * c_stage, c_par);
+                __syncwarp();
+                tc_fence_after();
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float4 sc = make_float4(a_mul, a_mul, a_mul, a_mul), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (affine) {
+                    sc = *reinterpret_cast<const float4*>(c_aff + c_c0 + 16 * g + 4 * cq);
+                    sh = *reinterpret_cast<const float4*>(c_aff + 256 + c_c0 + 16 * g + 4 * cq);
+                }
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const uint32_t ri = (half ? rowidx[2 + h] : rowidx[h]) + o;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) dst[4 * h + g] = __ldg(x4 + ri + 4 * g);
+                    float4 v = cur[4 * h + g];
+                    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                    v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    if (p.relu) { v.x = relu_nan(v.x); v.y = relu_nan(v.y); v.z = relu_nan(v.z); v.w = relu_nan(v.w); }
+                    if (!((cmask >> h) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);   // absent neighbour / row beyond the tile
+                    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+                    hi[4 * g + 2 * h] = *reinterpret_cast<const uint32_t*>(&h01);
+                    hi[4 * g + 2 * h + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                    lo[4 * g + 2 * h] = *reinterpret_cast<const uint32_t*>(&l01);
+                    lo[4 * g + 2 * h + 1] = *reinterpret_cast<const uint32_t*>(&l23);
                 }
-                if (!half) return;
-                i_c0 += kGroups * kKB;
-                while (i_c0 >= C) { i_c0 -= C; ++i_slot; }
-            };
-            auto consume = [&](const float4* cur, uint32_t cmask, const int half) {
-                if (half == 0) {
-                    if (lane == 0) mbar_wait(bar_aempty + 8 * c_stage, c_par);
-                    __syncwarp();
-                    tc_fence_after();
-                }
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float4 sc = make_float4(a_mul, a_mul, a_mul, a_mul), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (affine) {
-                        sc = *reinterpret_cast<const float4*>(aff + c_c0 + 16 * g + 4 * cq);
-                        sh = *reinterpret_cast<const float4*>(aff + 256 + c_c0 + 16 * g + 4 * cq);
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float4 v = cur[4 * h + g];
-                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                        if (p.relu) { v.x = relu_nan(v.x); v.y = relu_nan(v.y); v.z = relu_nan(v.z); v.w = relu_nan(v.w); }
-                        if (!((cmask >> h) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);   // absent neighbour / row beyond the tile
-                        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-                        const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                        const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
-                        hi[4 * g + 2 * h] = *reinterpret_cast<const uint32_t*>(&h01);
-                        hi[4 * g + 2 * h + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-                        lo[4 * g + 2 * h] = *reinterpret_cast<const uint32_t*>(&l01);
-                        lo[4 * g + 2 * h + 1] = *reinterpret_cast<const uint32_t*>(&l23);
-                    }
-                }
-                const uint32_t ta = tmem_base + ((uint32_t)(wrow0 + 16 * half) << 16) + a_col0 + (uint32_t)c_stage * 64u;
-                tmem_st_16x256b_x4(ta, hi);
-                tmem_st_16x256b_x4(ta + 32u, lo);
-                if (half == 0) return;
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_afull + 8 * c_stage);
-                c_c0 += kGroups * kKB;
-                while (c_c0 >= C) c_c0 -= C;
-                c_stage += kGroups;
-                while (c_stage >= SA) { c_stage -= SA; c_par ^= 1u; }
-            };
-            if (first < num_kb) issue(buf[0], bmask[0], 0);
-            for (int kb = first; kb < num_kb; kb += kGroups) {
-                issue(buf[1], bmask[1], 1);
-                consume(buf[0], bmask[0], 0);
-                if (kb + kGroups < num_kb) issue(buf[0], bmask[0], 0);
-                consume(buf[1], bmask[1], 1);
             }
-            if (p.flag[t.b] && !(amax < 65504.f)) atomicOr(p.flag[t.b], 1);
+            const uint32_t ta = tmem_base + ((uint32_t)(wrow0 + 16 * half) << 16) + a_col0 + (uint32_t)c_stage * 64u;
+            tmem_st_16x256b_x4(ta, hi);
+            tmem_st_16x256b_x4(ta + 32u, lo);
+            if (half == 0) return;
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_metaempty + 8 * q);   // this warp no longer reads the tile's neighbour slice / affine
-            kb_base += (uint32_t)num_kb;
+            if (lane == 0) mbar_arrive(bar_afull + 8 * c_stage);
+            c_stage += kGroups;
+            while (c_stage >= SA) { c_stage -= SA; c_par ^= 1u; }
+            if (--c_left == 0) { consume_next_tile(); return; }
+            c_c0 += kGroups * kKB;
+            while (c_c0 >= C) c_c0 -= C;
+        };
+        issue_next_tile();
+        consume_next_tile();
+        if (i_valid) issue(buf[0], bmask[0], 0);
+        while (c_valid) {
+            issue(buf[1], bmask[1], 1);     // second half of the k-block the issue cursor is on; moves the cursor on (maybe to the next tile)
+            consume(buf[0], bmask[0], 0);
+            if (i_valid) issue(buf[0], bmask[0], 0);
+            consume(buf[1], bmask[1], 1);   // completes the k-block; moves the consume cursor on
         }
     } else if (warp < kWarpMma) {
         // ===================== epilogue warpgroup: TMEM -> registers -> global ==============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
         const int qd = warp & 3;
-        const int et = tid - kWarpEpi0 * 32;   // 0..127
+        const int eh = (warp - kWarpEpi0) >> 2;   // which share of the 32-column chunks (0 when there is one epilogue warpgroup)
+        const int et = tid - kWarpEpi0 * 32;      // 0 .. 32 * kEpiWarps - 1
         const int chunk = lane & 7, sub = lane >> 3;
-        float* stage = reinterpret_cast<float*>(smem_epi + qd * 4096);
+        float* stage = reinterpret_cast<float*>(smem_epi + (warp - kWarpEpi0) * 4096);
         const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
         const float out_mul = p.out_mul;
         for (int it = 0;; ++it) {
@@ -285,7 +360,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             float* out = p.out[t.b];
             const float* res = p.res[t.b];
             float* colsum = s_colsum[it & 1];
-            for (int cb = 0; cb < t.N; cb += 32) {
+            for (int cb = eh * 32; cb < t.N; cb += 32 * (kEpiWarps / 4)) {
                 float acc[32];
                 tmem_ld32(t_lane + (uint32_t)(a * p.acc_stride + cb), acc);
 #pragma unroll
@@ -338,10 +413,10 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             if (p.has_sums) {
                 // per-tile column sums -> group sums -> one double atomic per group; the buffer of this tile parity is
                 // cleared here and next used two tiles later, after the next tile's barrier
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                 double* osums = p.out_sums[t.b];
                 const int g0 = t.n0 / p.out_cpg, g1 = (t.n0 + t.N) / p.out_cpg;   // n_tile is a multiple of out_cpg
-                for (int g = g0 + et; g < g1; g += 128) {
+                for (int g = g0 + et; g < g1; g += 32 * kEpiWarps) {
                     float sa = 0.f, sb = 0.f;
                     for (int c = g * p.out_cpg - t.n0; c < (g + 1) * p.out_cpg - t.n0; ++c) {
                         sa += colsum[c]; sb += colsum[256 + c];
@@ -413,38 +488,32 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             }
             __syncwarp();
         } else {
-            // ===================== tile prologue: neighbour slice + folded GroupNorm of the NEXT tiles ========
+            // ===================== tile prologue: the neighbour slices of the NEXT tiles ======================
             const int mt = tid - kWarpMeta0 * 32;   // 0..63
             for (int it = 0;; ++it) {
                 Tile t;
                 if (!tile_at(it, t)) break;
-                const int q = it & 1;
-                if (lane == 0) mbar_wait(bar_metaempty + 8 * q, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                const int q = it % kMetaBufs;
+                if (lane == 0) mbar_wait(bar_metaempty + 8 * q, ((uint32_t)(it / kMetaBufs) & 1u) ^ 1u);
                 __syncwarp();
                 const int Vq = s_vq[t.b], Vx = s_vx[t.b];
                 const int* nbr = p.nbr[t.b];
                 int* dst = s_nbr[q];
-                for (int i = mt; i < kBlockM * S; i += kMetaThreads) {
-                    const int r = i / S, sl = i - r * S;
+                int pref[kNbrPerMeta];   // all loads of the slice in flight together
+#pragma unroll
+                for (int u = 0; u < kNbrPerMeta; ++u) {
+                    const int i = mt + u * kMetaThreads;
+                    const int r = i / S;
                     int sv = -1;
-                    if (t.row0 + r < Vq) sv = nbr ? __ldg(nbr + (size_t)t.row0 * S + i) : t.row0 + r;
-                    if (sv >= Vx) sv = -1;
-                    dst[sl * kBlockM + r] = sv;
+                    if (i < kBlockM * S && t.row0 + r < Vq) sv = nbr ? __ldg(nbr + (size_t)t.row0 * S + i) : t.row0 + r;
+                    pref[u] = sv;
                 }
-                if (p.has_gn) {
-                    const double* sums = p.gn_sums[t.b];
-                    float* aff = s_affine[q];
-                    for (int c = mt; c < C; c += kMetaThreads) {
-                        const int g = c / p.gn_cpg;
-                        const double n = (double)Vx * p.gn_cpg;
-                        const double mean = sums[2 * g] / n;
-                        double var = sums[2 * g + 1] / n - mean * mean;
-                        if (var < 0.0) var = 0.0;
-                        const float rstd = (float)(1.0 / sqrt(var + (double)p.gn_eps));
-                        const float sc = rstd * (p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.0f);
-                        const float sh = (p.gn_beta ? __ldg(p.gn_beta + c) : 0.0f) - (float)mean * sc;
-                        aff[c] = sc * p.a_mul;
-                        aff[256 + c] = sh * p.a_mul;
+#pragma unroll
+                for (int u = 0; u < kNbrPerMeta; ++u) {
+                    const int i = mt + u * kMetaThreads;
+                    if (i < kBlockM * S) {
+                        const int r = i / S, sl = i - r * S;
+                        dst[sl * kBlockM + r] = pref[u] >= Vx ? -1 : pref[u];
                     }
                 }
                 __syncwarp();
@@ -556,12 +625,12 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
     p.stages_a = sa;
     const size_t b_stage = 2 * (size_t)n_tile * 128;
     static const int sb_cap = []() { const char* e = getenv("LTN_CONVB_SB"); return e && atoi(e) >= 2 ? atoi(e) : kMaxSB; }();
-    int sb = (int)((190 * 1024) / b_stage);
+    int sb = (int)(((size_t)(226 - 32 - 4 * kEpiWarps - 2) * 1024) / b_stage);   // 227 KB - static (~30 KB) - epilogue staging
     if (sb > kMaxSB) sb = kMaxSB;
     if (sb > sb_cap) sb = sb_cap;
     if (sb < 2) return -3;
     p.stages_b = sb;
-    const size_t smem = (size_t)sb * b_stage + 4 * 4096 + 1024;
+    const size_t smem = (size_t)sb * b_stage + (size_t)kEpiWarps * 4096 + 1024;
     alignas(64) CUtensorMap map_hi, map_lo;
     int rc = make_weight_map(&map_hi, wt_hi, F, p.S * C, n_tile, true);
     if (rc) return rc;
