@@ -42,13 +42,21 @@ class WindowTrainer:
             self.model.load_state_dict(state_dict_fn(shapes))
         broadcast_parameters(self.model)
         self.optimizer = torch.optim.AdamW(self.model.parameters(), lr=self.lr, weight_decay=self.weight_decay, amsgrad=True)
-        self.allreduce = FlatGradAllReduce(self.model.parameters())
+        # the parameters only the last frame uses (slice head, up-path residual blocks -- models.py:435-437,465): their
+        # gradients are final once the last frame's backward has run, so their exchange overlaps the earlier frames' backward
+        early = list(self.model.slice_fast_cuda.parameters()) + list(self.model.resnet_blocks_per_up_lvl_list.parameters())
+        self.allreduce = FlatGradAllReduce(self.model.parameters(), early=early)
         return self
 
     def step(self, frames, target):
         loss = self.forward_window(frames, target)
         self.optimizer.zero_grad(set_to_none=False)
+        self.allreduce.prepare()      # gradients are views of one flat buffer; arms the early bucket
         loss.backward()
         self.allreduce()
         self.optimizer.step()
         return loss.detach()
+
+    @property
+    def allreduce_ms(self):
+        return self.allreduce.elapsed_ms() if self.allreduce is not None else None

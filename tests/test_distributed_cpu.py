@@ -47,6 +47,30 @@ def _worker(rank, world_size, port, out):
             both = [torch.zeros_like(g) for _ in range(world_size)]
             dist.all_gather(both, g)
             assert torch.allclose(p.grad, sum(both) / world_size, atol=1e-6)
+        # the two-bucket form: gradients are views of one flat buffer, the `early` parameters are exchanged from their
+        # post-accumulate hooks DURING backward, the rest afterwards; same result
+        torch.manual_seed(50)
+        m2 = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.GroupNorm(1, 7), torch.nn.Linear(7, 3))
+        ar = parallel.FlatGradAllReduce(m2.parameters(), early=list(m2[2].parameters()))
+        for step in range(2):      # second step: the views are reused, zero_grad(set_to_none=False) keeps them
+            for q in m2.parameters():
+                if q.grad is not None:
+                    q.grad.zero_()
+            torch.manual_seed(11 + rank + 10 * step)
+            x2 = torch.randn(4, 5)
+            m2r = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.GroupNorm(1, 7), torch.nn.Linear(7, 3))
+            m2r.load_state_dict(m2.state_dict())
+            m2r(x2).square().sum().backward()
+            ar.prepare()
+            m2(x2).square().sum().backward()
+            assert ar._early_left == 0 and ar.n_early == sum(q.numel() for q in m2[2].parameters())
+            ar()
+            flat_ptr = ar._flat.data_ptr()
+            assert all(flat_ptr <= q.grad.data_ptr() < flat_ptr + 4 * ar.n for q in m2.parameters())
+            for q, qr in zip(m2.parameters(), m2r.parameters()):
+                both = [torch.zeros_like(qr.grad) for _ in range(world_size)]
+                dist.all_gather(both, qr.grad)
+                assert torch.allclose(q.grad, sum(both) / world_size, atol=1e-6)
         # identical AdamW steps on every rank keep the replicas in lock-step
         opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-3, amsgrad=True)
         opt.step()
