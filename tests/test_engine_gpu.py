@@ -348,3 +348,34 @@ def test_lockstep_runner_matches_eager_runner():
     torch.cuda.synchronize()
     for o, w in zip(outs, want[:2]):
         assert float(np.abs(o.cpu().numpy() - w).max()) / float(np.abs(w).max()) < 1e-4
+
+
+def test_grouped_lockstep_and_launch_trace():
+    """two lock-step groups of two windows in flight together give the eager results; the per-launch trace records of a
+    group cover every batched launch with plausible numbers (rows = live vertex counts, durations > 0)"""
+    from temporal_latticenet_b200.engine import GroupedLockstepRunner
+    from temporal_latticenet_b200.runner import WindowRunner
+    from temporal_latticenet_b200.seeding import seeded_state
+    dev = torch.device("cuda:0")
+    wins = [_window(41), _window(42, n=5200), _window(43, n=4800), _window(44, n=5600)]
+    to_dev = lambda w: [(torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)) for p, v in w]  # noqa: E731
+    devw = [to_dev(w) for w in wins]
+    eager = WindowRunner(CFG, 26, dev).materialise_parameters(devw[0], seeded_state)
+    want = [eager.infer_window_device(w).cpu().numpy() for w in devw]
+    g = GroupedLockstepRunner(CFG, 26, dev, lanes=2, groups=2).prepare(devw[0], seeded_state, devw)
+    assert g.supported and len(g.lanes) == 4
+    for rep in range(2):
+        outs = g.infer_windows_device(devw)
+        torch.cuda.synchronize()
+        assert g.counts_ok()
+        for o, w in zip(outs, want):
+            assert float(np.abs(o.cpu().numpy() - w).max()) / float(np.abs(w).max()) < 1e-4
+    host = [[(torch.from_numpy(p).pin_memory(), torch.from_numpy(v).pin_memory()) for p, v in w] for w in wins]
+    for l, w in zip(g.infer_windows(host), want):
+        assert (l.numpy() == w.argmax(1)).mean() > 0.999
+    rec = g.trace_group(devw)
+    one = g.groups[0]
+    assert len(rec) == one.batched_per_group(4) > 80
+    assert all(r["us"] > 0 and r["tiles"] > 0 and r["rows"] > 0 and r["ctas"] >= 1 for r in rec)
+    v0 = sum(int(l.static_lattice.hash_table.count_tensor().cpu()) for l in one.lanes)
+    assert max(r["rows"] for r in rec) == v0          # the last frame's V0-level layers see every vertex of both windows
