@@ -115,10 +115,32 @@ class KittiSequence:
         """the three float64 matrices of kitti_dataloader.py:160-167, in application order"""
         return np.ascontiguousarray(np.stack([self.poses[int(idx)], np.linalg.inv(self.poses[int(first_idx)]), self._rx]))
 
-    def read_raw(self, idx):
-        """the .bin payload as a pinned host tensor [N,4] float32 (no per-point work on the host)"""
-        raw = np.fromfile(self.scan_path(idx), dtype=np.float32).reshape(-1, 4)
-        return torch.from_numpy(raw).pin_memory()
+    def _staging(self, k, nr_floats):
+        """reused pinned staging buffer of frame slot k (grown on demand): the .bin payload is read straight into it"""
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        buf = self._pinned.get(k)
+        if buf is None or buf.numel() < nr_floats:
+            buf = torch.empty(max(nr_floats, 4 * 140000), dtype=torch.float32).pin_memory()
+            self._pinned[k] = buf
+        return buf
+
+    def read_raw(self, idx, slot=0):
+        """the .bin payload as a pinned host tensor [N,4] float32: ONE read of the file into the slot's reused pinned
+        buffer (no intermediate numpy array, no per-scan pinning, no per-point work on the host).  Valid until the slot is
+        read into again."""
+        path = self.scan_path(idx)
+        nr_floats = os.path.getsize(path) // 4
+        ev = getattr(self, "_copied", {}).get(slot)
+        if ev is not None:
+            ev.synchronize()        # the previous window's host-to-device copy out of this slot has completed
+        buf = self._staging(slot, nr_floats)
+        view = buf.numpy()[:nr_floats]
+        with open(path, "rb") as f:
+            got = f.readinto(memoryview(view).cast("B"))
+        if got != 4 * nr_floats or nr_floats % 4:
+            raise RuntimeError("%s is not a whole number of float32 x 4 points" % path)
+        return buf[:nr_floats].view(-1, 4)
 
     def labels(self, idx):
         if self.lut is None:
@@ -126,32 +148,43 @@ class KittiSequence:
         return torch.from_numpy(load_labels(os.path.join(self.dir, "labels", "%06d.label" % int(idx)), self.lut).astype(np.int64))
 
     def window(self, index, with_labels=False, cap_distance=-1.0, min_distance=-1.0, shuffle=False, generator=None):
-        """-> [(positions [N,3], values [N,1])] on the device (+ labels of the last frame): the model's inputs for the window
-        ending at scan `index`, every frame expressed in the first frame's coordinates (kitti_dataloader.py:119-171).
+        """-> [(positions [N,3], values [N,1])] on the device (+ labels of the last frame, on the HOST): the model's inputs for
+        the window ending at scan `index`, every frame expressed in the first frame's coordinates (kitti_dataloader.py:119-171).
         Training-time options of the reference loader: cap_distance / min_distance >= 0 drop the points outside that range
         of the SENSOR (:142-154, before the pose transform, order preserved), shuffle permutes the points of every frame
-        (:173-180; the same permutation for positions, values and labels)."""
+        (:173-180; the same permutation for positions, values and labels).  `generator`, when given, must be a CUDA generator
+        of this sequence's device (the permutation is drawn on the device).  Crop and shuffle act on the labels ON THE
+        DEVICE too; they come back to the host once per window, so a frame costs one pinned read, one host-to-device copy
+        and device work only."""
         _lib.require_cuda()
+        if generator is not None and generator.device != self.device:
+            raise RuntimeError("shuffle needs a generator on %s (torch.Generator(device=...)), got one on %s" % (self.device, generator.device))
         idxs = window_indices(index, self.frames, self.scope)
         out, last_labels = [], None
         for k, idx in enumerate(idxs):
-            raw = self.read_raw(idx).to(self.device, non_blocking=True)
+            raw = self.read_raw(idx, slot=k).to(self.device, non_blocking=True)
+            if not hasattr(self, "_copied"):
+                self._copied = {}
+            self._copied[k] = torch.cuda.Event()
+            self._copied[k].record()
             lab = self.labels(idx) if (with_labels and k == len(idxs) - 1) else None
+            if lab is not None:
+                lab = lab.pin_memory().to(self.device, non_blocking=True)
             keep = range_mask(raw, cap_distance, min_distance)
             if keep is not None:
                 raw = raw[keep]
                 if lab is not None:
-                    lab = lab[keep.cpu()]
+                    lab = lab[keep]
             if shuffle:
                 perm = torch.randperm(raw.shape[0], device=raw.device, generator=generator)
                 raw = raw[perm]
                 if lab is not None:
-                    lab = lab[perm.cpu()]
+                    lab = lab[perm]
             out.append(assemble_scan(raw, self.matrices(idx, idxs[0])))
             if lab is not None:
                 last_labels = lab
         if with_labels:
-            return out, last_labels
+            return out, (last_labels.cpu() if last_labels is not None else None)
         return out
 
 

@@ -66,6 +66,13 @@ class WindowRunner:
             self.range_flag.zero_()
         return raised
 
+    def evaluate_window(self, frames_dev, target, scores, unlabeled_idx=0):
+        """test_ln.py:165-234 for one window: predict the last frame and fold it into `scores` (scores.Scores, the
+        reference's phase.scores) on the device; returns the log-softmax"""
+        out = self.infer_window_device(frames_dev)
+        scores.accumulate_scores(out, target, unlabeled_idx)
+        return out
+
     def infer_window(self, frames_host):
         """frames_host: list of (positions, values) PINNED host tensors.  Returns predicted labels of
         the last frame as a pinned host int64 tensor (test_ln.py:219-222), synchronised."""

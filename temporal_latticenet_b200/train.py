@@ -10,6 +10,7 @@ from .lattice import Lattice, ModelParams
 from .lovasz import LovaszSoftmax
 from .model import LatticeNetSeq
 from .parallel import FlatGradAllReduce, broadcast_parameters
+from .scores import Scores
 
 
 class WindowTrainer:
@@ -23,6 +24,9 @@ class WindowTrainer:
         self.lr, self.weight_decay = lr, weight_decay
         self.optimizer = None
         self.allreduce = None
+        self.ignore_index = ignore_index
+        self.scores = Scores()       # phase.scores of the reference (callbacks/state_callback.py:11-16), accumulated on the device
+        self.last_output = None
 
     def forward_window(self, frames, target):
         self.model.reset_sequence()
@@ -31,6 +35,7 @@ class WindowTrainer:
         last = len(frames) - 1
         for i, (p, v) in enumerate(frames):
             out, _, ls = self.model(ls, p, v, i != last, True)
+        self.last_output = out.detach()
         return 0.5 * self.lovasz(out, target) + 0.5 * self.nll(out, target)
 
     def materialise(self, frames, target, state_dict_fn=None):
@@ -55,6 +60,8 @@ class WindowTrainer:
         loss.backward()
         self.allreduce()
         self.optimizer.step()
+        # cb.after_forward_pass(pred_softmax=..., target=...) of train_ln.py:219: IoU bookkeeping, no host round trip
+        self.scores.accumulate_scores(self.last_output, target, self.ignore_index)
         return loss.detach()
 
     @property
