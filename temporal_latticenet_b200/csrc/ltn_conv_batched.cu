@@ -28,18 +28,26 @@ constexpr int kBlockM = 128;
 constexpr int kKB = 64;               // fp16 K elements per k-block = one 128-byte swizzle row
 constexpr int kGroups = 2;            // producer warpgroups, alternate k-blocks
 constexpr int kMaxBatch = 8;
-#ifndef LTN_CONVB_EPI_WARPS
-#define LTN_CONVB_EPI_WARPS 8       // epilogue warps: 4 (one warpgroup) or 8 (two: alternate 32-column chunks)
-#endif
-constexpr int kEpiWarps = LTN_CONVB_EPI_WARPS;
-constexpr int kWarpEpi0 = 8, kWarpMma = kWarpEpi0 + kEpiWarps, kWarpTma = kWarpMma + 1, kWarpMeta0 = kWarpMma + 2;
-constexpr int kThreadsB = 32 * (kWarpMma + 4);   // producers (2 warpgroups) + epilogue (1 or 2) + auxiliary warpgroup
+constexpr int kWarpEpi0 = 8;          // warps 0..7: the two producer warpgroups
 constexpr int kMetaThreads = 64;
 constexpr int kMetaBufs = 3;          // neighbour-slice buffers: the gather's issue cursor runs up to two tiles ahead of its consume cursor
 constexpr int kNbrPerMeta = (LTN_FEXT * kBlockM + kMetaThreads - 1) / kMetaThreads;
 constexpr int kMaxSA = 4, kMaxSB = 4;
-// register budgets after setmaxnreg (the block starts at 65536 / threads per thread, rounded down to a multiple of 8)
-constexpr int kRegsProducer = kEpiWarps == 8 ? 144 : 168, kRegsEpilogue = kEpiWarps == 8 ? 80 : 96, kRegsAux = kEpiWarps == 8 ? 64 : 56;
+
+// Role layout and register budgets for EPI = 4 or 8 epilogue warps (one or two warpgroups; with two, they take alternate
+// 32-column chunks).  Budgets after setmaxnreg: the pool the roles share is what the CTA was given AT LAUNCH -- threads x
+// the launch-time register count (65536 / threads rounded down to a multiple of 8 under __launch_bounds__(threads, 1)); a
+// setmaxnreg.inc that asks for more than the decs have released never returns, so the budgets must sum to at most that.
+template <int EPI>
+struct Roles {
+    static constexpr int kWarpMma = kWarpEpi0 + EPI, kWarpTma = kWarpMma + 1, kWarpMeta0 = kWarpMma + 2;
+    static constexpr int kThreads = 32 * (kWarpMma + 4);   // producers (2 warpgroups) + epilogue (1 or 2) + auxiliary warpgroup
+    static constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8;
+    static constexpr int kRegsProducer = EPI == 8 ? 144 : 168, kRegsEpilogue = EPI == 8 ? 72 : 96, kRegsAux = EPI == 8 ? 48 : 56;
+    static_assert(EPI == 4 || EPI == 8, "one or two epilogue warpgroups");
+    static_assert(32 * (8 * kRegsProducer + EPI * kRegsEpilogue + 4 * kRegsAux) <= kThreads * kLaunchRegs,
+                  "the per-role register budgets exceed the CTA's register pool: setmaxnreg.inc would spin forever");
+};
 
 struct BatchParams {
     const float* x[kMaxBatch];        // [Vx_b, C]
@@ -74,9 +82,13 @@ constexpr int kTraceStride = 2 + 2 * 148;   // u64 per launch record
 unsigned long long* g_trace_b = nullptr;
 int g_trace_slots = 0, g_trace_next = 0;
 
-__global__ void __launch_bounds__(kThreadsB, 1)
+template <int kEpiWarps>
+__global__ void __launch_bounds__(Roles<kEpiWarps>::kThreads, 1)
 k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                   const __grid_constant__ BatchParams p) {
+    using R = Roles<kEpiWarps>;
+    constexpr int kThreadsB = R::kThreads, kWarpMma = R::kWarpMma, kWarpTma = R::kWarpTma, kWarpMeta0 = R::kWarpMeta0;
+    constexpr int kRegsProducer = R::kRegsProducer, kRegsEpilogue = R::kRegsEpilogue, kRegsAux = R::kRegsAux;
     extern __shared__ uint8_t smem_raw[];
     // barriers: a_full[4] a_empty[4] b_full[4] b_empty[4] acc_full[2] acc_empty[2] meta_full[3] meta_empty[3]
     __shared__ __align__(8) uint64_t bars[2 * kMaxSA + 2 * kMaxSB + 4 + 2 * kMetaBufs];
@@ -499,22 +511,26 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 const int Vq = s_vq[t.b], Vx = s_vx[t.b];
                 const int* nbr = p.nbr[t.b];
                 int* dst = s_nbr[q];
-                int pref[kNbrPerMeta];   // all loads of the slice in flight together
+                constexpr int kChunk = 6;   // loads in flight per thread (the auxiliary warps run on a small register budget)
+                for (int u0 = 0; u0 < kNbrPerMeta; u0 += kChunk) {
+                    int pref[kChunk];
 #pragma unroll
-                for (int u = 0; u < kNbrPerMeta; ++u) {
-                    const int i = mt + u * kMetaThreads;
-                    const int r = i / S;
-                    int sv = -1;
-                    if (i < kBlockM * S && t.row0 + r < Vq) sv = nbr ? __ldg(nbr + (size_t)t.row0 * S + i) : t.row0 + r;
-                    pref[u] = sv;
-                }
-#pragma unroll
-                for (int u = 0; u < kNbrPerMeta; ++u) {
-                    const int i = mt + u * kMetaThreads;
-                    if (i < kBlockM * S) {
-                        const int r = i / S, sl = i - r * S;
-                        dst[sl * kBlockM + r] = pref[u] >= Vx ? -1 : pref[u];
+                    for (int u = 0; u < kChunk; ++u) {
+                        const int i = mt + (u0 + u) * kMetaThreads;
+                        const int r = i / S;
+                        int sv = -1;
+                        if (i < kBlockM * S && t.row0 + r < Vq) sv = nbr ? __ldg(nbr + (size_t)t.row0 * S + i) : t.row0 + r;
+                        pref[u] = sv;
                     }
+#pragma unroll
+                    for (int u = 0; u < kChunk; ++u) {
+                        const int i = mt + (u0 + u) * kMetaThreads;
+                        if (i < kBlockM * S) {
+                            const int r = i / S, sl = i - r * S;
+                            dst[sl * kBlockM + r] = pref[u] >= Vx ? -1 : pref[u];
+                        }
+                    }
+                    if ((u0 + kChunk) * kMetaThreads >= kBlockM * S) break;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_metafull + 8 * q);
@@ -625,23 +641,26 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
     p.stages_a = sa;
     const size_t b_stage = 2 * (size_t)n_tile * 128;
     static const int sb_cap = []() { const char* e = getenv("LTN_CONVB_SB"); return e && atoi(e) >= 2 ? atoi(e) : kMaxSB; }();
-    int sb = (int)(((size_t)(226 - 32 - 4 * kEpiWarps - 2) * 1024) / b_stage);   // 227 KB - static (~30 KB) - epilogue staging
+    static const int epi = []() { const char* e = getenv("LTN_CONVB_EPI"); return e && atoi(e) == 4 ? 4 : 8; }();   // epilogue warps
+    int sb = (int)(((size_t)(226 - 36 - 4 * epi - 2) * 1024) / b_stage);   // 227 KB - static (~35 KB) - epilogue staging
     if (sb > kMaxSB) sb = kMaxSB;
     if (sb > sb_cap) sb = sb_cap;
     if (sb < 2) return -3;
     p.stages_b = sb;
-    const size_t smem = (size_t)sb * b_stage + (size_t)kEpiWarps * 4096 + 1024;
+    const size_t smem = (size_t)sb * b_stage + (size_t)epi * 4096 + 1024;
     alignas(64) CUtensorMap map_hi, map_lo;
     int rc = make_weight_map(&map_hi, wt_hi, F, p.S * C, n_tile, true);
     if (rc) return rc;
     rc = make_weight_map(&map_lo, wt_lo, F, p.S * C, n_tile, true);
     if (rc) return rc;
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const void* fn = epi == 8 ? (const void*)k_conv_tc_batched<8> : (const void*)k_conv_tc_batched<4>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     long long tiles = row_tiles * ny;
     static const int grid_cap = []() { const char* e = getenv("LTN_CONVB_GRID"); return e && atoi(e) >= 1 ? atoi(e) : 148; }();
     const int grid = (int)(tiles < grid_cap ? tiles : grid_cap);
-    k_conv_tc_batched<<<grid, kThreadsB, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
+    if (epi == 8) k_conv_tc_batched<8><<<grid, Roles<8>::kThreads, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
+    else k_conv_tc_batched<4><<<grid, Roles<4>::kThreads, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
     LTN_CHECK_LAUNCH();
     return 0;
 }
