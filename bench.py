@@ -393,7 +393,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
-    ap.add_argument("--windows", type=int, default=4, help="distinct synthetic windows cycled through (per rank)")
+    ap.add_argument("--windows", type=int, default=2, help="distinct synthetic windows cycled through (per rank; seeds 1000 + rank * windows + i)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm", action="store_true", help="skip the splat / slice / im2row / distribute bandwidth table")
     ap.add_argument("--eager", action="store_true", help="eager per-op launches instead of CUDA-graph replay")

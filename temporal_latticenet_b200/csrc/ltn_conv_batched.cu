@@ -32,7 +32,7 @@ constexpr int kWarpEpi0 = 8;          // warps 0..7: the two producer warpgroups
 constexpr int kMetaThreads = 64;
 constexpr int kMetaBufs = 3;          // neighbour-slice buffers: the gather's issue cursor runs up to two tiles ahead of its consume cursor
 constexpr int kNbrPerMeta = (LTN_FEXT * kBlockM + kMetaThreads - 1) / kMetaThreads;
-constexpr int kMaxSA = 4, kMaxSB = 4;
+constexpr int kMaxSA = 4, kMaxSB = 9;   // weight ring: up to 9 stages so that a whole small weight tile (all k-blocks) can stay RESIDENT
 
 // Role layout and register budgets for EPI = 4 or 8 epilogue warps (one or two warpgroups; with two, they take alternate
 // 32-column chunks).  Budgets after setmaxnreg: the pool the roles share is what the CTA was given AT LAUNCH -- threads x
@@ -70,6 +70,7 @@ struct BatchParams {
     int C, S, F, ldo, relu, has_gn, has_sums;
     int n_tile, ny;
     int stages_a, stages_b, acc_bufs, acc_stride;
+    int resident;                     // stages_b == number of k-blocks: a channel tile's weights are loaded once per CTA and kept across its row tiles
     float a_mul, out_mul;
     unsigned long long* trace;        // nullable: this launch's trace record: [sum of live rows, tiles, then per CTA (entry, exit)] globaltimer ns
 };
@@ -153,7 +154,8 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     auto tile_at = [&](int it, Tile& t) -> bool {
         const int idx = (int)blockIdx.x + it * (int)gridDim.x;
         if (idx >= total_tiles) return false;
-        const int n = idx % p.ny, r = idx / p.ny;
+        const int row_tiles = s_prefix[p.nb];
+        const int n = idx / row_tiles, r = idx - n * row_tiles;   // channel tile slowest: a CTA's consecutive tiles share their weights
         int b = 0;
         while (b + 1 < p.nb && r >= s_prefix[b + 1]) ++b;
         t.b = b;
@@ -485,17 +487,24 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             if (lane == 0) {
                 int sb = 0;
                 uint32_t pb = 1u;
+                int loaded_n0 = -1;   // resident mode: the channel tile whose k-blocks the stages hold (stage = k-block)
                 for (int it = 0;; ++it) {
                     Tile t;
                     if (!tile_at(it, t)) break;
+                    const bool keep = p.resident && t.n0 == loaded_n0;
                     for (int kb = 0; kb < num_kb; ++kb) {
                         mbar_wait(bar_bempty + 8 * sb, pb);
-                        const uint32_t bb = smem_u32(smem + (size_t)sb * b_stage);
-                        mbar_arrive_expect_tx(bar_bfull + 8 * sb, b_stage);
-                        tma_load_2d(bb, &map_hi, bar_bfull + 8 * sb, kb * kKB, t.n0);
-                        tma_load_2d(bb + b_bytes, &map_lo, bar_bfull + 8 * sb, kb * kKB, t.n0);
+                        if (keep) {
+                            mbar_arrive(bar_bfull + 8 * sb);   // the stage already holds this k-block: hand it over again, no L2 read
+                        } else {
+                            const uint32_t bb = smem_u32(smem + (size_t)sb * b_stage);
+                            mbar_arrive_expect_tx(bar_bfull + 8 * sb, b_stage);
+                            tma_load_2d(bb, &map_hi, bar_bfull + 8 * sb, kb * kKB, t.n0);
+                            tma_load_2d(bb + b_bytes, &map_lo, bar_bfull + 8 * sb, kb * kKB, t.n0);
+                        }
                         if (++sb == SB) { sb = 0; pb ^= 1u; }
                     }
+                    loaded_n0 = t.n0;
                 }
             }
             __syncwarp();
@@ -640,12 +649,24 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
     if (sa < 2) return -3;
     p.stages_a = sa;
     const size_t b_stage = 2 * (size_t)n_tile * 128;
-    static const int sb_cap = []() { const char* e = getenv("LTN_CONVB_SB"); return e && atoi(e) >= 2 ? atoi(e) : kMaxSB; }();
+    static const int sb_cap = []() { const char* e = getenv("LTN_CONVB_SB"); return e && atoi(e) >= 2 ? atoi(e) : 4; }();
     static const int epi = []() { const char* e = getenv("LTN_CONVB_EPI"); return e && atoi(e) == 4 ? 4 : 8; }();   // epilogue warps
-    int sb = (int)(((size_t)(226 - 36 - 4 * epi - 2) * 1024) / b_stage);   // 227 KB - static (~35 KB) - epilogue staging
-    if (sb > kMaxSB) sb = kMaxSB;
-    if (sb > sb_cap) sb = sb_cap;
-    if (sb < 2) return -3;
+    static const int want_resident = []() { const char* e = getenv("LTN_CONVB_RESIDENT"); return e ? atoi(e) : 1; }();
+    const size_t b_budget = (size_t)(226 - 36 - 4 * epi - 2) * 1024;   // 227 KB - static (~35 KB) - epilogue staging
+    const int num_kb = p.S * C / kKB;
+    int sb = (int)(b_budget / b_stage);
+    // Weights RESIDENT: when all k-blocks of a channel tile fit the ring (every dense layer, the 64 -> 64 convolutions), the
+    // ring gets one stage per k-block and the TMA lane loads each stage once per CTA and channel tile; the following row
+    // tiles re-use it.  Otherwise every row tile streams the whole K x N tile again from L2 -- which is what bounds the
+    // batched kernel (measured: 5-7 TB/s of L2 -> SM traffic, 40-60 % of it weights).
+    p.resident = (want_resident && num_kb <= kMaxSB && num_kb <= sb) ? 1 : 0;
+    if (p.resident) {
+        sb = num_kb;                 // stage = k-block (a single-k-block layer runs on a ring of one stage: nothing is ever re-loaded)
+    } else {
+        if (sb > 4) sb = 4;
+        if (sb > sb_cap) sb = sb_cap;
+        if (sb < 2) return -3;
+    }
     p.stages_b = sb;
     const size_t smem = (size_t)sb * b_stage + (size_t)epi * 4096 + 1024;
     alignas(64) CUtensorMap map_hi, map_lo;

@@ -600,17 +600,27 @@ class LockstepRunner:
                 graph.replay()
         return outs
 
+    def begin_windows_device(self, windows_dev):
+        """queues one group behind the caller's current stream WITHOUT making that stream wait for it; returns a handle for
+        end_windows_device().  Several runners (GroupedLockstepRunner) begin their groups first and end them afterwards, so
+        the groups overlap on the device."""
+        cur = torch.cuda.current_stream()
+        if not self._fits(windows_dev):
+            return ("lanes", [self.lanes[i % len(self.lanes)].infer_window_device(w) for i, w in enumerate(windows_dev)])
+        self.main.wait_stream(cur)
+        outs = self._run_group(windows_dev)
+        return ("group", [o[: w[-1][0].shape[0]] for o, w in zip(outs, windows_dev)])
+
+    def end_windows_device(self, handle):
+        if handle[0] == "group":
+            torch.cuda.current_stream().wait_stream(self.main)
+        return handle[1]
+
     def infer_windows_device(self, windows_dev):
         """windows_dev: lists of (positions, values) CUDA tensors, one per lane.  Returns the log-softmax of each window's
         last frame (views of the graphs' static outputs: valid until the next group runs; clone to keep).  The caller's
         stream waits for the group."""
-        cur = torch.cuda.current_stream()
-        if not self._fits(windows_dev):
-            return [self.lanes[i % len(self.lanes)].infer_window_device(w) for i, w in enumerate(windows_dev)]
-        self.main.wait_stream(cur)
-        outs = self._run_group(windows_dev)
-        cur.wait_stream(self.main)
-        return [o[: w[-1][0].shape[0]] for o, w in zip(outs, windows_dev)]
+        return self.end_windows_device(self.begin_windows_device(windows_dev))
 
     def submit(self, windows_host):
         """queues one group of windows given as PINNED host tensors; returns a ticket for collect().  The host -> device
@@ -737,9 +747,10 @@ class GroupedLockstepRunner:
         return [windows[i:i + k] for i in range(0, len(windows), k)]
 
     def infer_windows_device(self, windows_dev):
-        outs = []
-        for g, part in zip(self.groups, self._split(windows_dev)):
-            outs += g.infer_windows_device(part)     # queued asynchronously: the groups overlap on the device
+        handles = [g.begin_windows_device(part) for g, part in zip(self.groups, self._split(windows_dev))]   # all queued first:
+        outs = []                                                                                             # the groups overlap
+        for g, h in zip(self.groups, handles):
+            outs += g.end_windows_device(h)
         return outs
 
     def submit(self, windows_host):
@@ -763,6 +774,8 @@ class GroupedLockstepRunner:
     def trace_group(self, windows_dev):
         """records of ONE group's launches with the other groups running beside it (the timed configuration)"""
         parts = self._split(windows_dev)
-        for g, part in zip(self.groups[1:], parts[1:]):
-            g.infer_windows_device(part)
-        return self.groups[0].trace_group(parts[0])
+        handles = [g.begin_windows_device(part) for g, part in zip(self.groups[1:], parts[1:])]
+        rec = self.groups[0].trace_group(parts[0])
+        for g, h in zip(self.groups[1:], handles):
+            g.end_windows_device(h)
+        return rec

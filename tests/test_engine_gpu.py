@@ -133,8 +133,9 @@ def test_graph_runner_other_fusion_configs(rnn, tmp_path):
             assert graph.counts_ok()
             finite = np.isfinite(want)
             assert np.array_equal(finite, np.isfinite(got))   # AFlow's 0/0 rows (quirk Q5) stay where the eager path has them
-            err = float(np.abs(got[finite] - want[finite]).max()) / float(np.abs(want[finite]).max())
-            assert err < 1e-4, err
+            if finite.any():   # (an early AFlow's NaN reaches every vertex through the GroupNorm statistics, as in the reference)
+                err = float(np.abs(got[finite] - want[finite]).max()) / float(np.abs(want[finite]).max())
+                assert err < 1e-4, err
 
 
 def test_every_fusion_kind_has_a_static_capacity_path(tmp_path):
