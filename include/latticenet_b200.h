@@ -163,6 +163,9 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
  * launch (captured launches keep writing on every replay).  NULL switches it off.  Returns the records used since the
  * previous call. */
 int ltn_conv_batched_trace(unsigned long long* buf, int nr_records);
+/* role timeline of CTA 0 of the following batched launches: buf [64 tiles][16] u64 globaltimer stamps (see the source for
+ * the slots); NULL switches it off */
+int ltn_conv_batched_detail(unsigned long long* buf);
 /* phase tracing of the following ltn_conv_tc* launches (NULL switches it off): buf receives 8 globaltimer stamps (ns)
  * per CTA in launch-grid order -- entry, set-up done, first operands staged, producers done, accumulator complete,
  * epilogue stores issued, teardown, (unused) */

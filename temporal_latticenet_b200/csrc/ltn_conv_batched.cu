@@ -72,6 +72,7 @@ struct BatchParams {
     int stages_a, stages_b, acc_bufs, acc_stride;
     int resident;                     // stages_b == number of k-blocks: a channel tile's weights are loaded once per CTA and kept across its row tiles
     float a_mul, out_mul;
+    unsigned long long* detail;       // nullable: [64 tiles][16] globaltimer stamps of CTA 0's roles (ltn_conv_batched_detail)
     unsigned long long* trace;        // nullable: this launch's trace record: [sum of live rows, tiles, then per CTA (entry, exit)] globaltimer ns
 };
 
@@ -81,7 +82,16 @@ struct Tile {
 
 constexpr int kTraceStride = 2 + 2 * 148;   // u64 per launch record
 unsigned long long* g_trace_b = nullptr;
+unsigned long long* g_detail_b = nullptr;
 int g_trace_slots = 0, g_trace_next = 0;
+
+__device__ __forceinline__ void detail_stamp(unsigned long long* buf, int it, int slot) {
+    if (buf && blockIdx.x == 0 && it < 64) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        buf[it * 16 + slot] = t;
+    }
+}
 
 template <int kEpiWarps>
 __global__ void __launch_bounds__(Roles<kEpiWarps>::kThreads, 1)
@@ -245,12 +255,14 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 i_c0 = (first - i_slot * kb_per_slot) * kKB;
                 i_cur = -1;
                 i_valid = true;
+                if (tid == 0) detail_stamp(p.detail, i_it, 0);
                 return;
             }
         };
         auto consume_next_tile = [&]() {
             for (;;) {
                 if (c_it >= 0) {   // leaving tile c_it: its neighbour slice is no longer read by this warp (the issue cursor is ahead)
+                    if (tid == 0) detail_stamp(p.detail, c_it, 2);
                     if (c_flag && !(amax < 65504.f)) atomicOr(c_flag, 1);
                     amax = 0.f;
                     c_flag = nullptr;
@@ -269,6 +281,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 const int sl = first / kb_per_slot;
                 c_c0 = (first - sl * kb_per_slot) * kKB;
                 c_valid = true;
+                if (tid == 0) detail_stamp(p.detail, c_it, 1);
                 return;
             }
         };
@@ -370,6 +383,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             if (lane == 0) mbar_wait(bar_accfull + 8 * a, (uint32_t)use & 1u);
             __syncwarp();
             tc_fence_after();
+            if (warp == kWarpEpi0 && lane == 0) detail_stamp(p.detail, it, 6);
             const int Vq = s_vq[t.b];
             float* out = p.out[t.b];
             const float* res = p.res[t.b];
@@ -424,6 +438,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_accempty + 8 * a);
+            if (warp == kWarpEpi0 && lane == 0) detail_stamp(p.detail, it, 7);
             if (p.has_sums) {
                 // per-tile column sums -> group sums -> one double atomic per group; the buffer of this tile parity is
                 // cleared here and next used two tiles later, after the next tile's barrier
@@ -454,15 +469,19 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     Tile t;
                     if (!tile_at(it, t)) break;
                     const int a = it % p.acc_bufs, use = it / p.acc_bufs;
+                    detail_stamp(p.detail, it, 3);
                     mbar_wait(bar_accempty + 8 * a, ((uint32_t)use & 1u) ^ 1u);   // the epilogue has drained this accumulator
                     tc_fence_after();
+                    detail_stamp(p.detail, it, 4);
                     // instruction descriptor: D = F32 [4,6), A / B = F16 (0) [7,10) [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
                     const uint32_t idesc = (1u << 4) | ((uint32_t)(t.Nmma >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
                     const uint32_t td = tmem_base + (uint32_t)(a * p.acc_stride);
                     for (int kb = 0; kb < num_kb; ++kb) {
                         mbar_wait(bar_bfull + 8 * sb, pb);
+                        if (kb == 0) detail_stamp(p.detail, it, 8);
                         mbar_wait(bar_afull + 8 * sa, pa);
                         tc_fence_after();
+                        if (kb == 0) detail_stamp(p.detail, it, 9);
                         const uint32_t bb = smem_u32(smem + (size_t)sb * b_stage);
                         const uint64_t b_hi = make_desc(bb), b_lo = make_desc(bb + b_bytes);
                         const uint32_t ta = tmem_base + a_col0 + (uint32_t)sa * 64u;
@@ -479,6 +498,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                         if (++sb == SB) { sb = 0; pb ^= 1u; }
                     }
                     umma_commit(bar_accfull + 8 * a);
+                    detail_stamp(p.detail, it, 5);
                 }
             }
             __syncwarp();
@@ -505,6 +525,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                         if (++sb == SB) { sb = 0; pb ^= 1u; }
                     }
                     loaded_n0 = t.n0;
+                    detail_stamp(p.detail, it, 10);
                 }
             }
             __syncwarp();
@@ -543,6 +564,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_metafull + 8 * q);
+                if (mt == 0) detail_stamp(p.detail, it, 11);
             }
         }
     }
@@ -580,6 +602,15 @@ int ltn_conv_batched_trace(unsigned long long* buf, int nr_records) {
     g_trace_slots = buf ? nr_records : 0;
     g_trace_next = 0;
     return used;
+}
+
+// Role timeline of CTA 0 of the following batched launches: buf [64 tiles][16] u64 (zeroed by the caller) receives %globaltimer
+// stamps -- 0 gather issue cursor enters the tile, 1 / 2 gather consume cursor enters / leaves, 3 / 4 MMA issuer before / after
+// the accumulator hand-back wait, 8 / 9 first weight stage / first A stage ready, 5 accumulator committed, 6 / 7 epilogue
+// sees the accumulator / hands it back, 10 last weight k-block issued, 11 neighbour slice staged.  NULL switches it off.
+int ltn_conv_batched_detail(unsigned long long* buf) {
+    g_detail_b = buf;
+    return 0;
 }
 
 // The fp16-operand fused convolution of ltn_conv_tc_f16 for nb <= 8 independent problems that share the weights (the same
@@ -626,6 +657,7 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
     p.C = C; p.S = has_nbr ? S : 1; p.F = F; p.ldo = ldo; p.relu = relu; p.has_gn = has_gn ? 1 : 0; p.has_sums = has_sums ? 1 : 0;
     p.a_mul = ldexpf(1.0f, a_log2);
     p.out_mul = ldexpf(1.0f, -(a_log2 + w_log2));
+    p.detail = g_detail_b;
     p.trace = (g_trace_b && g_trace_next < g_trace_slots) ? g_trace_b + (size_t)kTraceStride * g_trace_next++ : nullptr;
     // Output channels per tile: at most 192, so that TWO accumulators and an A ring of >= 2 stages fit the 512 columns of
     // tensor memory; fewer when the tile list would leave SMs idle (small levels).
