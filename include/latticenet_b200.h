@@ -157,7 +157,15 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
                             const int* Vq, const int* const* vq_dev, int C, int S, const void* wt_hi, const void* wt_lo, int w_log2,
                             int a_log2, int F, const double* const* gn_sums, const float* gn_gamma, const float* gn_beta,
                             float gn_eps, int gn_groups, int relu, const float* bias, const float* const* res, float* const* out,
-                            int ldo, double* const* out_sums, int out_groups, int* const* flag, void* stream);
+                            int ldo, double* const* out_sums, int out_groups, int* const* flag, int staged, void* stream);
+/* A-operand pre-staging for the gathering layers (ConvLatticeModule / coarsen / finefy, S = 9): one pass per layer input does
+ * what the gather loop would otherwise repeat for each of a row's nine uses -- folded GroupNorm, ReLU, x 2^a_log2, fp16 range
+ * check, hi / lo split -- and writes, per 4 channels, the 16-byte quad {hi01, hi23, lo01, lo23} into out[b] ([Vx_b, C], the
+ * size of x[b]).  ltn_conv_tc_f16_batched(..., staged = 1) takes out[] in place of x[] (gn_sums then unused).  Bit-identical
+ * results. */
+int ltn_stage_a_batched(int nb, const float* const* x, const int* Vx, const int* const* vx_dev, int C, const double* const* gn_sums,
+                        const float* gn_gamma, const float* gn_beta, float gn_eps, int gn_groups, int relu, int a_log2,
+                        void* const* out, int* const* flag, void* stream);
 /* tracing of the following batched launches: launch i < nr_records writes record i of buf ([nr_records, 2 + 2*148] u64,
  * zeroed by the caller): live rows, tiles, then (entry, exit) globaltimer ns per CTA; the record address is baked into the
  * launch (captured launches keep writing on every replay).  NULL switches it off.  Returns the records used since the

@@ -70,8 +70,10 @@ struct BatchParams {
     int C, S, F, ldo, relu, has_gn, has_sums;
     int n_tile, ny;
     int stages_a, stages_b, acc_bufs, acc_stride;
+    int staged;                       // x[] hold PRE-STAGED operands (k_stage_a): per 4 channels one 16-byte quad {hi01, hi23, lo01, lo23}
     int resident;                     // stages_b == number of k-blocks: a channel tile's weights are loaded once per CTA and kept across its row tiles
     float a_mul, out_mul;
+    int debug;                        // timing experiments only (LTN_CONVB_DEBUG): 1 no gather loads, 2 no staging, 4 no MMA issue, 8 no epilogue work
     unsigned long long* detail;       // nullable: [64 tiles][16] globaltimer stamps of CTA 0's roles (ltn_conv_batched_detail)
     unsigned long long* trace;        // nullable: this launch's trace record: [sum of live rows, tiles, then per CTA (entry, exit)] globaltimer ns
 };
@@ -301,11 +303,13 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             }
             const uint32_t o = (uint32_t)i_c0 >> 2;
             dmask = half ? (rmask >> 2) : rmask;
+            if (!(p.debug & 1)) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t ri = (half ? rowidx[2 + h] : rowidx[h]) + o;
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t ri = (half ? rowidx[2 + h] : rowidx[h]) + o;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) dst[4 * h + g] = __ldg(i_x4 + ri + 4 * g);
+                    for (int g = 0; g < 4; ++g) dst[4 * h + g] = __ldg(i_x4 + ri + 4 * g);
+                }
             }
             if (!half) return;
             if (--i_left == 0) { issue_next_tile(); return; }
@@ -319,6 +323,23 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 tc_fence_after();
             }
             uint32_t hi[16], lo[16];
+            if (!(p.debug & 2)) {
+            if (p.staged) {
+                // operands were split once per layer by k_stage_a (GroupNorm + ReLU + x 2^a, fp16 hi / lo): the gathered
+                // 16 bytes ARE the four registers tcgen05.st wants for these 4 channels -- no arithmetic in the gather loop
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const bool ok = (cmask >> h) & 1u;   // absent neighbour / row beyond the tile -> zeros
+                        const float4 v = cur[4 * h + g];
+                        hi[4 * g + 2 * h] = ok ? __float_as_uint(v.x) : 0u;
+                        hi[4 * g + 2 * h + 1] = ok ? __float_as_uint(v.y) : 0u;
+                        lo[4 * g + 2 * h] = ok ? __float_as_uint(v.z) : 0u;
+                        lo[4 * g + 2 * h + 1] = ok ? __float_as_uint(v.w) : 0u;
+                    }
+                }
+            } else {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 float4 sc = make_float4(a_mul, a_mul, a_mul, a_mul), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -343,9 +364,11 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     lo[4 * g + 2 * h + 1] = *reinterpret_cast<const uint32_t*>(&l23);
                 }
             }
+            }
             const uint32_t ta = tmem_base + ((uint32_t)(wrow0 + 16 * half) << 16) + a_col0 + (uint32_t)c_stage * 64u;
             tmem_st_16x256b_x4(ta, hi);
             tmem_st_16x256b_x4(ta + 32u, lo);
+            }
             if (half == 0) return;
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
@@ -388,7 +411,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             float* out = p.out[t.b];
             const float* res = p.res[t.b];
             float* colsum = s_colsum[it & 1];
-            for (int cb = eh * 32; cb < t.N; cb += 32 * (kEpiWarps / 4)) {
+            for (int cb = eh * 32; cb < t.N && !(p.debug & 8); cb += 32 * (kEpiWarps / 4)) {
                 float acc[32];
                 tmem_ld32(t_lane + (uint32_t)(a * p.acc_stride + cb), acc);
 #pragma unroll
@@ -485,12 +508,14 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                         const uint32_t bb = smem_u32(smem + (size_t)sb * b_stage);
                         const uint64_t b_hi = make_desc(bb), b_lo = make_desc(bb + b_bytes);
                         const uint32_t ta = tmem_base + a_col0 + (uint32_t)sa * 64u;
+                        if (!(p.debug & 4)) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                            umma_ts<true>(td, ta + k * 8, b_hi + adv, idesc, (kb | k) != 0);
-                            umma_ts<true>(td, ta + 32u + k * 8, b_hi + adv, idesc, 1);
-                            umma_ts<true>(td, ta + k * 8, b_lo + adv, idesc, 1);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                                umma_ts<true>(td, ta + k * 8, b_hi + adv, idesc, (kb | k) != 0);
+                                umma_ts<true>(td, ta + 32u + k * 8, b_hi + adv, idesc, 1);
+                                umma_ts<true>(td, ta + k * 8, b_lo + adv, idesc, 1);
+                            }
                         }
                         umma_commit(bar_aempty + 8 * sa);
                         umma_commit(bar_bempty + 8 * sb);
@@ -588,6 +613,75 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     }
 }
 
+// A-operand pre-staging for the gathering (S = 9) layers.  The gather loop of the convolution touches every vertex row
+// nine times (once per neighbour slot, from different tiles); converting the row each time -- GroupNorm affine, ReLU,
+// fp16 range check, hi / lo split: ~16 instructions per value -- made the producers, not the tensor pipe or the memory
+// system, the bound of the batched kernel (measured: 1.1 us of staging per k-block against 0.6 us of MMA at N = 192).
+// This pass does that work ONCE per row and layer and leaves, per 4 channels, the 16 bytes {hi01, hi23, lo01, lo23} that
+// tcgen05.st takes for them -- same size and indexing as the fp32 row, so the gather loop only moves data.  The
+// arithmetic is the inline path's, operation for operation: results are bit-identical.
+struct StageParams {
+    const float* x[kMaxBatch];
+    const double* gn_sums[kMaxBatch];
+    uint4* out[kMaxBatch];
+    const int* vx_dev[kMaxBatch];
+    int* flag[kMaxBatch];
+    int Vx[kMaxBatch];
+    const float* gn_gamma;
+    const float* gn_beta;
+    float gn_eps, a_mul;
+    int gn_cpg, C, relu, has_gn;
+};
+
+__global__ void __launch_bounds__(256)
+k_stage_a(const __grid_constant__ StageParams p) {
+    __shared__ __align__(16) float s_aff[512];
+    const int b = blockIdx.y;
+    const int Vx = p.vx_dev[b] ? min(p.Vx[b], __ldg(p.vx_dev[b])) : p.Vx[b];
+    const int C = p.C, C4 = C >> 2;
+    if (p.has_gn) {
+        const double* sums = p.gn_sums[b];
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const int g = c / p.gn_cpg;
+            const double n = (double)Vx * p.gn_cpg;
+            const double mean = sums[2 * g] / n;
+            double var = sums[2 * g + 1] / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)p.gn_eps));
+            const float sc = rstd * (p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.0f);
+            const float sh = (p.gn_beta ? __ldg(p.gn_beta + c) : 0.0f) - (float)mean * sc;
+            s_aff[c] = sc * p.a_mul;
+            s_aff[256 + c] = sh * p.a_mul;
+        }
+    }
+    __syncthreads();
+    const float4* x4 = reinterpret_cast<const float4*>(p.x[b]);
+    uint4* out = p.out[b];
+    const long long total = (long long)Vx * C4;
+    float amax = 0.f;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(t % C4);
+        float4 sc = make_float4(p.a_mul, p.a_mul, p.a_mul, p.a_mul), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.has_gn) {
+            sc = *reinterpret_cast<const float4*>(s_aff + 4 * q);
+            sh = *reinterpret_cast<const float4*>(s_aff + 256 + 4 * q);
+        }
+        float4 v = __ldg(x4 + t);
+        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        if (p.relu) { v.x = relu_nan(v.x); v.y = relu_nan(v.y); v.z = relu_nan(v.z); v.w = relu_nan(v.w); }
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+        uint4 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&h01); o.y = *reinterpret_cast<const uint32_t*>(&h23);
+        o.z = *reinterpret_cast<const uint32_t*>(&l01); o.w = *reinterpret_cast<const uint32_t*>(&l23);
+        out[t] = o;
+    }
+    if (p.flag[b] && !(amax < 65504.f)) atomicOr(p.flag[b], 1);
+}
+
 }  // namespace
 
 extern "C" {
@@ -613,6 +707,38 @@ int ltn_conv_batched_detail(unsigned long long* buf) {
     return 0;
 }
 
+// A-operand pre-staging (k_stage_a) for nb problems: out[b] [Vx_b, C] (same bytes as x[b]) receives, per 4 channels, the
+// fp16 quads {hi01, hi23, lo01, lo23} of relu?(GroupNorm(x)) * 2^a_log2; flag[b] is OR-ed with 1 when a value leaves the
+// fp16 range.  ltn_conv_tc_f16_batched(..., staged = 1) then takes out[] in place of x[].
+int ltn_stage_a_batched(int nb, const float* const* x, const int* Vx, const int* const* vx_dev, int C, const double* const* gn_sums,
+                        const float* gn_gamma, const float* gn_beta, float gn_eps, int gn_groups, int relu, int a_log2,
+                        void* const* out, int* const* flag, void* stream) {
+    if (nb <= 0) return 0;
+    if (nb > kMaxBatch || C <= 0 || C % 4 || C > 256) return -2;
+    const bool has_gn = gn_sums && gn_sums[0];
+    if (has_gn && (gn_groups <= 0 || C % gn_groups)) return -2;
+    static StageParams p;
+    memset(&p, 0, sizeof(p));
+    int live = 0, vmax = 0;
+    for (int b = 0; b < nb; ++b) {
+        if (Vx[b] <= 0) continue;
+        p.x[live] = x[b]; p.gn_sums[live] = has_gn ? gn_sums[b] : nullptr; p.out[live] = reinterpret_cast<uint4*>(out[b]);
+        p.vx_dev[live] = vx_dev ? vx_dev[b] : nullptr; p.flag[live] = flag ? flag[b] : nullptr; p.Vx[live] = Vx[b];
+        if (Vx[b] > vmax) vmax = Vx[b];
+        ++live;
+    }
+    if (live == 0) return 0;
+    p.gn_gamma = gn_gamma; p.gn_beta = gn_beta; p.gn_eps = gn_eps; p.a_mul = ldexpf(1.0f, a_log2);
+    p.gn_cpg = has_gn ? C / gn_groups : 1; p.C = C; p.relu = relu; p.has_gn = has_gn ? 1 : 0;
+    long long items = (long long)vmax * (C / 4);
+    int bx = (int)((items + 256 * 4 - 1) / (256 * 4));   // ~4 quads per thread
+    if (bx < 1) bx = 1;
+    if (bx > 148 * 8) bx = 148 * 8;
+    k_stage_a<<<dim3(bx, live), 256, 0, (cudaStream_t)stream>>>(p);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
 // The fp16-operand fused convolution of ltn_conv_tc_f16 for nb <= 8 independent problems that share the weights (the same
 // layer of several windows in flight): every per-problem argument is a HOST array of nb entries.  Requirements as
 // ltn_conv_tc_f16 (C % 64 == 0, C <= 256 with a folded GroupNorm, F % 8 == 0, ldo % 4 == 0); an explicit a_scale/a_shift
@@ -621,7 +747,7 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
                             const int* Vq, const int* const* vq_dev, int C, int S, const void* wt_hi, const void* wt_lo, int w_log2,
                             int a_log2, int F, const double* const* gn_sums, const float* gn_gamma, const float* gn_beta,
                             float gn_eps, int gn_groups, int relu, const float* bias, const float* const* res, float* const* out,
-                            int ldo, double* const* out_sums, int out_groups, int* const* flag, void* stream) {
+                            int ldo, double* const* out_sums, int out_groups, int* const* flag, int staged, void* stream) {
     if (nb <= 0) return 0;
     if (nb > kMaxBatch) return -2;
     const bool has_nbr = nbr && nbr[0];
@@ -657,6 +783,10 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
     p.C = C; p.S = has_nbr ? S : 1; p.F = F; p.ldo = ldo; p.relu = relu; p.has_gn = has_gn ? 1 : 0; p.has_sums = has_sums ? 1 : 0;
     p.a_mul = ldexpf(1.0f, a_log2);
     p.out_mul = ldexpf(1.0f, -(a_log2 + w_log2));
+    p.staged = staged ? 1 : 0;       // x[] are ltn_stage_a_batched outputs: affine / ReLU / split already applied
+    if (p.staged) p.has_gn = 0;
+    static const int dbg = []() { const char* e = getenv("LTN_CONVB_DEBUG"); return e ? atoi(e) : 0; }();
+    p.debug = dbg;
     p.detail = g_detail_b;
     p.trace = (g_trace_b && g_trace_next < g_trace_slots) ? g_trace_b + (size_t)kTraceStride * g_trace_next++ : nullptr;
     // Output channels per tile: at most 192, so that TWO accumulators and an A ring of >= 2 stages fit the 512 columns of

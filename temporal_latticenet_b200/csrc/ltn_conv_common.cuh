@@ -103,7 +103,11 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mas
 // ReLU that keeps NaN (torch.relu semantics): fmaxf(NaN, 0) would return 0 and silently repair the NaN rows the
 // reference's AFlow produces on all-zero neighbourhoods (quirk Q5, lattice_modules.py:321), which GroupNorm then
 // spreads over the whole level -- parity includes producing NaN where the reference does
-__device__ __forceinline__ float relu_nan(float x) { return x < 0.f ? 0.f : x; }
+__device__ __forceinline__ float relu_nan(float x) {
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));   // one FMNMX.NAN instead of a compare + select
+    return r;
+}
 
 __device__ __forceinline__ float tf32_hi(float x) {
     uint32_t r;

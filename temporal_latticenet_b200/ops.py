@@ -1,6 +1,7 @@
 """Dense / reduction primitives shared by the lattice modules: fp32 matmul, GroupNorm(+ReLU) over
 lattice vertices, segmented max / add / mean.  GPU only."""
 import ctypes
+import os
 import threading
 import weakref
 
@@ -321,6 +322,7 @@ def conv_tc(x, nbr, wt, nr_rows=None, a_scale=None, a_shift=None, gn=None, relu=
     return out
 
 
+STAGE_GATHERED = os.environ.get("LTN_CONVB_STAGE", "1") != "0"   # pre-stage the A operand of gathering layers (csrc k_stage_a)
 _BATCH = threading.local()   # .ctx: coordinator of a lock-step capture (engine.LockstepRunner), absent otherwise
 MAX_BATCH = 8
 
@@ -346,11 +348,21 @@ def conv_tc_batched(reqs):
     ints = lambda k: (ctypes.c_int * nb)(*[int(r[k]) for r in reqs])   # noqa: E731
     arr = lambda k: _ptr_array([r[k] for r in reqs])                    # noqa: E731
     p = _lib.ptr
-    rc = _lib.load().ltn_conv_tc_f16_batched(nb, arr("x"), ints("Vx"), arr("vx_dev"), arr("nbr"), ints("Vq"), arr("vq_dev"), r0["C"], r0["S"],
-                                             p(r0["hi"]), p(r0["lo"]), r0["w_log2"], int(A_LOG2), r0["F"], arr("g_sums"), p(r0["g_gamma"]),
-                                             p(r0["g_beta"]), r0["g_eps"], r0["g_groups"], r0["relu"], p(r0["bias"]), arr("res"), arr("out"),
-                                             r0["ldo"], arr("out_sums"), 0 if r0["out_sums"] is None else r0["out_sums"].shape[0],
-                                             arr("flag"), _lib.stream())
+    lib = _lib.load()
+    x_arr, gn_arr, staged = arr("x"), arr("g_sums"), 0
+    if STAGE_GATHERED and r0["nbr"] is not None and r0["C"] <= 256:
+        # gathering layer: every row is used by ~9 tiles, so its GroupNorm / ReLU / fp16 hi-lo split is done ONCE here
+        # (k_stage_a) instead of nine times in the gather loop; the convolution then only moves the staged quads
+        bufs = [torch.empty_like(r["x"]) for r in reqs]
+        rc = lib.ltn_stage_a_batched(nb, x_arr, ints("Vx"), arr("vx_dev"), r0["C"], gn_arr, p(r0["g_gamma"]), p(r0["g_beta"]), r0["g_eps"],
+                                     r0["g_groups"], r0["relu"], int(A_LOG2), _ptr_array(bufs), arr("flag"), _lib.stream())
+        _lib.check(rc, "ltn_stage_a_batched")
+        x_arr, staged = _ptr_array(bufs), 1
+    rc = lib.ltn_conv_tc_f16_batched(nb, x_arr, ints("Vx"), arr("vx_dev"), arr("nbr"), ints("Vq"), arr("vq_dev"), r0["C"], r0["S"],
+                                     p(r0["hi"]), p(r0["lo"]), r0["w_log2"], int(A_LOG2), r0["F"], gn_arr, p(r0["g_gamma"]),
+                                     p(r0["g_beta"]), r0["g_eps"], r0["g_groups"], r0["relu"], p(r0["bias"]), arr("res"), arr("out"),
+                                     r0["ldo"], arr("out_sums"), 0 if r0["out_sums"] is None else r0["out_sums"].shape[0],
+                                     arr("flag"), staged, _lib.stream())
     _lib.check(rc, "ltn_conv_tc_f16_batched")
 
 
