@@ -324,22 +324,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             }
             uint32_t hi[16], lo[16];
             if (!(p.debug & 2)) {
-            if (p.staged) {
-                // operands were split once per layer by k_stage_a (GroupNorm + ReLU + x 2^a, fp16 hi / lo): the gathered
-                // 16 bytes ARE the four registers tcgen05.st wants for these 4 channels -- no arithmetic in the gather loop
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const bool ok = (cmask >> h) & 1u;   // absent neighbour / row beyond the tile -> zeros
-                        const float4 v = cur[4 * h + g];
-                        hi[4 * g + 2 * h] = ok ? __float_as_uint(v.x) : 0u;
-                        hi[4 * g + 2 * h + 1] = ok ? __float_as_uint(v.y) : 0u;
-                        lo[4 * g + 2 * h] = ok ? __float_as_uint(v.z) : 0u;
-                        lo[4 * g + 2 * h + 1] = ok ? __float_as_uint(v.w) : 0u;
-                    }
-                }
-            } else {
+            {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 float4 sc = make_float4(a_mul, a_mul, a_mul, a_mul), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -380,6 +365,91 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             c_c0 += kGroups * kKB;
             while (c_c0 >= C) c_c0 -= C;
         };
+        if (p.staged) {
+            // ---- pre-staged operands (k_stage_a): the gather only moves 16-byte quads, so what bounds it is the number of
+            // loads in flight.  THREE register buffers: the loads run two units (one k-block) ahead of the tensor-memory
+            // stores.  The issue cursor changes tile LAZILY (at its next first-half issue), so that it never waits for a
+            // neighbour slice whose buffer this very warp has not released yet.
+            float4 sb3[3][8];
+            uint32_t sm3[3];
+            bool sv3[3] = {false, false, false};
+            bool i_pending = false;
+            auto issue_s = [&](float4* dst, uint32_t& dmask, bool& dvalid, const int half) {
+                if (!half) {
+                    if (i_pending) { issue_next_tile(); i_pending = false; }
+                    if (!i_valid) { dvalid = false; return; }
+                } else if (!i_valid) { dvalid = false; return; }
+                dvalid = true;
+                if (i_slot != i_cur) {
+                    i_cur = i_slot;
+                    const int* tap = i_nbr + i_slot * kBlockM + wrow0 + ra;
+                    rmask = 0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int sv = tap[8 * r];
+                        rowidx[r] = (uint32_t)(sv >= 0 ? sv : 0) * c4 + (uint32_t)cq;
+                        rmask |= (sv >= 0 ? 1u : 0u) << r;
+                    }
+                }
+                const uint32_t o = (uint32_t)i_c0 >> 2;
+                dmask = half ? (rmask >> 2) : rmask;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t ri = (half ? rowidx[2 + h] : rowidx[h]) + o;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) dst[4 * h + g] = __ldg(i_x4 + ri + 4 * g);
+                }
+                if (!half) return;
+                if (--i_left == 0) { i_pending = true; return; }
+                i_c0 += kGroups * kKB;
+                while (i_c0 >= C) { i_c0 -= C; ++i_slot; }
+            };
+            auto consume_s = [&](const float4* cur, uint32_t cmask, bool cvalid, const int half) -> bool {
+                if (!cvalid || !c_valid) return false;
+                if (half == 0) {
+                    if (lane == 0) mbar_wait(bar_aempty + 8 * c_stage, c_par);
+                    __syncwarp();
+                    tc_fence_after();
+                }
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const bool ok = (cmask >> h) & 1u;   // absent neighbour / row beyond the tile -> zeros
+                        const float4 v = cur[4 * h + g];
+                        hi[4 * g + 2 * h] = ok ? __float_as_uint(v.x) : 0u;
+                        hi[4 * g + 2 * h + 1] = ok ? __float_as_uint(v.y) : 0u;
+                        lo[4 * g + 2 * h] = ok ? __float_as_uint(v.z) : 0u;
+                        lo[4 * g + 2 * h + 1] = ok ? __float_as_uint(v.w) : 0u;
+                    }
+                }
+                const uint32_t ta = tmem_base + ((uint32_t)(wrow0 + 16 * half) << 16) + a_col0 + (uint32_t)c_stage * 64u;
+                tmem_st_16x256b_x4(ta, hi);
+                tmem_st_16x256b_x4(ta + 32u, lo);
+                if (half == 0) return true;
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_afull + 8 * c_stage);
+                c_stage += kGroups;
+                while (c_stage >= SA) { c_stage -= SA; c_par ^= 1u; }
+                if (--c_left == 0) consume_next_tile();
+                return true;
+            };
+            issue_next_tile();
+            consume_next_tile();
+            issue_s(sb3[0], sm3[0], sv3[0], 0);
+            issue_s(sb3[1], sm3[1], sv3[1], 1);
+            for (;;) {   // unit n is consumed while units n+1, n+2 are in flight; buffers and halves repeat every six units
+                issue_s(sb3[2], sm3[2], sv3[2], 0); if (!consume_s(sb3[0], sm3[0], sv3[0], 0)) break;
+                issue_s(sb3[0], sm3[0], sv3[0], 1); if (!consume_s(sb3[1], sm3[1], sv3[1], 1)) break;
+                issue_s(sb3[1], sm3[1], sv3[1], 0); if (!consume_s(sb3[2], sm3[2], sv3[2], 0)) break;
+                issue_s(sb3[2], sm3[2], sv3[2], 1); if (!consume_s(sb3[0], sm3[0], sv3[0], 1)) break;
+                issue_s(sb3[0], sm3[0], sv3[0], 0); if (!consume_s(sb3[1], sm3[1], sv3[1], 0)) break;
+                issue_s(sb3[1], sm3[1], sv3[1], 1); if (!consume_s(sb3[2], sm3[2], sv3[2], 1)) break;
+            }
+        } else {
         issue_next_tile();
         consume_next_tile();
         if (i_valid) issue(buf[0], bmask[0], 0);
@@ -388,6 +458,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             consume(buf[0], bmask[0], 0);
             if (i_valid) issue(buf[0], bmask[0], 0);
             consume(buf[1], bmask[1], 1);   // completes the k-block; moves the consume cursor on
+        }
         }
     } else if (warp < kWarpMma) {
         // ===================== epilogue warpgroup: TMEM -> registers -> global ==============================
@@ -812,7 +883,10 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
     p.stages_a = sa;
     const size_t b_stage = 2 * (size_t)n_tile * 128;
     static const int sb_cap = []() { const char* e = getenv("LTN_CONVB_SB"); return e && atoi(e) >= 2 ? atoi(e) : 4; }();
-    static const int epi = []() { const char* e = getenv("LTN_CONVB_EPI"); return e && atoi(e) == 4 ? 4 : 8; }();   // epilogue warps
+    // Epilogue warps: 8 for the dense layers (their tiles are epilogue-bound), 4 for the gathering layers on pre-staged
+    // operands: that role layout leaves the producers 168 registers, enough for the three-deep gather pipeline.
+    static const int epi_env = []() { const char* e = getenv("LTN_CONVB_EPI"); return e ? atoi(e) : 0; }();
+    const int epi = (epi_env == 4 || epi_env == 8) ? epi_env : (p.staged ? 4 : 8);
     static const int want_resident = []() { const char* e = getenv("LTN_CONVB_RESIDENT"); return e ? atoi(e) : 1; }();
     const size_t b_budget = (size_t)(226 - 36 - 4 * epi - 2) * 1024;   // 227 KB - static (~35 KB) - epilogue staging
     const int num_kb = p.S * C / kKB;
