@@ -402,6 +402,9 @@ def main():
     ap.add_argument("--streams", action="store_true", help="round-1 execution: one stream + one graph per window in flight "
                     "(MultiWindowRunner) instead of the lock-step group graph with batched tensor-core launches (LockstepRunner)")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="the K-step timed loop is repeated until it has run this long")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="after the timed regions, replay ONE more group between cudaProfilerStart/Stop: with `ncu --profile-from-start off` "
+                         "the launch list then holds exactly the steady-state kernels of one group (profiles/README.md)")
     ap.add_argument("--driver", default="mirror", choices=["mirror", "reference"],
                     help="reference: ALSO time the reference's own seq_lattice/models.py over the shims (tools/reference_driver.py)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
@@ -551,6 +554,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     clk = clocks.stop() if rank == 0 else None
+    if args.profile_range and rank == 0:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        run_group(0, lanes)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     h2d = sum(sum(p.numel() * 4 + v.numel() * 4 for p, v in w) for w in host) // nw
     d2h = int(labels.numel() * 8)
 

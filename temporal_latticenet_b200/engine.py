@@ -708,7 +708,8 @@ class LockstepRunner:
                     us = float(stamps[live, 1].max() - stamps[live, 0].min()) / 1e3
                     out.append({"frame": t, "C": C, "S": S, "F": F, "rows": rows, "tiles": tiles, "ctas": int(live.sum()), "us": us,
                                 "flop": 2.0 * rows * S * C * F,
-                                "cta_us_mean": float((stamps[live, 1] - stamps[live, 0]).mean()) / 1e3})
+                                "cta_us_mean": float((stamps[live, 1] - stamps[live, 0]).mean()) / 1e3,
+                                "t0_ns": int(stamps[live, 0].min()), "t1_ns": int(stamps[live, 1].max())})
         cur.wait_stream(self.main)
         return out
 
