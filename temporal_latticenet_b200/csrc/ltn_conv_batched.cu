@@ -32,6 +32,7 @@ constexpr int kWarpEpi0 = 8;          // warps 0..7: the two producer warpgroups
 constexpr int kMetaThreads = 64;
 constexpr int kMetaBufs = 3;          // neighbour-slice buffers: the gather's issue cursor runs up to two tiles ahead of its consume cursor
 constexpr int kNbrPerMeta = (LTN_FEXT * kBlockM + kMetaThreads - 1) / kMetaThreads;
+constexpr int kColMax = 192;          // output channels per tile at most (two accumulators + the A ring in 512 columns of tensor memory)
 constexpr int kMaxSA = 4, kMaxSB = 9;   // weight ring: up to 9 stages so that a whole small weight tile (all k-blocks) can stay RESIDENT
 
 // Role layout and register budgets for EPI = 4 or 8 epilogue warps (one or two warpgroups; with two, they take alternate
@@ -71,6 +72,7 @@ struct BatchParams {
     int n_tile, ny;
     int stages_a, stages_b, acc_bufs, acc_stride;
     int staged;                       // x[] hold PRE-STAGED operands (k_stage_a): per 4 channels one 16-byte quad {hi01, hi23, lo01, lo23}
+    int res_async;                    // residual rows of the NEXT 32-column chunk prefetched with cp.async (4 epilogue warps, pre-staged operands)
     int resident;                     // stages_b == number of k-blocks: a channel tile's weights are loaded once per CTA and kept across its row tiles
     float a_mul, out_mul;
     int debug;                        // timing experiments only (LTN_CONVB_DEBUG): 1 no gather loads, 2 no staging, 4 no MMA issue, 8 no epilogue work
@@ -102,6 +104,16 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     using R = Roles<kEpiWarps>;
     constexpr int kThreadsB = R::kThreads, kWarpMma = R::kWarpMma, kWarpTma = R::kWarpTma, kWarpMeta0 = R::kWarpMeta0;
     constexpr int kRegsProducer = R::kRegsProducer, kRegsEpilogue = R::kRegsEpilogue, kRegsAux = R::kRegsAux;
+    // The role layout fixes the operand form: 4 epilogue warps <=> pre-staged operands (the gathering layers), 8 <=> fp32 rows
+    // converted in the gather loop (the dense layers).  Each instantiation carries ONE producer pipeline: the kernel's
+    // instruction footprint is what its 20 warps in five roles share one instruction cache for (ncu: "no instruction" was
+    // the top stall reason with both pipelines and the timing switches compiled in).
+    constexpr bool kStaged = kEpiWarps == 4;
+#ifdef LTN_CONVB_DEBUG_BUILD
+    const int dbg = p.debug;
+#else
+    constexpr int dbg = 0;
+#endif
     extern __shared__ uint8_t smem_raw[];
     // barriers: a_full[4] a_empty[4] b_full[4] b_empty[4] acc_full[2] acc_empty[2] meta_full[3] meta_empty[3]
     __shared__ __align__(8) uint64_t bars[2 * kMaxSA + 2 * kMaxSB + 4 + 2 * kMetaBufs];
@@ -110,14 +122,17 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     __shared__ int s_vq[kMaxBatch], s_vx[kMaxBatch];
     __shared__ __align__(16) float s_affine[kMaxBatch][512];  // per PROBLEM: folded GroupNorm scale [256] | shift [256], computed once per CTA
     __shared__ int s_nbr[kMetaBufs][LTN_FEXT * kBlockM];      // per meta buffer: [slot][tile row], -1 = absent
-    __shared__ float s_colsum[2][512];                        // per tile parity: column sums [256] | sums of squares [256]
+    // Output statistics, per tile parity and row quadrant: column sums [192] | sums of squares [192].  Every (quadrant, column)
+    // has exactly ONE writer per tile (the epilogue warp of that quadrant and 32-column chunk), so the slots are plainly
+    // stored, never cleared and never added to: shared-memory float atomics compile to a compare-and-swap loop, and eight of
+    // them per lane and chunk were a third of the epilogue's instructions (ncu source page, round 2).
+    __shared__ __align__(16) float s_colsum[2][4][2 * kColMax];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < p.nb) {
         s_vq[tid] = p.vq_dev[tid] ? min(p.Vq[tid], __ldg(p.vq_dev[tid])) : p.Vq[tid];
         s_vx[tid] = p.vx_dev[tid] ? min(p.Vx[tid], __ldg(p.vx_dev[tid])) : p.Vx[tid];
     }
-    for (int i = tid; i < 2 * 512; i += kThreadsB) (&s_colsum[0][0])[i] = 0.f;
     __syncthreads();
     if (p.has_gn) {
         // GroupNorm folded to scale = rstd*gamma, shift = beta - mean*scale (statistics over all Vx rows), x the fp16 pre-scale
@@ -303,7 +318,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             }
             const uint32_t o = (uint32_t)i_c0 >> 2;
             dmask = half ? (rmask >> 2) : rmask;
-            if (!(p.debug & 1)) {
+            if (!(dbg & 1)) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t ri = (half ? rowidx[2 + h] : rowidx[h]) + o;
@@ -323,7 +338,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 tc_fence_after();
             }
             uint32_t hi[16], lo[16];
-            if (!(p.debug & 2)) {
+            if (!(dbg & 2)) {
             {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -365,7 +380,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             c_c0 += kGroups * kKB;
             while (c_c0 >= C) c_c0 -= C;
         };
-        if (p.staged) {
+        if constexpr (kStaged) {
             // ---- pre-staged operands (k_stage_a): the gather only moves 16-byte quads, so what bounds it is the number of
             // loads in flight.  THREE register buffers: the loads run two units (one k-block) ahead of the tensor-memory
             // stores.  The issue cursor changes tile LAZILY (at its next first-half issue), so that it never waits for a
@@ -470,6 +485,34 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         float* stage = reinterpret_cast<float*>(smem_epi + (warp - kWarpEpi0) * 4096);
         const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
         const float out_mul = p.out_mul;
+        // Residual prefetch (res_async): a synchronous __ldg per row in the store loop made the residual layers 1.5x slower
+        // than their twins without one (64 -> 64 on 56k rows: 39 against 26 us; 192 -> 192 on 93k rows: 215 against 144 us).
+        // The residual quad a lane adds to row r = 4 * i8 + sub, columns 4 * chunk .. + 3 is fetched by THAT lane one chunk
+        // ahead with cp.async (also across a tile boundary, i.e. under the wait for the next accumulator) into one of two
+        // 4 KB buffers per warp: the first is the folded-GroupNorm table, unused on pre-staged operands, the second follows
+        // the transpose blocks in dynamic shared memory.
+        const bool ra = p.res_async != 0;
+        const uint8_t* rbuf0 = reinterpret_cast<const uint8_t*>(&s_affine[0][0]) + ((warp - kWarpEpi0) & 3) * 4096 + lane * 16;
+        const uint8_t* rbuf1 = smem_epi + kEpiWarps * 4096 + ((warp - kWarpEpi0) & 3) * 4096 + lane * 16;
+        int rq = 0;
+        auto res_issue = [&](const Tile& tt, const int cb, const int q) {
+            const float* res = p.res[tt.b];
+            if (res && 4 * chunk < tt.N - cb) {
+                const int vq = s_vq[tt.b];
+                const float* src = res + (size_t)(tt.row0 + qd * 32 + sub) * p.F + tt.n0 + cb + 4 * chunk;
+                const uint32_t dst = smem_u32(q ? rbuf1 : rbuf0);
+#pragma unroll
+                for (int i8 = 0; i8 < 8; ++i8)
+                    if (tt.row0 + qd * 32 + i8 * 4 + sub < vq)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i8 * 512u), "l"(src + (size_t)i8 * 4 * p.F) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (ra) {
+            Tile t0;
+            if (tile_at(0, t0) && eh * 32 < t0.N) res_issue(t0, eh * 32, 0);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         for (int it = 0;; ++it) {
             Tile t;
             if (!tile_at(it, t)) break;
@@ -481,19 +524,33 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             const int Vq = s_vq[t.b];
             float* out = p.out[t.b];
             const float* res = p.res[t.b];
-            float* colsum = s_colsum[it & 1];
-            for (int cb = eh * 32; cb < t.N && !(p.debug & 8); cb += 32 * (kEpiWarps / 4)) {
+            float* colsum = s_colsum[it & 1][qd];
+            for (int cb = eh * 32; cb < t.N && !(dbg & 8); cb += 32 * (kEpiWarps / 4)) {
+                const bool col_ok = 4 * chunk < t.N - cb;
+                const int col = t.n0 + cb + 4 * chunk;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                if (ra) {   // the next chunk's residual rows (this tile's, or the first chunk of the next tile) go on their way now
+                    int ncb = cb + 32 * (kEpiWarps / 4);
+                    Tile tn = t;
+                    bool more = true;
+                    if (ncb >= t.N) {
+                        ncb = eh * 32;
+                        more = tile_at(it + 1, tn) && ncb < tn.N;
+                    }
+                    if (more) res_issue(tn, ncb, rq ^ 1);
+                    else asm volatile("cp.async.commit_group;" ::: "memory");
+                }
                 float acc[32];
                 tmem_ld32(t_lane + (uint32_t)(a * p.acc_stride + cb), acc);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
                         make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                if (ra) asm volatile("cp.async.wait_group 1;" ::: "memory");   // all but the group just committed: this chunk's rows are in
                 __syncwarp();
-                const bool col_ok = 4 * chunk < t.N - cb;
-                const int col = t.n0 + cb + 4 * chunk;
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                const uint8_t* rcur = rq ? rbuf1 : rbuf0;
+                rq ^= ra ? 1 : 0;
                 float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq2 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int i8 = 0; i8 < 8; ++i8) {
@@ -504,7 +561,8 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
                     if (v < Vq && col_ok) {
                         if (res) {
-                            const float4 rr = __ldg(reinterpret_cast<const float4*>(res + (size_t)v * p.F + col));
+                            const float4 rr = ra ? *reinterpret_cast<const float4*>(rcur + i8 * 512)
+                                                 : __ldg(reinterpret_cast<const float4*>(res + (size_t)v * p.F + col));
                             o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
                         }
                         *reinterpret_cast<float4*>(out + (size_t)v * p.ldo + col) = o;
@@ -522,9 +580,8 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                         cq2.z += __shfl_xor_sync(0xffffffffu, cq2.z, o); cq2.w += __shfl_xor_sync(0xffffffffu, cq2.w, o);
                     }
                     if (sub == 0 && col_ok) {
-                        float* sc = colsum + cb + 4 * chunk;
-                        atomicAdd(sc, cs.x); atomicAdd(sc + 1, cs.y); atomicAdd(sc + 2, cs.z); atomicAdd(sc + 3, cs.w);
-                        atomicAdd(sc + 256, cq2.x); atomicAdd(sc + 257, cq2.y); atomicAdd(sc + 258, cq2.z); atomicAdd(sc + 259, cq2.w);
+                        *reinterpret_cast<float4*>(colsum + cb + 4 * chunk) = cs;
+                        *reinterpret_cast<float4*>(colsum + kColMax + cb + 4 * chunk) = cq2;
                     }
                 }
             }
@@ -534,16 +591,19 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             if (lane == 0) mbar_arrive(bar_accempty + 8 * a);
             if (warp == kWarpEpi0 && lane == 0) detail_stamp(p.detail, it, 7);
             if (p.has_sums) {
-                // per-tile column sums -> group sums -> one double atomic per group; the buffer of this tile parity is
-                // cleared here and next used two tiles later, after the next tile's barrier
+                // per-tile column sums of the four row quadrants -> group sums -> one double atomic per group; the slots of this
+                // tile parity are next written two tiles later, i.e. after the next tile's barrier
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                 double* osums = p.out_sums[t.b];
                 const int g0 = t.n0 / p.out_cpg, g1 = (t.n0 + t.N) / p.out_cpg;   // n_tile is a multiple of out_cpg
+                const float* all = s_colsum[it & 1][0];
                 for (int g = g0 + et; g < g1; g += 32 * kEpiWarps) {
                     float sa = 0.f, sb = 0.f;
                     for (int c = g * p.out_cpg - t.n0; c < (g + 1) * p.out_cpg - t.n0; ++c) {
-                        sa += colsum[c]; sb += colsum[256 + c];
-                        colsum[c] = 0.f; colsum[256 + c] = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            sa += all[q * 2 * kColMax + c]; sb += all[q * 2 * kColMax + kColMax + c];
+                        }
                     }
                     if (osums) {
                         atomicAdd(osums + 2 * g, (double)sa);
@@ -552,6 +612,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 }
             }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));
         if (warp == kWarpMma) {
@@ -579,7 +640,7 @@ k_conv_tc_batched(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                         const uint32_t bb = smem_u32(smem + (size_t)sb * b_stage);
                         const uint64_t b_hi = make_desc(bb), b_lo = make_desc(bb + b_bytes);
                         const uint32_t ta = tmem_base + a_col0 + (uint32_t)sa * 64u;
-                        if (!(p.debug & 4)) {
+                        if (!(dbg & 4)) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t adv = (uint64_t)((k * 32) >> 4);
@@ -862,7 +923,7 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
     p.trace = (g_trace_b && g_trace_next < g_trace_slots) ? g_trace_b + (size_t)kTraceStride * g_trace_next++ : nullptr;
     // Output channels per tile: at most 192, so that TWO accumulators and an A ring of >= 2 stages fit the 512 columns of
     // tensor memory; fewer when the tile list would leave SMs idle (small levels).
-    static const int n_cap = []() { const char* e = getenv("LTN_CONVB_NCAP"); return e && atoi(e) >= 16 ? atoi(e) : 192; }();
+    static const int n_cap = []() { const char* e = getenv("LTN_CONVB_NCAP"); return e && atoi(e) >= 16 && atoi(e) <= kColMax ? atoi(e) : kColMax; }();
     const int unit = has_sums ? lcm16(p.out_cpg) : 16;
     int ny = (F + n_cap - 1) / n_cap;
     while (row_tiles * (ny + 1) <= 148 && (F / (ny + 1)) >= 32) ++ny;
@@ -886,9 +947,15 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
     // Epilogue warps: 8 for the dense layers (their tiles are epilogue-bound), 4 for the gathering layers on pre-staged
     // operands: that role layout leaves the producers 168 registers, enough for the three-deep gather pipeline.
     static const int epi_env = []() { const char* e = getenv("LTN_CONVB_EPI"); return e ? atoi(e) : 0; }();
-    const int epi = (epi_env == 4 || epi_env == 8) ? epi_env : (p.staged ? 4 : 8);
+    (void)epi_env;
+    const int epi = p.staged ? 4 : 8;   // the role layout IS the operand form (see the kernel)
     static const int want_resident = []() { const char* e = getenv("LTN_CONVB_RESIDENT"); return e ? atoi(e) : 1; }();
-    const size_t b_budget = (size_t)(226 - 36 - 4 * epi - 2) * 1024;   // 227 KB - static (~35 KB) - epilogue staging
+    bool any_res = false;
+    for (int b = 0; b < live; ++b) any_res = any_res || p.res[b] != nullptr;
+    static const int want_res_async = []() { const char* e = getenv("LTN_CONVB_RESASYNC"); return e ? atoi(e) : 1; }();
+    p.res_async = (want_res_async && any_res && p.staged && epi == 4) ? 1 : 0;
+    const int res_kb = p.res_async ? 16 : 0;   // the second residual buffer of each epilogue warp
+    const size_t b_budget = (size_t)(226 - 44 - 4 * epi - res_kb - 2) * 1024;   // 227 KB - static (~43 KB) - epilogue staging
     const int num_kb = p.S * C / kKB;
     int sb = (int)(b_budget / b_stage);
     // Weights RESIDENT: when all k-blocks of a channel tile fit the ring (every dense layer, the 64 -> 64 convolutions), the
@@ -904,7 +971,7 @@ int ltn_conv_tc_f16_batched(int nb, const float* const* x, const int* Vx, const 
         if (sb < 2) return -3;
     }
     p.stages_b = sb;
-    const size_t smem = (size_t)sb * b_stage + (size_t)epi * 4096 + 1024;
+    const size_t smem = (size_t)sb * b_stage + (size_t)epi * 4096 + (size_t)res_kb * 1024 + 1024;
     alignas(64) CUtensorMap map_hi, map_lo;
     int rc = make_weight_map(&map_hi, wt_hi, F, p.S * C, n_tile, true);
     if (rc) return rc;
