@@ -96,6 +96,15 @@ int ltn_slice_classify(const float* vals, int V, const int* v_dev, int C, const 
 int ltn_slice_classify_bwd(const float* grad_logit, const float* vals, int V, int C, const int* idx, const float* w,
                            const float* dw, int N, const float* Wc, int K, float* grad_vals, float* grad_dw,
                            void* stream);
+/* The per-point tail of SliceFastCUDALatticeModule (models.py:232,465) and the model's LogSoftmax (models.py:251,470) in two
+ * kernels, inference: gather [N,4*9] of the bottleneck values bott [V,8] -> minus gamma*max-over-simplex + beta -> Linear
+ * 36->36 (W1) -> GroupNorm(18 groups, statistics over all points; sums [18,2] double scratch) + ReLU -> Linear 36->4 (W2, b2)
+ * = delta weights -> logits [N,K] = cls_bias + sum_r (w + dw) * scores[idx] (scores [V, ld_scores]: the vertices' class scores,
+ * K <= 32) -> logsm [N,K] = log_softmax.  no_deform = experiment "slice_no_deform" (delta weights ignored).  logits nullable. */
+int ltn_slice_head(const float* bott, int V, const int* v_dev, const float* scores, int ld_scores, const int* idx, const float* w,
+                   int N, const int* n_dev, const float* gamma, const float* beta, const float* W1, const float* gn_w,
+                   const float* gn_b, float gn_eps, const float* W2, const float* b2, const float* cls_bias, int K, int no_deform,
+                   double* sums, float* logits, float* logsm, void* stream);
 
 /* ---- segmented reductions, normalisation ------------------------------------------------------ */
 

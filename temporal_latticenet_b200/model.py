@@ -273,4 +273,5 @@ class LatticeNetSeq(torch.nn.Module):
 
         sv = self.slice_fast_cuda(lv, ls, positions, indices, weights)
         self.first_sequence = False
-        return self.logsoftmax(sv), sv, ls
+        logsm = getattr(sv, "_ltn_logsoftmax", None)   # the fused slice head (csrc/ltn_slice_head.cu) already took it
+        return (logsm if logsm is not None else self.logsoftmax(sv)), sv, ls

@@ -10,6 +10,7 @@ import math
 
 import torch
 
+from . import _lib
 from . import funcs as F_
 from . import ops
 from .funcs import *  # noqa: F401,F403  (the reference expects the Functions in this namespace too)
@@ -338,8 +339,32 @@ class SliceFastCUDALatticeModule(torch.nn.Module):
         for i in range(2):
             b, lsb = self.stepdown[i](b, lsb)
         b, lsb = self.bottleneck(b, lsb)
-        g = F_.GatherLattice.apply(b, lsb, positions, indices, weights)
+        W, cb = self.linear_clasify.weight, self.linear_clasify.bias
         N = positions.shape[0]
+        if (ops.no_grad_path(lv, b, W, self.linear_pre_deltaW.weight) and lv.shape[1] % 32 == 0 and lv.shape[0] > 0 and N > 0
+                and b.shape[1] == 8 and self.nr_classes <= 32 and self.gn_middle.gn.weight is not None):
+            # inference: classify the VERTICES once (slicing is linear: a [V,C] x [C,classes] tensor-core GEMM, classes padded to
+            # a multiple of 8), then ONE pair of kernels does everything per point -- gather, max over the simplex, both
+            # small linears with the GroupNorm between them, the slice of the class scores with the deformed weights, bias and
+            # the model's log-softmax (csrc/ltn_slice_head.cu)
+            kp = (self.nr_classes + 7) // 8 * 8
+            ls.set_values(lv)
+            scores = ops.conv_tc(lv, None, ops.k_major_padded(W, kp))
+            logits = torch.empty(N, self.nr_classes, dtype=torch.float32, device=lv.device)
+            logsm = torch.empty_like(logits)
+            sums = torch.empty(18, 2, dtype=torch.float64, device=lv.device)
+            p = _lib.ptr
+            rc = _lib.load().ltn_slice_head(p(b.contiguous()), b.shape[0], _lib.rows_dev(b.shape[0]), p(scores), scores.stride(0),
+                                            p(indices), p(weights), N, _lib.rows_dev(N), p(self.gamma.detach()), p(self.beta.detach()),
+                                            p(self.linear_pre_deltaW.weight.detach()), p(self.gn_middle.gn.weight.detach()),
+                                            p(self.gn_middle.gn.bias.detach()), float(self.gn_middle.gn.eps),
+                                            p(self.linear_deltaW.weight.detach()), p(self.linear_deltaW.bias.detach()),
+                                            None if cb is None else p(cb.detach()), self.nr_classes,
+                                            1 if self.experiment == "slice_no_deform" else 0, p(sums), p(logits), p(logsm), _lib.stream())
+            _lib.check(rc, "ltn_slice_head")
+            logits._ltn_logsoftmax = logsm   # LatticeNetSeq.forward returns it instead of running LogSoftmax again
+            return logits
+        g = F_.GatherLattice.apply(b, lsb, positions, indices, weights)
         g3 = g.view(N, 4, self.bottleneck_size + 1)
         mx = g3.max(1, keepdim=True)[0]
         g = (g3 - (self.gamma * mx + self.beta)).reshape(N, -1)

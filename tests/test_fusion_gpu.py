@@ -283,3 +283,52 @@ def test_group_norm_backward_kernel_matches_torch_autograd(C, relu):
     for got, want in ((xa.grad, xd.grad), (ga.grad, gd.grad), (ba.grad, bd.grad)):
         scale = float(want.abs().max()) + 1e-12
         assert float((got.double() - want).abs().max()) / scale < 1e-4
+
+
+@pytest.mark.parametrize("no_deform", [0, 1])
+def test_slice_head_matches_float64(dev, no_deform):
+    """csrc/ltn_slice_head.cu (the per-point tail of SliceFastCUDALatticeModule, models.py:232,465, fused into two kernels)
+    against the same recipe spelled out in float64 torch: gather -> minus gamma*max+beta -> Linear -> GroupNorm(18) + ReLU ->
+    Linear = delta weights -> slice of the class scores -> bias -> log-softmax.  Absent vertices (id -1), a device-side point
+    count below the capacity (static-capacity mode) and K = 26 of 32 score columns are all exercised.  Tolerance 2e-5 of
+    abs-max (36-term fp32 dot products; the GroupNorm statistics are double precision in both)."""
+    from temporal_latticenet_b200 import _lib
+    g = torch.Generator().manual_seed(5 + no_deform)
+    cap, N, V, K = 6000, 5317, 800, 26
+    bott = torch.randn(V, 8, generator=g)
+    scores = torch.randn(V, 32, generator=g)
+    idx = torch.randint(0, V, (4 * cap,), generator=g).int()
+    idx[torch.rand(4 * cap, generator=g) < 0.05] = -1
+    w = torch.rand(4 * cap, generator=g)
+    gamma, beta = torch.rand(9, generator=g) + 0.5, 0.1 * torch.randn(9, generator=g)
+    W1, W2, b2 = torch.randn(36, 36, generator=g) / 6, 0.1 * torch.randn(4, 36, generator=g), 0.1 * torch.randn(4, generator=g)
+    gw, gb, cb = torch.rand(36, generator=g) + 0.5, 0.1 * torch.randn(36, generator=g), torch.randn(K, generator=g)
+
+    d = lambda t: t.to(dev).contiguous()   # noqa: E731
+    n_dev = torch.tensor([N], dtype=torch.int32, device=dev)
+    logits = torch.full((cap, K), float("nan"), device=dev)
+    logsm = torch.full((cap, K), float("nan"), device=dev)
+    sums = torch.empty(18, 2, dtype=torch.float64, device=dev)
+    t = [d(x) for x in (bott, scores, idx, w, gamma, beta, W1, gw, gb, W2, b2, cb)]
+    p = _lib.ptr
+    rc = _lib.load().ltn_slice_head(p(t[0]), V, None, p(t[1]), 32, p(t[2]), p(t[3]), cap, p(n_dev), p(t[4]), p(t[5]), p(t[6]), p(t[7]),
+                                    p(t[8]), 1e-5, p(t[9]), p(t[10]), p(t[11]), K, no_deform, p(sums), p(logits), p(logsm), _lib.stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+
+    i64, ok = idx[: 4 * N].long().clamp(min=0), (idx[: 4 * N] >= 0)
+    wv = torch.where(ok, w[: 4 * N], torch.zeros(())).double()
+    rows = torch.cat([wv[:, None] * bott.double()[i64], wv[:, None]], 1).view(N, 4, 9)
+    mx = rows.max(1, keepdim=True)[0]
+    gg = (rows - (gamma.double() * mx + beta.double())).reshape(N, 36)
+    h = gg @ W1.double().t()
+    y = torch.relu(torch.nn.functional.group_norm(h.t().unsqueeze(0), 18, gw.double(), gb.double(), 1e-5).squeeze(0).t())
+    dw = y @ W2.double().t() + b2.double()
+    ww = w[: 4 * N].double() + (0.0 if no_deform else 1.0) * dw.reshape(-1)
+    ww = torch.where(ok, ww, torch.zeros((), dtype=torch.float64))
+    want = (ww[:, None] * scores.double()[i64][:, :K]).view(N, 4, K).sum(1) + cb.double()
+    got = logits[:N].cpu().double()
+    assert float((got - want).abs().max()) < 2e-5 * float(want.abs().max())
+    want_ls = torch.log_softmax(want, 1)
+    assert float((logsm[:N].cpu().double() - want_ls).abs().max()) < 2e-5 * float(want_ls.abs().max())
+    assert torch.isnan(logits[N:]).all() and torch.isnan(logsm[N:]).all()   # rows beyond the live count stay untouched
