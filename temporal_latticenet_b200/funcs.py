@@ -4,6 +4,8 @@
 Forward and backward both run hand-written sm_100a kernels; dense contractions go through
 `ops.matmul` (fp32).  No CPU fallback.
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -41,6 +43,7 @@ def row2im_raw(grad_rows, nbr_t, nr_vals, C):
     return out
 
 
+_FLIP_DEV = {}
 _FLIP = (1, 0, 3, 2, 5, 4, 7, 6, 8)   # slot pairs swap under transposition (2a <-> 2a+1), the centre stays
 
 
@@ -48,7 +51,12 @@ def transposed_weight(weight, C, F):
     """[9C, F] slot-major conv weight -> the weight of the TRANSPOSED convolution, [9F, C]:
     Wt[s'*F + f, c] = W[flip(s')*C + c, f]; cached per parameter version (ops.k_major on the result)."""
     def make():
-        wt = weight.detach().view(FEXT, C, F)[list(_FLIP)].transpose(1, 2).contiguous().view(FEXT * F, C)
+        # the slot permutation as a cached DEVICE index: indexing with a Python list builds and uploads an index tensor per
+        # call (0.2 ms of host time each, 60 convolutions per training step: 13 ms of a 59 ms step in the host profile)
+        flip = _FLIP_DEV.get(weight.device)
+        if flip is None:
+            flip = _FLIP_DEV[weight.device] = torch.tensor(_FLIP, dtype=torch.long, device=weight.device)
+        wt = weight.detach().view(FEXT, C, F).index_select(0, flip).transpose(1, 2).contiguous().view(FEXT * F, C)
         return ops.SplitWeight(wt.float(), False)
     return ops._cached_split(weight, (id(weight), "transposed"), make)
 
@@ -89,6 +97,117 @@ class _GatherConv(Function):
             rows = im2row_raw(values, nbr)
             gw = ops.matmul(rows.t(), grad_out)
         return gv, gw, None, None
+
+
+class _FusedConv(Function):
+    """Training-time form of a whole layer  y = conv(act(x)) (+ bias) (+ res),  act = relu(GroupNorm(x)) or the identity
+    (GnReluConv / GnReluCoarsen / GnReluFinefy / GnRelu1x1 / ConvLatticeModule, lattice_modules.py:75-140,436-440,573).
+
+    forward  = the SAME fused tensor-core kernel inference uses (GroupNorm folded into the gathered operand, bias, residual
+               and the output's GroupNorm statistics in the epilogue; tf32 hi/lo operands, three passes, fp32 results): no
+               [V, 9C] buffer, no separate normalisation pass.  Round 1 ran im2row + an fp32 SIMT GEMM + two GroupNorm
+               kernels here.
+    backward = act recomputed in one pass (k_gn_apply) instead of kept alive; d act = the forward kernel over the
+               opposite-direction neighbour table with the transposed weight (`ltn_conv_bwd_data` of SURVEY.md 8b);
+               d W = gathered-act^T . dy; then the GroupNorm + ReLU backward kernel (k_gn_bwd) gives d x, d gamma, d beta.
+    `linear`: weight is an nn.Linear weight [F, C] and there is no neighbour table (S = 1)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, res, gamma, beta, nbr, nbr_t, cfg):
+        linear, groups, eps, sums_in = cfg
+        x = _f32c(x)
+        has_gn = gamma is not None
+        F = weight.shape[0] if linear else weight.shape[1]
+        sums = None
+        if has_gn:
+            sums = sums_in if sums_in is not None else ops.gn_sums(x, groups)
+            if sums._base is not None:
+                sums = sums.clone()   # a slot of the per-frame arena: the next frame reuses it, backward comes after all frames
+        wt = ops.k_major(weight, transposed=True) if linear else ops.k_major(weight)
+        # own storage, not the per-frame arena: back-propagation through time reads these after the later frames have run
+        out_sums = torch.zeros(ops.gn_groups(F), 2, dtype=torch.float64, device=x.device)
+        out = ops.conv_tc(x, nbr, wt, gn=(sums, gamma.detach(), beta.detach(), eps) if has_gn else None, relu=has_gn,
+                          bias=None if bias is None else bias.detach(), res=None if res is None else _f32c(res.detach()),
+                          out_sums=out_sums, operands="tf32")
+        ctx.save_for_backward(x, weight, gamma, beta, nbr, nbr_t, sums)
+        ctx.cfg = (linear, groups, eps, has_gn)
+        ctx.mark_non_differentiable(out_sums)
+        return out, out_sums
+
+    @staticmethod
+    def backward(ctx, gy, _unused):
+        x, weight, gamma, beta, nbr, nbr_t, sums = ctx.saved_tensors
+        linear, groups, eps, has_gn = ctx.cfg
+        need = ctx.needs_input_grad
+        gy = _f32c(gy)
+        V, C = x.shape
+        F = weight.shape[0] if linear else weight.shape[1]
+        lib, p = _lib.load(), _lib.ptr
+        g_x = g_w = g_b = g_res = g_gamma = g_beta = None
+        if need[3]:
+            g_res = gy
+        if need[2]:
+            g_b = gy.sum(0)
+        act = x
+        if has_gn:
+            act = torch.empty_like(x)
+            _lib.check(lib.ltn_gn_apply(p(x), V, None, C, groups, p(sums), p(gamma), p(beta), float(eps), 1, p(act), _lib.stream()),
+                       "ltn_gn_apply")
+        if need[1]:
+            if linear:
+                g_w = ops.matmul(gy.t(), act)                      # [F, C]
+            else:
+                g_w = ops.matmul(im2row_raw(act, nbr).t(), gy)     # [9C, F]
+        if need[0] or (has_gn and (need[4] or need[5])):
+            if linear:
+                if ops.conv_tc_supported(F, C, False):
+                    wt_t = ops._cached_split(weight, (id(weight), "linear_t"),
+                                             lambda: ops.SplitWeight(weight.detach().t().contiguous().float(), True))
+                    d_act = ops.conv_tc(gy, None, wt_t, operands="tf32")
+                else:
+                    d_act = ops.matmul(gy, weight)
+            elif ops.conv_tc_supported(F, C, False) and gy.shape[0] > 0:
+                vu = min(V, nbr_t.shape[0])
+                d_act = torch.zeros(V, C, dtype=torch.float32, device=gy.device) if vu < V else \
+                    torch.empty(V, C, dtype=torch.float32, device=gy.device)
+                ops.conv_tc(gy, nbr_t, transposed_weight(weight, C, F), nr_rows=vu, out=d_act, operands="tf32")
+            else:
+                d_act = row2im_raw(ops.matmul(gy, weight.t()), nbr_t, V, C)
+            if has_gn:
+                chan = torch.empty(C, 2, dtype=torch.float64, device=x.device)
+                g_x = torch.empty_like(x)
+                _lib.check(lib.ltn_gn_bwd(p(x), p(d_act), p(act), V, C, groups, p(sums), p(gamma), float(eps), p(chan), p(g_x),
+                                          _lib.stream()), "ltn_gn_bwd")
+                chan = chan.float()
+                g_gamma, g_beta = chan[:, 1].contiguous(), chan[:, 0].contiguous()
+            else:
+                g_x = d_act
+        return g_x, g_w, g_b, g_res, g_gamma, g_beta, None, None, None
+
+
+def fused_conv_train(x, weight, bias, res, norm, nbr, nbr_t_fn, linear=False):
+    """the layer through _FusedConv; `norm` = GroupNormLatticeModule (GroupNorm + ReLU folded in) or None; the output's
+    GroupNorm statistics travel with it to the next layer (ops.sums_of), as on the inference path"""
+    gamma = beta = sums = None
+    groups, eps = 0, 0.0
+    if norm is not None:
+        gamma, beta, groups, eps = norm.gn.weight, norm.gn.bias, norm.groups, norm.gn.eps
+        s = getattr(x, "_ltn_gn_sums", None)
+        if s is not None and s[0] == ops._FRAME["id"] and s[1].shape[0] == groups and os.environ.get("LTN_TRAIN_NOSUMS", "0") != "1":
+            sums = s[1]
+    nbr_t = None
+    if not linear:
+        nbr_t = nbr_t_fn() if x.requires_grad else nbr
+    out, out_sums = _FusedConv.apply(x, weight, bias, res, gamma, beta, nbr, nbr_t, (linear, groups, eps, sums))
+    out._ltn_gn_sums = (ops._FRAME["id"], out_sums)
+    return out
+
+
+def train_fusable(x, C, F, norm=None):
+    """grad mode, shapes the tensor-core kernel takes, GroupNorm with affine parameters (or none at all)"""
+    return (torch.is_grad_enabled() and x.is_cuda and x.shape[0] > 0 and ops.conv_tc_supported(C, F, norm is not None)
+            and (norm is None or norm.gn.weight is not None) and ops._FRAME["arena"] is not None
+            and os.environ.get("LTN_TRAIN_UNFUSED", "0") != "1")
 
 
 def gather_conv(values, weight, nbr, nbr_t_fn):

@@ -1,5 +1,11 @@
 """Lovasz-softmax loss on log-probabilities (train_ln.py:119,214: `LovaszSoftmax(ignore_index)`
-applied to `pred_logsoftmax`).  Published algorithm: Berman, Triki, Blaschko, CVPR 2018."""
+applied to `pred_logsoftmax`).  Published algorithm: Berman, Triki, Blaschko, CVPR 2018.
+
+All classes at once in a [classes, points] layout: the sort and the two cumulative sums run along the CONTIGUOUS dimension
+(a cumsum down the rows of a [125k, 26] tensor is torch's outer-dimension scan: 21.7 ms each on B200, half of the whole
+training step in round 2's first profile), and nothing reads a value back to the host -- ignored points are kept as
+zero-error entries (they sort behind every real entry and contribute nothing) instead of being filtered into a tensor
+of data-dependent size, and the mean over the present classes is a masked sum."""
 import torch
 
 
@@ -9,24 +15,25 @@ class LovaszSoftmax(torch.nn.Module):
         self.ignore_index = ignore_index
 
     def forward(self, logsoftmax, target):
-        p = logsoftmax.exp()
-        if self.ignore_index is not None:
-            keep = target != self.ignore_index
-            p, target = p[keep], target[keep]
-        n, k = p.shape
+        p = logsoftmax.exp().t().contiguous()                               # [k, n]
+        k, n = p.shape
         if n == 0:
             return p.sum() * 0.0
-        fg = torch.nn.functional.one_hot(target, k).to(p.dtype)          # [n,k]
-        present = fg.sum(0) > 0
-        err = (fg - p).abs()
-        err_sorted, perm = torch.sort(err, 0, descending=True)           # all classes at once
-        fg_sorted = fg.gather(0, perm)
-        total = fg_sorted.sum(0, keepdim=True)
-        inter = total - fg_sorted.cumsum(0)
-        union = total + (1.0 - fg_sorted).cumsum(0)
+        fg = target.unsqueeze(0) == torch.arange(k, device=p.device).unsqueeze(1)
+        if self.ignore_index is not None:
+            valid = (target != self.ignore_index).unsqueeze(0)
+            fg = fg & valid
+            err = (fg.to(p.dtype) - p).abs() * valid.to(p.dtype)
+        else:
+            err = (fg.to(p.dtype) - p).abs()
+        fg = fg.to(p.dtype)
+        err_sorted, perm = torch.sort(err, 1, descending=True)
+        fg_sorted = fg.gather(1, perm)
+        total = fg_sorted.sum(1, keepdim=True)
+        inter = total - fg_sorted.cumsum(1)
+        union = total + (1.0 - fg_sorted).cumsum(1)
         jac = 1.0 - inter / union
-        jac = torch.cat([jac[:1], jac[1:] - jac[:-1]], 0)
-        per_class = (err_sorted * jac).sum(0)
-        if not bool(present.any()):
-            return p.sum() * 0.0
-        return per_class[present].mean()
+        jac = torch.cat([jac[:, :1], jac[:, 1:] - jac[:, :-1]], 1)
+        per_class = (err_sorted * jac).sum(1)
+        present = (total.squeeze(1) > 0).to(p.dtype)
+        return (per_class * present).sum() / present.sum().clamp(min=1.0)

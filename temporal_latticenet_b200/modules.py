@@ -111,6 +111,8 @@ class GnRelu1x1(torch.nn.Module):
             lv = ops.conv_tc(lv, None, ops.k_major(self.linear.weight, transposed=True), gn=self.norm.affine(lv), relu=True,
                              bias=None if self.linear.bias is None else self.linear.bias.detach(), res=res,
                              out_sums=ops.new_sums(self.out_channels, lv.device))
+        elif F_.train_fusable(lv, lv.shape[1], self.out_channels, self.norm):   # training: the same fused kernel under autograd
+            lv = F_.fused_conv_train(lv, self.linear.weight, self.linear.bias, res, self.norm, None, None, linear=True)
         else:
             lv, ls = self.norm(lv, ls, relu=True)
             lv = ops.linear(lv, self.linear.weight, self.linear.bias)
@@ -136,15 +138,18 @@ class ConvLatticeModule(torch.nn.Module):
                 b = 1.0 / math.sqrt(rows)
                 self.bias = torch.nn.Parameter(torch.empty(self.nr_filters, device=_dev()).uniform_(-b, b))
 
-    def forward(self, lv, ls, pre=None, res=None):
+    def forward(self, lv, ls, pre=None, res=None, norm=None):
         """pre = (sums, gamma, beta, eps): a GroupNorm+ReLU to fold into the gather (fused inference path only);
-        res: residual added in the epilogue."""
+        norm: the GroupNormLatticeModule to fold in on the TRAINING path (funcs._FusedConv); res: residual added in the epilogue."""
         ls.set_values(lv)
         self.create(lv, ls)
         if ops.no_grad_path(lv, self.weight) and ops.conv_tc_supported(lv.shape[1], self.nr_filters) and lv.shape[0] > 0:
             out = ops.conv_tc(lv, ls.neighbours(dilation=self.dilation), ops.k_major(self.weight),
                               gn=pre, relu=pre is not None, bias=None if self.bias is None else self.bias.detach(), res=res,
                               out_sums=ops.new_sums(self.nr_filters, lv.device))
+        elif norm is not None or (pre is None and F_.train_fusable(lv, lv.shape[1], self.nr_filters)):
+            nbr = ls.neighbours(dilation=self.dilation)   # training: the same fused kernel under autograd (funcs._FusedConv)
+            out = F_.fused_conv_train(lv, self.weight, self.bias, res, norm, nbr, lambda: nbr)
         else:
             if pre is not None:
                 raise RuntimeError("a folded GroupNorm needs the fused kernel")
@@ -162,7 +167,7 @@ class CoarsenLatticeModule(torch.nn.Module):
         super().__init__()
         self.nr_filters, self.weight = nr_filters, None
 
-    def forward(self, lv, ls, pre=None):
+    def forward(self, lv, ls, pre=None, norm=None):
         ls.set_values(lv)
         if self.weight is None:
             self.weight = _conv_weight(ls.get_filter_extent(1) * lv.shape[1], self.nr_filters)
@@ -170,6 +175,10 @@ class CoarsenLatticeModule(torch.nn.Module):
             coarse = ls.create_coarse_verts()
             out = ops.conv_tc(lv, coarse.neighbours(ls, mode=1), ops.k_major(self.weight),
                               gn=pre, relu=pre is not None, out_sums=ops.new_sums(self.nr_filters, lv.device))
+        elif norm is not None or (pre is None and F_.train_fusable(lv, lv.shape[1], self.nr_filters)):
+            coarse = ls.create_coarse_verts()
+            out = F_.fused_conv_train(lv, self.weight, None, None, norm, coarse.neighbours(ls, mode=1),
+                                      lambda: ls.neighbours(coarse, mode=2))
         else:
             if pre is not None:
                 raise RuntimeError("a folded GroupNorm needs the fused kernel")
@@ -183,7 +192,7 @@ class FinefyLatticeModule(torch.nn.Module):
         super().__init__()
         self.nr_filters, self.weight = nr_filters, None
 
-    def forward(self, lv_coarse, ls_coarse, ls_fine, pre=None):
+    def forward(self, lv_coarse, ls_coarse, ls_fine, pre=None, norm=None):
         ls_coarse.set_values(lv_coarse)
         if self.weight is None:
             self.weight = _conv_weight(ls_coarse.get_filter_extent(1) * lv_coarse.shape[1], self.nr_filters)
@@ -191,6 +200,9 @@ class FinefyLatticeModule(torch.nn.Module):
                 and lv_coarse.shape[0] > 0):
             out = ops.conv_tc(lv_coarse, ls_fine.neighbours(ls_coarse, mode=2), ops.k_major(self.weight),
                               gn=pre, relu=pre is not None)
+        elif norm is not None or (pre is None and F_.train_fusable(lv_coarse, lv_coarse.shape[1], self.nr_filters)):
+            out = F_.fused_conv_train(lv_coarse, self.weight, None, None, norm, ls_fine.neighbours(ls_coarse, mode=2),
+                                      lambda: ls_coarse.neighbours(ls_fine, mode=1))
         else:
             if pre is not None:
                 raise RuntimeError("a folded GroupNorm needs the fused kernel")
@@ -211,6 +223,8 @@ class GnReluConv(torch.nn.Module):
             self.norm = GroupNormLatticeModule(lv.shape[1])
         if self.norm.fusable(lv, self.conv.nr_filters) and (self.drop is None or not self.training):
             return self.conv(lv, ls, pre=self.norm.affine(lv), res=res)
+        if F_.train_fusable(lv, lv.shape[1], self.conv.nr_filters, self.norm) and (self.drop is None or not self.training):
+            return self.conv(lv, ls, res=res, norm=self.norm)
         lv, ls = self.norm(lv, ls, relu=True)
         if self.drop is not None:
             lv = self.drop(lv)
@@ -230,6 +244,8 @@ class GnReluCoarsen(torch.nn.Module):
             self.norm = GroupNormLatticeModule(lv.shape[1])
         if self.norm.fusable(lv, self.coarse.nr_filters):
             return self.coarse(lv, ls, pre=self.norm.affine(lv))
+        if F_.train_fusable(lv, lv.shape[1], self.coarse.nr_filters, self.norm):
+            return self.coarse(lv, ls, norm=self.norm)
         lv, ls = self.norm(lv, ls, relu=True)
         return self.coarse(lv, ls)
 
@@ -247,6 +263,8 @@ class GnReluFinefy(torch.nn.Module):
             self.norm = GroupNormLatticeModule(lv_coarse.shape[1])
         if self.norm.fusable(lv_coarse, self.fine.nr_filters):
             return self.fine(lv_coarse, ls_coarse, ls_fine, pre=self.norm.affine(lv_coarse))
+        if F_.train_fusable(lv_coarse, lv_coarse.shape[1], self.fine.nr_filters, self.norm):
+            return self.fine(lv_coarse, ls_coarse, ls_fine, norm=self.norm)
         lv_coarse, ls_coarse = self.norm(lv_coarse, ls_coarse, relu=True)
         return self.fine(lv_coarse, ls_coarse, ls_fine)
 

@@ -377,3 +377,62 @@ def test_batched_conv_device_side_counts_and_tiny_problems(dev, lattice):
     # problems smaller than one tile, and a group in which most CTAs have nothing to do
     _batched_vs_single(dev, ls, 150, (64, 64, 9), 3, folded=True, with_res=False, with_bias=False, with_sums=True, seed=9)
     _batched_vs_single(dev, ls, 40, (192, 192, 9), 2, folded=False, with_res=True, with_bias=True, with_sums=True, seed=10)
+
+
+@pytest.mark.parametrize("kind", ["conv_gn_res_bias", "conv_plain", "linear_gn_res_bias", "coarsen_gn"])
+def test_fused_training_layer_gradients_match_unfused(dev, lattice, kind):
+    """funcs._FusedConv (training: the fused tensor-core kernel under autograd; backward = act recompute + the forward kernel
+    over the transposed table + gathered-act^T . dy + the GroupNorm/ReLU backward kernel) against the UNFUSED autograd
+    composition (ops.group_norm -> funcs.gather_conv / torch linear -> + bias -> + res) on the same inputs: output and every
+    gradient (x, weight, bias, residual, gamma, beta) within 2e-4 of the abs-max (fp32 summation orders differ)."""
+    from temporal_latticenet_b200 import funcs, ops
+    from temporal_latticenet_b200.modules import GroupNormLatticeModule
+    ls, _ = lattice
+    g = torch.Generator().manual_seed(11)
+    V = ls.nr_lattice_vertices()
+    C, F = (128, 64) if kind != "linear_gn_res_bias" else (64, 256)
+    linear = kind.startswith("linear")
+    with_gn = "gn" in kind
+    with_rb = "res_bias" in kind
+    if kind == "coarsen_gn":
+        coarse = ls.create_coarse_verts()
+        nbr, nbr_t = coarse.neighbours(ls, mode=1), ls.neighbours(coarse, mode=2)
+    else:
+        nbr = nbr_t = ls.neighbours()
+    Vq = V if linear else nbr.shape[0]
+    ops.begin_frame(ls, dev)
+
+    def leaf(*shape, scale=1.0, shift=0.0):
+        return (torch.randn(*shape, generator=g) * scale + shift).to(dev).requires_grad_(True)
+    x0 = leaf(V, C, scale=2.0, shift=0.3)
+    w0 = leaf(F, C, scale=C ** -0.5) if linear else leaf(9 * C, F, scale=(9 * C) ** -0.5)
+    b0 = leaf(F) if with_rb else None
+    r0 = leaf(Vq, F) if with_rb else None
+    norm = GroupNormLatticeModule(C) if with_gn else None
+    if norm is not None:
+        with torch.no_grad():
+            norm.gn.weight.copy_(torch.rand(C, generator=g) + 0.5)
+            norm.gn.bias.copy_(torch.randn(C, generator=g) * 0.2)
+    gy = torch.randn(Vq, F, generator=g).to(dev)
+
+    def grads(out, leaves):
+        for t in leaves:
+            if t is not None and t.grad is not None:
+                t.grad = None
+        (out * gy).sum().backward()
+        return [None if t is None else t.grad.clone() for t in leaves]
+    leaves = [x0, w0, b0, r0] + ([norm.gn.weight, norm.gn.bias] if norm is not None else [])
+    fused = funcs.fused_conv_train(x0, w0, b0, r0, norm, None if linear else nbr, None if linear else (lambda: nbr_t), linear=linear)
+    gf = grads(fused, leaves)
+    a = ops.group_norm(x0, norm.gn.weight, norm.gn.bias, norm.groups, norm.gn.eps, True) if norm is not None else x0
+    plain = torch.nn.functional.linear(a, w0) if linear else funcs.gather_conv(a, w0, nbr, lambda: nbr_t)
+    if with_rb:
+        plain = plain + b0 + r0
+    gp = grads(plain, leaves)
+
+    def rel(u, v):
+        return float((u - v).abs().max()) / (float(v.abs().max()) + 1e-30)
+    assert rel(fused.detach(), plain.detach()) < 2e-4
+    for name, u, v in zip(("x", "weight", "bias", "res", "gamma", "beta"), gf, gp):
+        if v is not None:
+            assert rel(u, v) < 2e-4, (kind, name, rel(u, v))

@@ -112,11 +112,24 @@ def test_window_matches_reference_golden(name, tmp_path):
     assert np.array_equal(logits.argmax(1)[clear], g.argmax(1)[clear])
 
 
-def test_training_step_gradients_match_oracle_autograd(tmp_path):
+@pytest.mark.parametrize("path", ["unfused", "fused"])
+def test_training_step_gradients_match_oracle_autograd(tmp_path, path, monkeypatch):
     """BPTT through a 2-frame window (train_ln.py:163-233): every parameter gradient of the CUDA path
     (conv transpose-as-gather, slice_classify / gather backward kernels, scatter_max, GroupNorm) equals
     torch autograd over the oracle's unfused CPU graph with the same seeded weights, and one AdamW
-    step lowers the loss.  Tolerance: GRAD_TOL of each gradient's absolute maximum (fp32 accumulation order; the largest observed is printed)."""
+    step lowers the loss.
+
+    Two forms of the training graph, two stated tolerances (relative to each gradient tensor's absolute maximum; the largest
+    observed is printed):
+    * "unfused" (LTN_TRAIN_UNFUSED=1): every layer as separate GroupNorm / im2row / fp32 GEMM kernels -- GRAD_TOL (observed 3e-3);
+    * "fused" (default, funcs._FusedConv): every layer's forward AND its backward-data GEMM on the tensor cores (3-pass tf32
+      split).  Each layer is within 2e-4 of the unfused composition (tests/test_conv_tc_gpu.py::test_fused_training_layer_...),
+      i.e. within the convolution's stated bound 2e-5 * sum|a||w|, but a tensor-core accumulator truncates where an fp32 FMA
+      chain rounds, and through ~80 layers of back-propagation (2 frames) those per-layer differences add up in the gradients
+      whose terms cancel (GroupNorm biases, AFlow's two scalars).  Stated: every tensor within FUSED_GRAD_TOL of its abs-max
+      AND the whole flattened gradient within FUSED_GRAD_L2 in relative L2 norm (what an optimizer step sees)."""
+    FUSED_GRAD_TOL, FUSED_GRAD_L2 = 1e-1, 2e-2
+    monkeypatch.setenv("LTN_TRAIN_UNFUSED", "1" if path == "unfused" else "0")
     from oracle import window_oracle as WO
     from temporal_latticenet_b200.config import ConfigParser
     from temporal_latticenet_b200.lattice import Lattice, ModelParams
@@ -164,19 +177,25 @@ def test_training_step_gradients_match_oracle_autograd(tmp_path):
     oloss.backward()
     assert abs(float(loss0) - float(oloss)) < 1e-4 * abs(float(oloss))
     ograds = {k: p.grad for k, p in orc.model.named_parameters()}
-    bad, worst = [], 0.0
+    bad, worst, num, den = [], 0.0, 0.0, 0.0
+    tol = GRAD_TOL if path == "unfused" else FUSED_GRAD_TOL
     for k, p in model.named_parameters():
         if ".AFLOW.weight" in k:
             continue  # quirk Q4: created, never used
         og = ograds[k]
         assert p.grad is not None and og is not None, k
         scale = float(og.abs().max()) + 1e-12
-        err = float((p.grad.cpu() - og).abs().max()) / scale
+        diff = p.grad.cpu() - og
+        err = float(diff.abs().max()) / scale
+        num += float((diff.double() ** 2).sum())
+        den += float((og.double() ** 2).sum())
         worst = max(worst, err)
-        if err > GRAD_TOL:
+        if err > tol:
             bad.append((k, err))
-    print("largest gradient error / absmax over all parameters: %.2e" % worst)
+    l2 = (num / den) ** 0.5
+    print("%s: largest gradient error / absmax over all parameters: %.2e, relative L2 error of the whole gradient: %.2e" % (path, worst, l2))
     assert not bad, bad
+    assert l2 < (GRAD_TOL if path == "unfused" else FUSED_GRAD_L2), l2
     opt.step()
     with torch.no_grad():
         loss1 = window_loss()
