@@ -215,6 +215,10 @@ int ltn_pointnet_trace(long long* buf);
 /* GRUModule.forward pointwise stage (lattice_modules.py:58-63); rows >= Vh are the zero padding */
 int ltn_gru_pointwise(const float* gi, const float* gh, const float* h, const float* b_hh, int V, int Vh, const int* v_dev,
                       const int* vh_dev, int C, float* out, void* stream);
+/* the same stage, leaving the GroupNorm statistics of its output behind for the layer that normalises it next (sums
+ * [groups,2] double, zeroed by the caller): GnReluConv / GnReluCoarsen after a GRU fusion point, models.py:340-353,435 */
+int ltn_gru_pointwise_stats(const float* gi, const float* gh, const float* h, const float* b_hh, int V, int Vh, const int* v_dev,
+                            const int* vh_dev, int C, float* out, double* sums, int groups, void* stream);
 /* LSTMModule.forward pointwise stage with c_prev = 0 (lattice_modules.py:32-37) */
 int ltn_lstm_pointwise(const float* gi, const float* gh, const float* b_hh, int V, int Vh, const int* v_dev,
                        const int* vh_dev, int C, float* out, void* stream);

@@ -79,6 +79,59 @@ k_gru_pointwise4(const float4* __restrict__ gi, const float4* __restrict__ gh, c
     }
 }
 
+// k_gru_pointwise4 that ALSO leaves the GroupNorm statistics of its output behind ([G,2] double: per-group sum and sum of
+// squares), so the layer that normalises h' next does not read it once more (k_gn_stats).  The launch makes the grid's
+// thread count a multiple of C4, so a thread owns ONE channel quad for its whole grid-stride walk and keeps the eight
+// partial sums in registers; they meet per block in shared memory and leave as one double atomic per group and block.
+__global__ void __launch_bounds__(kThreads)
+k_gru_pointwise4_stats(const float4* __restrict__ gi, const float4* __restrict__ gh, const float4* __restrict__ h,
+                       const float4* __restrict__ b_hh, int V, int Vh, const int* __restrict__ v_dev,
+                       const int* __restrict__ vh_dev, int C4, float4* __restrict__ out, double* __restrict__ sums, int cpg) {
+    __shared__ float s_acc[2 * 256];   // per channel: sum | sum of squares (C <= 256)
+    if (v_dev) V = min(V, *v_dev);
+    if (vh_dev) Vh = min(Vh, *vh_dev);
+    const int C = 4 * C4;
+    for (int i = threadIdx.x; i < 2 * 256; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    const long long total = (long long)V * C4;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (int)(t0 % C4);
+    float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sq = sa;
+    for (long long t = t0; t < total; t += (long long)gridDim.x * blockDim.x) {   // stride % C4 == 0: c stays
+        const int v = (int)(t / C4);
+        const float4* gi_v = gi + (size_t)v * 3 * C4;
+        const float4 a = __ldg(gi_v + c), b = __ldg(gi_v + C4 + c), d = __ldg(gi_v + 2 * C4 + c);
+        float4 hr, hz, hn, hp;
+        if (v < Vh) {
+            const float4* gh_v = gh + (size_t)v * 3 * C4;
+            hr = __ldg(gh_v + c); hz = __ldg(gh_v + C4 + c); hn = __ldg(gh_v + 2 * C4 + c);
+            hp = __ldg(h + t);
+        } else {
+            hr = __ldg(b_hh + c); hz = __ldg(b_hh + C4 + c); hn = __ldg(b_hh + 2 * C4 + c);
+            hp = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float4 o;
+        o.x = gru_gate(a.x, b.x, d.x, hr.x, hz.x, hn.x, hp.x);
+        o.y = gru_gate(a.y, b.y, d.y, hr.y, hz.y, hn.y, hp.y);
+        o.z = gru_gate(a.z, b.z, d.z, hr.z, hz.z, hn.z, hp.z);
+        o.w = gru_gate(a.w, b.w, d.w, hr.w, hz.w, hn.w, hp.w);
+        out[t] = o;
+        sa.x += o.x; sa.y += o.y; sa.z += o.z; sa.w += o.w;
+        sq.x = fmaf(o.x, o.x, sq.x); sq.y = fmaf(o.y, o.y, sq.y); sq.z = fmaf(o.z, o.z, sq.z); sq.w = fmaf(o.w, o.w, sq.w);
+    }
+    atomicAdd(&s_acc[4 * c], sa.x); atomicAdd(&s_acc[4 * c + 1], sa.y); atomicAdd(&s_acc[4 * c + 2], sa.z); atomicAdd(&s_acc[4 * c + 3], sa.w);
+    atomicAdd(&s_acc[256 + 4 * c], sq.x); atomicAdd(&s_acc[256 + 4 * c + 1], sq.y);
+    atomicAdd(&s_acc[256 + 4 * c + 2], sq.z); atomicAdd(&s_acc[256 + 4 * c + 3], sq.w);
+    __syncthreads();
+    const int G = C / cpg;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int k = g * cpg; k < (g + 1) * cpg; ++k) { a += s_acc[k]; b += s_acc[256 + k]; }
+        atomicAdd(sums + 2 * g, (double)a);
+        atomicAdd(sums + 2 * g + 1, (double)b);
+    }
+}
+
 // LSTMCell pointwise with c_prev = 0 (lattice_modules.py:36; gate order i,f,g,o):
 //   c' = s(i)*tanh(g) ; h' = s(o)*tanh(c')
 __global__ void __launch_bounds__(kThreads)
@@ -196,6 +249,28 @@ int ltn_gru_pointwise(const float* gi, const float* gh, const float* h, const fl
     }
     k_gru_pointwise<<<grid_for((long long)V * C, kThreads), kThreads, 0, (cudaStream_t)stream>>>(gi, gh, h, b_hh, V, Vh, v_dev,
                                                                                                   vh_dev, C, out);
+    LTN_CHECK_LAUNCH();
+    return 0;
+}
+
+// ltn_gru_pointwise + the GroupNorm statistics of h' (sums [groups, 2] double, ZEROED by the caller; C % 4 == 0, C <= 256,
+// C % groups == 0): see k_gru_pointwise4_stats
+int ltn_gru_pointwise_stats(const float* gi, const float* gh, const float* h, const float* b_hh, int V, int Vh, const int* v_dev,
+                            const int* vh_dev, int C, float* out, double* sums, int groups, void* stream) {
+    if (V <= 0) return 0;
+    if (C % 4 || C > 256 || groups <= 0 || C % groups || !sums) return -2;
+    const int C4 = C / 4;
+    long long want = ((long long)V * C4 + kThreads - 1) / kThreads;
+    if (want > 148 * 8) want = 148 * 8;
+    // grid * kThreads must be a multiple of C4 (a thread keeps its channel quad): C4 = 2^a * 3^b here, so a multiple of C4 / gcd(C4, kThreads)
+    int g = C4, th = kThreads;
+    while (th) { int r = g % th; g = th; th = r; }
+    const int unit = C4 / g;
+    int grid = (int)((want + unit - 1) / unit) * unit;
+    if (grid < unit) grid = unit;
+    k_gru_pointwise4_stats<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(gi), reinterpret_cast<const float4*>(gh), reinterpret_cast<const float4*>(h),
+        reinterpret_cast<const float4*>(b_hh), V, Vh, v_dev, vh_dev, C4, reinterpret_cast<float4*>(out), sums, C / groups);
     LTN_CHECK_LAUNCH();
     return 0;
 }

@@ -47,11 +47,21 @@ class _HiddenState:
             if getattr(self, "_h_buf", None) is None or self._h_buf.shape != lv.shape:
                 self._h_buf = torch.empty_like(lv)
                 self._h_rows = torch.zeros(1, dtype=torch.int32, device=lv.device)
-            self._h_buf.copy_(lv)
+            if lv.data_ptr() != self._h_buf.data_ptr():   # a module that wrote its output into _out_buffer() skips the copy
+                self._h_buf.copy_(lv)
             self._h_rows.copy_(_lib.rows_tensor(lv.shape[0]))
             self.h_lv = self._h_buf
         else:
             self.h_lv = lv
+
+    def _out_buffer(self, like):
+        """where a module whose inputs are all OTHER tensors (the gates, the projected hidden state) may write its output
+        directly: static-capacity mode -> the persistent hidden-state buffer itself (the frame's later layers read it there,
+        the next frame finds it as h^{t-1}: one [V, C] copy per fusion point and frame less); eager mode -> a fresh tensor"""
+        buf = getattr(self, "_h_buf", None)
+        if _lib.static_mode() and buf is not None and buf.shape == like.shape:
+            return buf
+        return torch.empty_like(like)
 
     def _rows_dev(self):
         if _lib.static_mode() and getattr(self, "_h_rows", None) is not None:
@@ -90,10 +100,18 @@ class GRUModule(torch.nn.Module, _HiddenState):
                 _pad_rows(h, V)
             gi = ops.linear(lv, g.weight_ih, g.bias_ih)
             gh = ops.linear(h, g.weight_hh, g.bias_hh, rows_dev=hrows)
-            new_lv = torch.empty_like(lv)
+            new_lv = self._out_buffer(lv)   # h (the projection of h^{t-1}), gi and gh are separate tensors: writing in place is safe
             p = _lib.ptr
-            _lib.check(_lib.load().ltn_gru_pointwise(p(gi), p(gh), p(h.contiguous()), p(g.bias_hh), V, Vh, _lib.rows_dev(V),
-                                                     self._rows_dev(), C, p(new_lv), _lib.stream()), "ltn_gru_pointwise")
+            if C % 4 == 0 and C <= 256:
+                # the statistics the next layer's GroupNorm needs come out of the same pass (no k_gn_stats read of h')
+                sums = ops.new_sums(C, lv.device)
+                _lib.check(_lib.load().ltn_gru_pointwise_stats(p(gi), p(gh), p(h.contiguous()), p(g.bias_hh), V, Vh, _lib.rows_dev(V),
+                                                               self._rows_dev(), C, p(new_lv), p(sums), sums.shape[0], _lib.stream()),
+                           "ltn_gru_pointwise_stats")
+                new_lv._ltn_gn_sums = (ops._FRAME["id"], sums)
+            else:
+                _lib.check(_lib.load().ltn_gru_pointwise(p(gi), p(gh), p(h.contiguous()), p(g.bias_hh), V, Vh, _lib.rows_dev(V),
+                                                         self._rows_dev(), C, p(new_lv), _lib.stream()), "ltn_gru_pointwise")
         else:
             new_lv = g(lv, _pad_rows(h, V))
         self._store(new_lv)
