@@ -289,6 +289,11 @@ def hbm_kernels(dev, window_np, pk):
         out.append({"kernel": name, "cloud": cloud, "us": 1e3 * ms, "algorithmic_mb": nbytes / 1e6, "achieved": gbs, "unit": "GB/s",
                     "peak": pk["hbm_gbs"], "frac": gbs / pk["hbm_gbs"], "shape": note, "l2": "flushed before every launch"})
 
+    # context for the write-dominated kernels (slice writes N x C, im2row V x 9C): what a pure WRITE stream reaches on this device,
+    # against the copy (read + write) figure the fractions are quoted on
+    out.append({"kernel": "memset 256 MB (write-only reference, not a kernel of this library)", "cloud": "-", "us": 1e3 * flush_ms,
+                "algorithmic_mb": (256 << 20) / 1e6, "achieved": (256 << 20) / (flush_ms * 1e-3) / 1e9, "unit": "GB/s", "peak": pk["hbm_gbs"],
+                "frac": (256 << 20) / (flush_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "shape": "torch zero_ of the L2-flush buffer", "l2": "-"})
     clouds = [("one scan (headline config)", window_np[0][0], window_np[0][1]),
               ("4 scans accumulated", np.concatenate([f[0] for f in window_np], 0), np.concatenate([f[1] for f in window_np], 0))]
     for cloud, pos_np, val_np in clouds:
