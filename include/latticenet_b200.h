@@ -125,6 +125,13 @@ int ltn_gn_apply(const float* x, int V, const int* v_dev, int C, int G, const do
 int ltn_gn_bwd(const float* x, const float* gy, const float* y, int V, int C, int G, const double* sums, const float* gamma,
                float eps, double* chan, float* gx, void* stream);
 
+/* Weight gradient of ConvLatticeModule / CoarsenLattice / FinefyLattice / the 1x1 layers on the tensor cores (train_ln.py:229-231
+ * loss.backward(); SURVEY.md 8b `ltn_conv_bwd_weight`): dW [S*C, F] += sum_v act[nbr[v,s], :]^T dy[v, :], dW zeroed by the caller.
+ * act [Vx, C]: the layer's input activations (after GroupNorm / ReLU); dy [Vq, F]; nbr [Vq, S] or NULL (S = 1, row v).
+ * C % 4 == 0, F % 16 == 0, 16 <= F <= 256.  fp32 parity: 3-pass tf32 hi/lo split, both operands MN-major in shared memory. */
+int ltn_conv_bwd_weight(const float* act, int Vx, const int* nbr, int Vq, int C, int S, const float* dy, int F, float* dW,
+                        void* stream);
+
 /* ConvLatticeModule / CoarsenLattice / FinefyLattice (lattice_modules.py:440,573; models.py:353,398) and
  * the dense layers around them (GnRelu1x1, Conv1x1, nn.Linear, GRU/LSTM gate GEMMs) WITHOUT the [V,9C]
  * im2row buffer:  out[v,f] = sum_{s<S} sum_c act(x[nbr[v,s],c]) * W[s*C+c, f] (+bias[f]) (+res[v,f]),

@@ -99,6 +99,22 @@ class _GatherConv(Function):
         return gv, gw, None, None
 
 
+def conv_bwd_weight(act, gy, nbr):
+    """[S*C, F] weight gradient on the tensor cores (csrc/ltn_conv_bwd_weight.cu): sum_v gathered-act[v]^T gy[v]; None when the
+    shape is not supported (the caller falls back to im2row + fp32 GEMM).  nbr None: S = 1."""
+    C, F = act.shape[1], gy.shape[1]
+    if (C % 4 or F % 16 or F < 16 or F > 256 or gy.shape[0] == 0 or act.shape[0] == 0
+            or os.environ.get("LTN_TRAIN_DW_SIMT", "0") == "1"):
+        return None
+    S = 1 if nbr is None else nbr.shape[1]
+    act, gy = _f32c(act), _f32c(gy)
+    out = torch.zeros(S * C, F, dtype=torch.float32, device=act.device)
+    p = _lib.ptr
+    _lib.check(_lib.load().ltn_conv_bwd_weight(p(act), act.shape[0], p(nbr), gy.shape[0], C, S, p(gy), F, p(out), _lib.stream()),
+               "ltn_conv_bwd_weight")
+    return out
+
+
 class _FusedConv(Function):
     """Training-time form of a whole layer  y = conv(act(x)) (+ bias) (+ res),  act = relu(GroupNorm(x)) or the identity
     (GnReluConv / GnReluCoarsen / GnReluFinefy / GnRelu1x1 / ConvLatticeModule, lattice_modules.py:75-140,436-440,573).
@@ -154,10 +170,11 @@ class _FusedConv(Function):
             _lib.check(lib.ltn_gn_apply(p(x), V, None, C, groups, p(sums), p(gamma), p(beta), float(eps), 1, p(act), _lib.stream()),
                        "ltn_gn_apply")
         if need[1]:
-            if linear:
-                g_w = ops.matmul(gy.t(), act)                      # [F, C]
-            else:
-                g_w = ops.matmul(im2row_raw(act, nbr).t(), gy)     # [9C, F]
+            g_w = conv_bwd_weight(act, gy, None if linear else nbr)
+            if g_w is None:   # shapes the tensor-core kernel does not take
+                g_w = ops.matmul(gy.t(), act) if linear else ops.matmul(im2row_raw(act, nbr).t(), gy)
+            elif linear:
+                g_w = g_w.t().contiguous()                         # nn.Linear layout [F, C]
         if need[0] or (has_gn and (need[4] or need[5])):
             if linear:
                 if ops.conv_tc_supported(F, C, False):

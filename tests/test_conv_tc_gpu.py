@@ -436,3 +436,25 @@ def test_fused_training_layer_gradients_match_unfused(dev, lattice, kind):
     for name, u, v in zip(("x", "weight", "bias", "res", "gamma", "beta"), gf, gp):
         if v is not None:
             assert rel(u, v) < 2e-4, (kind, name, rel(u, v))
+
+
+@pytest.mark.parametrize("C,F,S", [(64, 64, 9), (192, 192, 9), (128, 256, 9), (256, 128, 9), (96, 16, 1), (192, 96, 1), (64, 256, 1), (36, 48, 1)])
+def test_weight_gradient_on_tensor_cores_matches_float64(dev, lattice, C, F, S):
+    """csrc/ltn_conv_bwd_weight.cu (both operands MN-major in shared memory, 3-pass tf32 split, split-K over vertex ranges with
+    fp32 reductions) against the same contraction in float64 over the oracle's neighbour table:
+    dW[s*C + c, f] = sum_v act[nbr[v,s], c] * dy[v, f].  Bound as for the forward kernel: 2e-5 * sum|a||dy| per entry."""
+    from temporal_latticenet_b200 import funcs
+    ls, tab = lattice
+    V = ls.nr_lattice_vertices()
+    g = torch.Generator().manual_seed(C + F + S)
+    act = torch.relu(torch.randn(V, C, generator=g)) * 1.5
+    dy = torch.randn(V, F, generator=g) * 1e-3
+    nbr = ls.neighbours() if S == 9 else None
+    got = funcs.conv_bwd_weight(act.to(dev), dy.to(dev), nbr)
+    assert got is not None and tuple(got.shape) == (S * C, F)
+    got = got.cpu().numpy().astype(np.float64)
+    a64, d64 = act.numpy().astype(np.float64), dy.numpy().astype(np.float64)
+    rows = O.im2row(tab.neighbours(), act.numpy()).astype(np.float64) if S == 9 else a64   # [V, S*C]
+    want = rows.T @ d64
+    bound = np.abs(rows).T @ np.abs(d64) + 1e-30
+    assert float((np.abs(got - want) / bound).max()) < 2e-5, float((np.abs(got - want) / bound).max())
