@@ -402,7 +402,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm", action="store_true", help="skip the splat / slice / im2row / distribute bandwidth table")
     ap.add_argument("--eager", action="store_true", help="eager per-op launches instead of CUDA-graph replay")
-    ap.add_argument("--lanes", type=int, default=4, help="windows per lock-step group (one batched launch per layer serves them)")
+    ap.add_argument("--lanes", type=int, default=8, help="windows per lock-step group (one batched launch per layer serves them; at most 8). "
+                    "When --steps is not a multiple of it, the remainder of every K-step pass runs as ONE smaller lock-step group")
     ap.add_argument("--groups", type=int, default=1, help="lock-step groups in flight per GPU (each with its own graphs and streams)")
     ap.add_argument("--streams", action="store_true", help="round-1 execution: one stream + one graph per window in flight "
                     "(MultiWindowRunner) instead of the lock-step group graph with batched tensor-core launches (LockstepRunner)")
@@ -461,11 +462,20 @@ def main():
             multi = GroupedLockstepRunner(cfg, classes, dev, lanes=lanes, groups=args.groups)
             lanes = lanes * args.groups      # windows in flight per GPU
         else:
+            lanes = min(lanes, 8, max(1, args.steps))
             multi = LockstepRunner(cfg, classes, dev, lanes=lanes)
         multi.prepare(devw[0], seeded_state, devw)
         runner = multi.lanes[0]
         if not multi.supported:
             multi, lanes = None, 1
+    # K steps = full groups of `lanes` windows + ONE smaller lock-step group for the remainder (its own graphs), so that a pass
+    # times exactly K windows whatever K is
+    rem_multi, rem = None, args.steps % lanes
+    if multi is not None and rem and isinstance(multi, LockstepRunner):
+        rem_multi = LockstepRunner(cfg, classes, dev, lanes=rem)
+        rem_multi.prepare(devw[0], seeded_state, devw)
+        if not rem_multi.supported:
+            rem_multi = None
     lockstep = isinstance(multi, (LockstepRunner, GroupedLockstepRunner))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -482,10 +492,13 @@ def main():
             for j in range(n):
                 runner.infer_window_device(devw[(i0 + j) % nw])
         else:
-            multi.infer_windows_device([devw[(i0 + j) % nw] for j in range(n)])
+            (rem_multi if (rem_multi is not None and n == rem) else multi).infer_windows_device([devw[(i0 + j) % nw] for j in range(n)])
 
     for i in range(0, max(args.warmup, 3), lanes):
         run_group(i, lanes)
+    if rem_multi is not None:
+        for _ in range(2):
+            run_group(0, rem)
     torch.cuda.synchronize()
 
     # ---- timed region 1: device-resident inputs; EXACTLY `steps` windows per repeat, repeated until >= min_seconds ------
@@ -518,10 +531,12 @@ def main():
         if lockstep:
             one = multi.groups[0] if hasattr(multi, "groups") else multi
             per = len(one.lanes)
-            launches = sum((n // per) * one.kernels_per_group(frames) + (n % per) * runner.kernels_per_window(frames) for _, _, n in evs)
+            launches = sum((n // per) * one.kernels_per_group(frames) +
+                           ((rem_multi.kernels_per_group(frames) if (rem_multi is not None and n % per == rem) else (n % per) * runner.kernels_per_window(frames))
+                            if n % per else 0) for _, _, n in evs)
         else:
             launches = sum(n for _, _, n in evs) * runner.kernels_per_window(frames)
-        capacity_ok = multi.counts_ok()
+        capacity_ok = multi.counts_ok() and (rem_multi is None or rem_multi.counts_ok())
     group_ms = [a.elapsed_time(b) for a, b, _ in evs]
     ms_rank = sum(group_ms)
     t = torch.tensor([ms_rank], dtype=torch.float64, device=dev)
@@ -541,11 +556,13 @@ def main():
         else:   # one group of windows is always queued behind the one the host is waiting for
             pending = None
             for i in range(0, args.steps, lanes):
-                ticket = multi.submit([host[(i + j) % nw] for j in range(min(lanes, args.steps - i))])
+                n = min(lanes, args.steps - i)
+                who = rem_multi if (rem_multi is not None and n == rem) else multi
+                ticket = (who, who.submit([host[(i + j) % nw] for j in range(n)]))
                 if pending is not None:
-                    labels = multi.collect(pending)[-1]
+                    labels = pending[0].collect(pending[1])[-1]
                 pending = ticket
-            labels = multi.collect(pending)[-1]
+            labels = pending[0].collect(pending[1])[-1]
         torch.cuda.synchronize()
         return labels
     e2e_pass()   # untimed: first use allocates the pinned label / counter buffers of this path
@@ -627,6 +644,8 @@ def main():
         execution = ("%d lock-step group(s) of %d windows per GPU: ONE CUDA graph per frame kind covers a group, every tensor-core layer is one "
                      "persistent batched launch (k_conv_tc_batched), the other kernels run on per-window streams inside the graph"
                      % (max(1, args.groups), lanes // max(1, args.groups)))
+        if rem_multi is not None:
+            execution += "; the %d windows that remain of every %d-step pass run as one smaller lock-step group" % (rem, args.steps)
     elif graph_mode:
         execution = "CUDA-graph replay per frame kind, %d window(s) in flight per GPU (one stream + one graph each)" % lanes
     else:
@@ -649,7 +668,8 @@ def main():
     if ref_driver is not None:
         line["reference_driver"] = ref_driver
     if graph_mode:   # windows that left the graph path: static capacities exceeded / fp16 operand range flag raised
-        line["fallbacks"] = {"eager_reruns": sum(l.fallbacks for l in multi.lanes), "fp16_range": sum(l.range_fallbacks for l in multi.lanes)}
+        all_lanes = list(multi.lanes) + (list(rem_multi.lanes) if rem_multi is not None else [])
+        line["fallbacks"] = {"eager_reruns": sum(l.fallbacks for l in all_lanes), "fp16_range": sum(l.range_fallbacks for l in all_lanes)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
