@@ -398,7 +398,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
-    ap.add_argument("--windows", type=int, default=2, help="distinct synthetic windows cycled through (per rank; seeds 1000 + rank * windows + i)")
+    ap.add_argument("--windows", type=int, default=8, help="distinct synthetic windows cycled through (per rank; seeds 1000 + rank * windows + i): "
+                    "enough of them that a rank's total work is an average over the window sizes, not the size of the two it happened to draw")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm", action="store_true", help="skip the splat / slice / im2row / distribute bandwidth table")
     ap.add_argument("--eager", action="store_true", help="eager per-op launches instead of CUDA-graph replay")
@@ -576,6 +577,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     clk = clocks.stop() if rank == 0 else None
+    fb = torch.zeros(2, dtype=torch.float64, device=dev)   # windows that left the graph path, summed over ALL ranks
+    if multi is not None:
+        all_lanes = list(multi.lanes) + (list(rem_multi.lanes) if rem_multi is not None else [])
+        fb[0], fb[1] = sum(l.fallbacks for l in all_lanes), sum(l.range_fallbacks for l in all_lanes)
+    if world > 1:
+        dist.all_reduce(fb)
     if args.profile_range and rank == 0:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -662,14 +669,13 @@ def main():
                         "execution": execution, "static_capacities": getattr(runner, "caps", None), "capacities_respected": capacity_ok,
                         "timing": {"repeats_of_the_K_step_loop": repeats, "timed_steps_total": timed_steps, "timed_ms_total": ms_max,
                                    "ms_per_group_of_%d" % lanes: stats_ms([m for m, (_, _, n) in zip(group_ms, evs) if n == lanes] or group_ms),
-                                   "per_rank_ms_total": per_rank_ms}},
+                                   "per_rank_ms_total": per_rank_ms, "per_rank_ms_min_max": [min(per_rank_ms), max(per_rank_ms)]}},
             "e2e": {"value": total_scans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "hbm_kernels": hbm, "cpu_baseline": cpu, "parity": parity}
     if ref_driver is not None:
         line["reference_driver"] = ref_driver
     if graph_mode:   # windows that left the graph path: static capacities exceeded / fp16 operand range flag raised
-        all_lanes = list(multi.lanes) + (list(rem_multi.lanes) if rem_multi is not None else [])
-        line["fallbacks"] = {"eager_reruns": sum(l.fallbacks for l in all_lanes), "fp16_range": sum(l.range_fallbacks for l in all_lanes)}
+        line["fallbacks"] = {"eager_reruns": int(fb[0].item()), "fp16_range": int(fb[1].item()), "scope": "all ranks"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
