@@ -30,9 +30,13 @@ struct HeadIn {
     const float* beta;   // [9]
 };
 
-// h = W1 (g - (gamma * max_r g + beta)) of one point; sW1 [36][36] in shared memory (uniform reads: broadcasts)
+// h = W1 (g - (gamma * max_r g + beta)) of one point; sW1 [36][36] in shared memory (uniform reads: broadcasts).  Every h[j] is
+// handed to `fold(j, h_j)` as soon as it exists: neither kernel keeps the 36 values (the statistics kernel adds them to its
+// group sums, the apply kernel normalises them and adds them to the four delta weights), which is the difference between
+// 168 and ~100 registers per thread, i.e. between 3 and 5 blocks per SM for a kernel that waits on shared-memory broadcasts.
+template <class Fold>
 __device__ __forceinline__ void head_h(const HeadIn& in, int V, long long p, const float* sW1, const float* sGB, int4& id4, float4& w4,
-                                       float* h) {
+                                       Fold&& fold) {
     id4 = __ldg(reinterpret_cast<const int4*>(in.idx) + p);
     w4 = __ldg(reinterpret_cast<const float4*>(in.w) + p);
     const int ids[4] = {id4.x, id4.y, id4.z, id4.w};
@@ -69,7 +73,7 @@ __device__ __forceinline__ void head_h(const HeadIn& in, int V, long long p, con
             acc = fmaf(ww.x, g[4 * q], acc); acc = fmaf(ww.y, g[4 * q + 1], acc);
             acc = fmaf(ww.z, g[4 * q + 2], acc); acc = fmaf(ww.w, g[4 * q + 3], acc);
         }
-        h[j] = acc;
+        fold(j, acc);
     }
 }
 
@@ -88,14 +92,11 @@ k_head_stats(HeadIn in, int V, const int* __restrict__ v_dev, int N, const int* 
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) { s[g] = 0.f; q[g] = 0.f; }
     for (long long p = (long long)blockIdx.x * kHeadThreads + threadIdx.x; p < N; p += (long long)gridDim.x * kHeadThreads) {
-        float h[kG];
         int4 id4; float4 w4;
-        head_h(in, V, p, sW1, sGB, id4, w4, h);
-#pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
-            s[g] += h[2 * g] + h[2 * g + 1];
-            q[g] = fmaf(h[2 * g], h[2 * g], fmaf(h[2 * g + 1], h[2 * g + 1], q[g]));
-        }
+        head_h(in, V, p, sW1, sGB, id4, w4, [&](const int j, const float hj) {
+            s[j >> 1] += hj;                          // j is a compile-time constant after unrolling: plain register adds
+            q[j >> 1] = fmaf(hj, hj, q[j >> 1]);
+        });
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -148,17 +149,14 @@ k_head_apply(HeadIn in, int V, const int* __restrict__ v_dev, int N, const int* 
     for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         const long long p0 = blk * kHeadThreads, p = p0 + threadIdx.x;
         if (p < N) {
-            float h[kG];
             int4 id4; float4 w4;
-            head_h(in, V, p, sW1, sGB, id4, w4, h);
             float dw[4] = {sB2[0], sB2[1], sB2[2], sB2[3]};
-#pragma unroll
-            for (int j = 0; j < kG; ++j) {
-                float y = fmaf(h[j], sAff[j], sAff[kG + j]);
+            head_h(in, V, p, sW1, sGB, id4, w4, [&](const int j, const float hj) {
+                float y = fmaf(hj, sAff[j], sAff[kG + j]);
                 y = y > 0.f ? y : (y != y ? y : 0.f);   // ReLU that keeps NaN
 #pragma unroll
                 for (int r = 0; r < 4; ++r) dw[r] = fmaf(sW2[r * kG + j], y, dw[r]);
-            }
+            });
             const int ids[4] = {id4.x, id4.y, id4.z, id4.w};
             const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
             float acc[32];
