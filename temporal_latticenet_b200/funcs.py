@@ -177,7 +177,7 @@ class _FusedConv(Function):
                 g_w = g_w.t().contiguous()                         # nn.Linear layout [F, C]
         if need[0] or (has_gn and (need[4] or need[5])):
             if linear:
-                if ops.conv_tc_supported(F, C, False):
+                if ops.conv_tc_supported(F, C, False) and os.environ.get("LTN_TRAIN_LIN_DACT_SIMT", "0") != "1":
                     wt_t = ops._cached_split(weight, (id(weight), "linear_t"),
                                              lambda: ops.SplitWeight(weight.detach().t().contiguous().float(), True))
                     d_act = ops.conv_tc(gy, None, wt_t, operands="tf32")
