@@ -214,7 +214,8 @@ def fused_conv_train(x, weight, bias, res, norm, nbr, nbr_t_fn, linear=False):
             sums = s[1]
     nbr_t = None
     if not linear:
-        nbr_t = nbr_t_fn() if x.requires_grad else nbr
+        # the opposite-direction table is what d act runs over: needed for d x and, through the GroupNorm backward, for d gamma / d beta
+        nbr_t = nbr_t_fn() if (x.requires_grad or norm is not None) else nbr
     out, out_sums = _FusedConv.apply(x, weight, bias, res, gamma, beta, nbr, nbr_t, (linear, groups, eps, sums))
     out._ltn_gn_sums = (ops._FRAME["id"], out_sums)
     return out
