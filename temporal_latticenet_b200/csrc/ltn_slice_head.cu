@@ -15,6 +15,7 @@
 // over all points, so there are two passes: k_head_stats computes h and only its group sums, k_head_apply RECOMPUTES h
 // (36 x 36 multiply-adds per point from 4 x 32 bytes of input: cheaper than writing and re-reading [N, 36]) and finishes.
 #include "ltn_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -224,7 +225,12 @@ int ltn_slice_head(const float* bott, int V, const int* v_dev, const float* scor
     HeadIn in{bott, idx, w, gamma, beta};
     long long blocks = ((long long)N + kHeadThreads - 1) / kHeadThreads;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_head_stats<<<(int)blocks, kHeadThreads, 0, st>>>(in, V, v_dev, N, n_dev, W1, sums);
+    // the statistics kernel ends every block with 36 double atomics on the same 36 addresses: fewer, longer blocks
+    // (grid-stride loop) trade latency hiding for fewer serialised reductions; LTN_HEAD_STATS_BPS = blocks per SM.  Measured on one
+    // scan (tools/bench_slice_head.py, both kernels): 1 -> 57.6, 2 -> 55.6, 3 -> 55.5, 4 -> 57.7, 8 -> 60.5 us per call
+    static const int stats_bps = []() { const char* e = getenv("LTN_HEAD_STATS_BPS"); return e && atoi(e) >= 1 ? atoi(e) : 3; }();
+    long long sblocks = blocks < 148LL * stats_bps ? blocks : 148LL * stats_bps;
+    k_head_stats<<<(int)sblocks, kHeadThreads, 0, st>>>(in, V, v_dev, N, n_dev, W1, sums);
     LTN_CHECK_LAUNCH();
     k_head_apply<<<(int)blocks, kHeadThreads, 0, st>>>(in, V, v_dev, N, n_dev, W1, sums, gn_w, gn_b, gn_eps, W2, b2, no_deform, scores,
                                                        ld_scores, cls_bias, K, logits, logsm);
